@@ -1,0 +1,231 @@
+"""ctypes front-end of oracle/liboracle.so (spring_oracle.c) and of oracle/_ref/spring_ref.
+
+TEST INFRASTRUCTURE ONLY: importable from tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs; never from spring_b200.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from dataclasses import dataclass
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "liboracle.so")
+REF_BIN = os.path.join(HERE, "_ref", "spring_ref")
+REFERENCE_SRC = "/root/reference"
+
+
+def build(force: bool = False) -> None:
+    """Compile the restatement; and, where the reference sources exist (this container, not the
+    GPU box), the reference itself into oracle/_ref/."""
+    if force or not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < os.path.getmtime(os.path.join(HERE, "spring_oracle.c")):
+        subprocess.check_call(["make", "-s", "-C", HERE, "oracle"])
+    if os.path.isdir(os.path.join(REFERENCE_SRC, "src")) and (force or not os.path.exists(REF_BIN)):
+        subprocess.check_call(["make", "-s", "-j8", "-C", HERE, "ref"])
+
+
+class _ByteVec(C.Structure):
+    _fields_ = [("p", C.POINTER(C.c_uint8)), ("n", C.c_size_t), ("cap", C.c_size_t)]
+
+    def to_numpy(self, dtype=np.uint8) -> np.ndarray:
+        if self.n == 0:
+            return np.zeros(0, dtype=dtype)
+        return np.ctypeslib.as_array(self.p, shape=(self.n,)).copy().view(dtype)
+
+
+class _Counters(C.Structure):
+    _fields_ = [("probes", C.c_uint64), ("probe_hits", C.c_uint64), ("compares", C.c_uint64),
+                ("passes", C.c_uint64), ("rounds", C.c_uint64), ("lost_proposals", C.c_uint64),
+                ("unmatched", C.c_uint32)]
+
+
+class _ReorderOut(C.Structure):
+    _fields_ = [("order", C.POINTER(C.c_uint32)), ("flag", C.POINTER(C.c_uint8)),
+                ("pos", C.POINTER(C.c_int64)), ("rc", C.POINTER(C.c_uint8)), ("n", C.c_uint64),
+                ("s_order", C.POINTER(C.c_uint32)), ("n_s", C.c_uint64), ("ctr", _Counters)]
+
+
+class _EncodeOut(C.Structure):
+    _fields_ = [("seq", _ByteVec), ("pos", _ByteVec), ("noise", _ByteVec), ("noisepos", _ByteVec),
+                ("rc", _ByteVec), ("order", _ByteVec), ("lengths", _ByteVec), ("unaligned", _ByteVec),
+                ("unaligned_len", C.c_uint64), ("num_aligned", C.c_uint64),
+                ("matched_s", C.c_uint32), ("matched_N", C.c_uint32),
+                ("enc_probes", C.c_uint64), ("enc_compares", C.c_uint64)]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(LIB_PATH)
+        assert _lib.orc_sizeof_reorder_out() == C.sizeof(_ReorderOut)
+        assert _lib.orc_sizeof_encode_out() == C.sizeof(_EncodeOut)
+        _lib.orc_reorder_dict.restype = C.c_uint32
+        _lib.orc_pack_seq.restype = C.c_uint64
+    return _lib
+
+
+def _p(a: np.ndarray, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+def _arr(ptr, n, dtype):
+    if n == 0:
+        return np.zeros(0, dtype=dtype)
+    return np.ctypeslib.as_array(ptr, shape=(n,)).copy()
+
+
+@dataclass
+class ReorderResult:
+    order: np.ndarray      # uint32 clean indices, stream order
+    flag: np.ndarray       # uint8 0 = first read of a contig, 1 = matched
+    pos: np.ndarray        # int64
+    rc: np.ndarray         # uint8 'd' / 'r'
+    s_order: np.ndarray    # uint32 singletons
+    counters: dict
+
+
+def reorder(packed: np.ndarray, lengths: np.ndarray, max_readlen: int, num_chains: int = 1) -> ReorderResult:
+    packed = np.ascontiguousarray(packed, dtype=np.uint64)
+    lengths = np.ascontiguousarray(lengths, dtype=np.uint16)
+    out = _ReorderOut()
+    rc = lib().orc_reorder(_p(packed, C.c_uint64), _p(lengths, C.c_uint16), C.c_uint32(len(lengths)),
+                           C.c_int(max_readlen), C.c_int(num_chains), C.byref(out))
+    if rc != 0:
+        raise RuntimeError(f"orc_reorder failed: {rc}")
+    res = ReorderResult(_arr(out.order, out.n, np.uint32), _arr(out.flag, out.n, np.uint8),
+                        _arr(out.pos, out.n, np.int64), _arr(out.rc, out.n, np.uint8),
+                        _arr(out.s_order, out.n_s, np.uint32),
+                        {f: getattr(out.ctr, f) for f, _ in _Counters._fields_})
+    lib().orc_reorder_free(C.byref(out))
+    return res
+
+
+@dataclass
+class EncodeResult:
+    """The encoder's output streams (SURVEY 8b "data contract out"), un-sharded."""
+    seq: np.ndarray         # uint8 ASCII consensus
+    pos: np.ndarray         # uint64
+    noise: np.ndarray       # uint8
+    noisepos: np.ndarray    # uint16
+    rc: np.ndarray          # uint8
+    order: np.ndarray       # uint32 (aligned then unaligned)
+    lengths: np.ndarray     # uint16 (same order)
+    unaligned: np.ndarray   # uint8 4-bit records
+    unaligned_len: int
+    num_aligned: int
+    matched_s: int
+    matched_N: int
+    enc_probes: int = 0
+    enc_compares: int = 0
+
+    def packed_seq(self) -> tuple[bytes, bytes]:
+        """(2-bit packed bytes, ASCII tail) as pack_compress_seq writes them (encoder.cpp:126-147)."""
+        n = len(self.seq)
+        buf = np.zeros(n // 4, dtype=np.uint8)
+        seq = np.ascontiguousarray(self.seq)
+        lib().orc_pack_seq(_p(seq, C.c_uint8), C.c_uint64(n), _p(buf, C.c_uint8))
+        return buf.tobytes(), seq[n - n % 4:].tobytes() if n % 4 else b""
+
+
+def encode(packed, lengths, max_readlen, ro: ReorderResult, n_records: bytes, order_n: np.ndarray,
+           num_total: int) -> EncodeResult:
+    packed = np.ascontiguousarray(packed, dtype=np.uint64)
+    lengths = np.ascontiguousarray(lengths, dtype=np.uint16)
+    nrec = np.frombuffer(n_records, dtype=np.uint8).copy() if n_records else np.zeros(1, np.uint8)
+    order_n = np.ascontiguousarray(order_n, dtype=np.uint32)
+    onp = order_n if len(order_n) else np.zeros(1, np.uint32)
+    out = _EncodeOut()
+    so = ro.s_order if len(ro.s_order) else np.zeros(1, np.uint32)
+    st = [a if len(a) else np.zeros(1, a.dtype) for a in (ro.order, ro.flag, ro.pos, ro.rc)]
+    rc = lib().orc_encode(_p(packed, C.c_uint64), _p(lengths, C.c_uint16), C.c_uint32(len(lengths)), C.c_int(max_readlen),
+                          _p(st[0], C.c_uint32), _p(st[1], C.c_uint8), _p(st[2], C.c_int64), _p(st[3], C.c_uint8),
+                          C.c_uint64(len(ro.order)), _p(so, C.c_uint32), C.c_uint64(len(ro.s_order)),
+                          _p(nrec, C.c_uint8), C.c_uint64(len(n_records)), _p(onp, C.c_uint32), C.c_uint32(len(order_n)),
+                          C.c_uint32(num_total), C.byref(out))
+    if rc != 0:
+        raise RuntimeError(f"orc_encode failed: {rc}")
+    res = EncodeResult(out.seq.to_numpy(), out.pos.to_numpy(np.uint64), out.noise.to_numpy(), out.noisepos.to_numpy(np.uint16),
+                       out.rc.to_numpy(), out.order.to_numpy(np.uint32), out.lengths.to_numpy(np.uint16),
+                       out.unaligned.to_numpy(), out.unaligned_len, out.num_aligned, out.matched_s, out.matched_N,
+                       out.enc_probes, out.enc_compares)
+    lib().orc_encode_free(C.byref(out))
+    return res
+
+
+def reorder_encode(packed, lengths, max_readlen, n_records=b"", order_n=None, num_total=None, num_chains=1):
+    order_n = np.zeros(0, np.uint32) if order_n is None else order_n
+    ro = reorder(packed, lengths, max_readlen, num_chains)
+    if num_total is None:
+        num_total = len(lengths) + len(order_n)
+    return ro, encode(packed, lengths, max_readlen, ro, n_records, order_n, num_total)
+
+
+def decode(er, stride: int | None = None) -> list[bytes]:
+    """Rebuild every read of the stream (aligned then unaligned), decompress.cpp:263-283."""
+    n = len(er.lengths)
+    stride = stride or (int(er.lengths.max()) if n else 1) or 1
+    out = np.zeros((max(n, 1), stride), dtype=np.uint8)
+    a = [np.ascontiguousarray(x) if len(x) else np.zeros(1, x.dtype) for x in
+         (er.seq, er.pos, er.noise, er.noisepos, er.rc, er.lengths, er.unaligned)]
+    rc = lib().orc_decode(_p(a[0], C.c_uint8), C.c_uint64(len(er.seq)), _p(a[1], C.c_uint64), _p(a[2], C.c_uint8),
+                          C.c_uint64(len(er.noise)), _p(a[3], C.c_uint16), C.c_uint64(len(er.noisepos)),
+                          _p(a[4], C.c_uint8), C.c_uint64(er.num_aligned), _p(a[5], C.c_uint16), C.c_uint64(n),
+                          _p(a[6], C.c_uint8), C.c_uint64(len(er.unaligned)), _p(out, C.c_uint8), C.c_int(stride))
+    if rc != 0:
+        raise RuntimeError(f"orc_decode failed: {rc}")
+    return [out[i, : er.lengths[i]].tobytes() for i in range(n)]
+
+
+def reorder_dict(packed, lengths, max_readlen, which):
+    packed = np.ascontiguousarray(packed, dtype=np.uint64)
+    lengths = np.ascontiguousarray(lengths, dtype=np.uint16)
+    n = len(lengths)
+    keys = np.zeros(max(n, 1), np.uint64); bs = np.zeros(n + 1, np.uint32); rid = np.zeros(max(n, 1), np.uint32)
+    dn = C.c_uint32(0)
+    nk = lib().orc_reorder_dict(_p(packed, C.c_uint64), _p(lengths, C.c_uint16), C.c_uint32(n), C.c_int(max_readlen),
+                                C.c_int(which), _p(keys, C.c_uint64), _p(bs, C.c_uint32), _p(rid, C.c_uint32), C.byref(dn))
+    return keys[:nk].copy(), bs[: nk + 1].copy(), rid[: dn.value].copy()
+
+
+# ---------------------------------------------------------------------------------------------
+# the real reference (oracle/_ref/spring_ref), when it was built
+# ---------------------------------------------------------------------------------------------
+def have_reference() -> bool:
+    return os.path.exists(REF_BIN)
+
+
+def run_reference_hotpath(temp_dir: str, num_thr: int = 1, unbsc: bool = True) -> tuple[float, float, str]:
+    """call_reorder + call_encoder of the unmodified reference on a prepared temp_dir.
+    returns (reorder seconds, encode seconds, stdout)."""
+    cmd = [REF_BIN, "--hotpath", "--temp", temp_dir, "-t", str(num_thr)] + (["--unbsc"] if unbsc else [])
+    r = subprocess.run(cmd, capture_output=True, text=True, cwd=temp_dir)
+    if r.returncode != 0:
+        raise RuntimeError(f"spring_ref --hotpath failed:\n{r.stdout}\n{r.stderr}")
+    line = [l for l in r.stdout.splitlines() if l.startswith("HOTPATH_SECONDS")][0].split()
+    return float(line[1]), float(line[2]), r.stdout
+
+
+def load_reference_streams(temp_dir: str, num_thr: int) -> EncodeResult:
+    """Read what the reference's encoder left in temp_dir (after --unbsc) into an EncodeResult."""
+    def rd(name, dtype=np.uint8):
+        p = os.path.join(temp_dir, name)
+        return np.fromfile(p, dtype=dtype) if os.path.getsize(p) else np.zeros(0, dtype)
+    seq_parts = []
+    code = np.frombuffer(b"ACGT", dtype=np.uint8)
+    for t in range(num_thr):
+        b = rd(f"read_seq.bin.{t}")
+        chars = code[np.stack([(b >> (2 * j)) & 3 for j in range(4)], axis=1).reshape(-1)] if len(b) else np.zeros(0, np.uint8)
+        seq_parts += [chars, rd(f"read_seq.bin.{t}.tail")]
+    seq = np.concatenate(seq_parts) if seq_parts else np.zeros(0, np.uint8)
+    rc = rd("read_rev.txt")
+    ul = int(np.fromfile(os.path.join(temp_dir, "read_unaligned.txt.count"), dtype=np.uint64)[0])
+    return EncodeResult(seq, rd("read_pos.bin", np.uint64), rd("read_noise.txt"), rd("read_noisepos.bin", np.uint16), rc,
+                        rd("read_order.bin", np.uint32), rd("read_lengths.bin", np.uint16), rd("read_unaligned.txt"),
+                        ul, len(rc), -1, -1)

@@ -1,0 +1,168 @@
+/*
+ * spring_b200.h -- C ABI of libspring_b200.so: SPRING's short-read reorder + encode hot path
+ * on NVIDIA B200 (sm_100a).
+ *
+ * The reference (shubhamchandak94/Spring) has no plugin/FFI layer; the seam this library fills
+ * is the pair of C++ calls
+ *     void call_reorder(const std::string &temp_dir, compression_params &cp);
+ *     void call_encoder(const std::string &temp_dir, compression_params &cp);
+ * (src/call_template_functions.h:9-11, invoked at src/spring.cpp:153 and :166).  Every entry
+ * point below cites the reference code it replaces.  Plain pointers and sizes only; no
+ * exceptions cross the boundary: every function returns 0 on success or a negative
+ * SPRING_B200_E* code, with a message retrievable through spring_b200_last_error().
+ *
+ * There is NO CPU fallback: without a CUDA device every compute entry point fails with
+ * SPRING_B200_ENODEV.
+ */
+#ifndef SPRING_B200_H_
+#define SPRING_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPRING_B200_OK 0
+#define SPRING_B200_EINVAL (-1)  /* bad argument (e.g. max_readlen > 511: "Wrong bitset size.", call_template_functions.cpp:61) */
+#define SPRING_B200_ENODEV (-2)  /* no usable CUDA device */
+#define SPRING_B200_ECUDA (-3)   /* CUDA runtime error */
+#define SPRING_B200_EIO (-4)     /* file-level entry point: cannot read/write temp_dir */
+#define SPRING_B200_ELIMIT (-5)  /* internal limit hit (watchdog, contig > 10 M reads, ...) */
+
+/* Mirror of spring::compression_params (src/util.h:30-51), the raw 64-byte struct the host
+ * writes to cp.bin (src/spring.cpp:218-221).  Offsets checked with static_assert in the library. */
+typedef struct spring_b200_cp {
+  uint8_t paired_end, preserve_order, preserve_quality, preserve_id;
+  uint8_t long_flag, qvz_flag, ill_bin_flag, bin_thr_flag;
+  double qvz_ratio;
+  uint32_t bin_thr_thr, bin_thr_high, bin_thr_low;
+  uint32_t num_reads;
+  uint32_t num_reads_clean[2];
+  uint32_t max_readlen;
+  uint8_t paired_id_code;
+  uint8_t paired_id_match;
+  int32_t num_reads_per_block;
+  int32_t num_reads_per_block_long;
+  int32_t num_thr;
+} spring_b200_cp;
+
+typedef struct spring_b200_ctx spring_b200_ctx; /* one per GPU; not thread-safe; owns all device + pinned memory */
+
+/* The hot path's inputs, i.e. what preprocess leaves in temp_dir (src/preprocess.cpp:296-403),
+ * already in the layout the reference's readDnaFile builds in RAM (src/reorder.h:222-244):
+ * one bitset of W = (2*max_readlen-1)/64+1 uint64 words per clean read (2 bits/base, A0 G1 C2 T3,
+ * base j at bits 2j..2j+1, zero beyond the read's length) + uint16 lengths. */
+typedef struct spring_b200_input {
+  const uint64_t *reads;      /* [num_clean * W]; host or device pointer, see each entry point */
+  const uint16_t *lengths;    /* [num_clean] */
+  uint32_t num_clean;         /* cp.num_reads_clean[0] + cp.num_reads_clean[1] */
+  uint32_t max_readlen;       /* cp.max_readlen, 1..511 */
+  const uint8_t *n_records;   /* HOST: contents of input_N.dna, 4-bit records (src/util.cpp:322-348) */
+  uint64_t n_record_bytes;
+  const uint32_t *order_n;    /* HOST: contents of read_order_N.bin (src/preprocess.cpp:300-301,373-378) */
+  uint32_t num_n;             /* cp.num_reads - num_clean */
+  uint32_t num_reads;         /* cp.num_reads */
+} spring_b200_input;
+
+/* The encoder's output streams (what src/encoder.h:386-487 leaves for reorder_compress_streams,
+ * src/reorder_compress_streams.cpp:91-172), as flat arrays.  Pointers are owned by the context
+ * and stay valid until the next call on it. */
+typedef struct spring_b200_streams {
+  const uint8_t *seq_packed;   /* consensus, 2 bits/base A0 C1 G2 T3, 4 bases/byte LSB first (src/encoder.cpp:126-141) */
+  uint64_t seq_len;            /* bases; seq_packed holds ceil(seq_len/4) bytes (the reference keeps the
+                                  last seq_len%4 bases as ASCII in .tail; see spring_b200_write_streams) */
+  const uint64_t *pos;         /* read_pos.bin: absolute position per aligned read (src/encoder.h:473-487) */
+  const uint8_t *noise;        /* read_noise.txt: substitution codes + '\n' per aligned read (src/encoder.cpp:88-97) */
+  uint64_t noise_bytes;
+  const uint16_t *noisepos;    /* read_noisepos.bin: delta position per noise symbol */
+  uint64_t num_noise;
+  const uint8_t *rev;          /* read_rev.txt: 'd' / 'r' per aligned read */
+  const uint32_t *order;       /* read_order.bin: original index per read; aligned first, then unaligned */
+  const uint16_t *lengths;     /* read_lengths.bin, same order */
+  const uint8_t *unaligned;    /* read_unaligned.txt: 4-bit records (src/encoder.h:438-447) */
+  uint64_t unaligned_bytes;
+  uint64_t unaligned_len;      /* read_unaligned.txt.count: total bases */
+  uint64_t num_aligned;
+  uint64_t num_reads;
+  uint32_t singletons_aligned; /* "N singleton reads were aligned" (src/encoder.h:490-492) */
+  uint32_t n_reads_aligned;
+} spring_b200_streams;
+
+/* Output of the reorder stage alone (what the reference's reorder threads write to
+ * read_order.bin.<t>, tempflag.txt.<t>, temppos.txt.<t>, read_rev.txt.<t> and
+ * read_order.bin.singleton, src/reorder.h:498-512, :594-609), chain after chain. */
+typedef struct spring_b200_reorder_out {
+  const uint32_t *order;   /* clean-read index */
+  const uint8_t *flag;     /* 0 = first read of a contig, 1 = matched */
+  const int64_t *pos;
+  const uint8_t *rev;      /* 'd' / 'r' */
+  uint64_t num;
+  const uint32_t *singleton_order;
+  uint64_t num_singletons;
+} spring_b200_reorder_out;
+
+typedef struct spring_b200_stats {
+  uint32_t num_chains;       /* chains actually run (reference: cp.num_thr greedy threads) */
+  uint32_t unmatched;        /* "Reordering done, X were unmatched" (src/reorder.h:633-635) */
+  uint64_t rounds;           /* scheduler rounds of the chain kernel */
+  uint64_t lost_proposals;
+  uint64_t probes_issued;    /* dictionary lookups the GPU issued (speculative across shifts) */
+  uint64_t probes_seq;       /* lookups a sequential search_match would have issued (src/reorder.h:262-273) */
+  uint64_t compares;         /* Hamming evaluations counted as the sequential scan would */
+  uint64_t gpu_launches;     /* kernels launched by the last call (ours + CUB) */
+  float ms_h2d, ms_dict, ms_chains, ms_scatter, ms_encode, ms_d2h, ms_total;
+} spring_b200_stats;
+
+/* ---- context ---------------------------------------------------------------------------- */
+const char *spring_b200_version(void);
+int spring_b200_device_count(void);
+/* device: CUDA ordinal.  stream: a cudaStream_t to run on (e.g. torch's current stream) or NULL
+ * for a stream owned by the context. */
+int spring_b200_create(int device, void *stream, spring_b200_ctx **out);
+void spring_b200_destroy(spring_b200_ctx *ctx);
+const char *spring_b200_last_error(const spring_b200_ctx *ctx); /* ctx may be NULL: last create() error */
+int spring_b200_get_stats(const spring_b200_ctx *ctx, spring_b200_stats *out);
+
+/* ---- the hot path ------------------------------------------------------------------------ */
+/* reorder_main + encoder_main (src/reorder.h:732-786, src/encoder.h:572-633) on HOST buffers:
+ * host->device copies, all kernels, device->host copies of the streams.  num_chains = 0 picks
+ * the largest co-resident chain count; 1 reproduces the reference's single-thread result. */
+int spring_b200_reorder_encode(spring_b200_ctx *ctx, const spring_b200_input *in, uint32_t num_chains,
+                               spring_b200_streams *out);
+/* Same with in->reads / in->lengths already resident in HBM (device pointers); the streams are
+ * left on the device (out pointers are device pointers); scalar fields are filled. */
+int spring_b200_reorder_encode_device(spring_b200_ctx *ctx, const spring_b200_input *in, uint32_t num_chains,
+                                      spring_b200_streams *out);
+/* Copy the streams of the last *_device call to pinned host memory. */
+int spring_b200_fetch_streams(spring_b200_ctx *ctx, spring_b200_streams *out);
+
+/* ---- stages, for parity tests ------------------------------------------------------------- */
+/* constructdictionary (src/bitset_util.h:74-221) for reorder dictionary `which` (0/1): sorted
+ * unique keys, CSR bin starts, read ids ascending per bin.  Host inputs, host outputs sized
+ * num_clean, num_clean+1, num_clean. */
+int spring_b200_build_dictionary(spring_b200_ctx *ctx, const spring_b200_input *in, int which, uint64_t *keys,
+                                 uint32_t *bin_start, uint32_t *read_id, uint32_t *num_keys, uint32_t *dict_numreads);
+/* reorder<>() alone (src/reorder.h:320-641), host inputs, host outputs owned by the context. */
+int spring_b200_reorder(spring_b200_ctx *ctx, const spring_b200_input *in, uint32_t num_chains,
+                        spring_b200_reorder_out *out);
+
+/* ---- file-level drop-in -------------------------------------------------------------------- */
+/* Replaces call_reorder + call_encoder (src/call_template_functions.cpp:9-143) on a temp_dir:
+ * reads input_clean_1.dna [input_clean_2.dna], input_N.dna, read_order_N.bin, deletes them
+ * (as src/reorder.h:232,241, src/encoder.h:606, src/encoder.cpp:218 do) and writes
+ * read_seq.bin.<t> (2-bit packed, NOT yet BSC-compressed) + read_seq.bin.<t>.tail for
+ * t < cp->num_thr, read_pos.bin, read_noise.txt, read_noisepos.bin, read_rev.txt,
+ * read_order.bin, read_lengths.bin, read_unaligned.txt, read_unaligned.txt.count.
+ * The host then runs bsc::BSC_compress on each read_seq.bin.<t> exactly as
+ * pack_compress_seq does (src/encoder.cpp:148-153); see INTEGRATION.md. */
+int spring_b200_reorder_encode_files(spring_b200_ctx *ctx, const char *temp_dir, const spring_b200_cp *cp,
+                                     uint32_t num_chains);
+/* Write a host-side spring_b200_streams into temp_dir in that layout (num_shards = cp.num_thr). */
+int spring_b200_write_streams(spring_b200_ctx *ctx, const char *temp_dir, const spring_b200_streams *s, int num_shards);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPRING_B200_H_ */

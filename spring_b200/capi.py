@@ -1,0 +1,241 @@
+"""ctypes binding of libspring_b200.so (include/spring_b200.h).
+
+The CUDA library is the only implementation: if it is missing, or no GPU is visible, every
+compute call raises -- there is no CPU fallback on the product path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libspring_b200.so")
+
+EXPORTS = [
+    "spring_b200_version", "spring_b200_device_count", "spring_b200_create", "spring_b200_destroy",
+    "spring_b200_last_error", "spring_b200_get_stats", "spring_b200_reorder_encode",
+    "spring_b200_reorder_encode_device", "spring_b200_fetch_streams", "spring_b200_build_dictionary",
+    "spring_b200_reorder", "spring_b200_reorder_encode_files", "spring_b200_write_streams",
+]
+
+
+class SpringB200Error(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"spring_b200 error {code}: {msg}")
+        self.code = code
+
+
+class CP(C.Structure):
+    """spring_b200_cp == spring::compression_params (src/util.h:30-51)."""
+    _fields_ = [("paired_end", C.c_uint8), ("preserve_order", C.c_uint8), ("preserve_quality", C.c_uint8),
+                ("preserve_id", C.c_uint8), ("long_flag", C.c_uint8), ("qvz_flag", C.c_uint8),
+                ("ill_bin_flag", C.c_uint8), ("bin_thr_flag", C.c_uint8), ("qvz_ratio", C.c_double),
+                ("bin_thr_thr", C.c_uint32), ("bin_thr_high", C.c_uint32), ("bin_thr_low", C.c_uint32),
+                ("num_reads", C.c_uint32), ("num_reads_clean", C.c_uint32 * 2), ("max_readlen", C.c_uint32),
+                ("paired_id_code", C.c_uint8), ("paired_id_match", C.c_uint8),
+                ("num_reads_per_block", C.c_int32), ("num_reads_per_block_long", C.c_int32), ("num_thr", C.c_int32)]
+
+
+class Input(C.Structure):
+    _fields_ = [("reads", C.c_void_p), ("lengths", C.c_void_p), ("num_clean", C.c_uint32), ("max_readlen", C.c_uint32),
+                ("n_records", C.c_void_p), ("n_record_bytes", C.c_uint64), ("order_n", C.c_void_p),
+                ("num_n", C.c_uint32), ("num_reads", C.c_uint32)]
+
+
+class Streams(C.Structure):
+    _fields_ = [("seq_packed", C.c_void_p), ("seq_len", C.c_uint64), ("pos", C.c_void_p), ("noise", C.c_void_p),
+                ("noise_bytes", C.c_uint64), ("noisepos", C.c_void_p), ("num_noise", C.c_uint64), ("rev", C.c_void_p),
+                ("order", C.c_void_p), ("lengths", C.c_void_p), ("unaligned", C.c_void_p),
+                ("unaligned_bytes", C.c_uint64), ("unaligned_len", C.c_uint64), ("num_aligned", C.c_uint64),
+                ("num_reads", C.c_uint64), ("singletons_aligned", C.c_uint32), ("n_reads_aligned", C.c_uint32)]
+
+
+class ReorderOut(C.Structure):
+    _fields_ = [("order", C.c_void_p), ("flag", C.c_void_p), ("pos", C.c_void_p), ("rev", C.c_void_p), ("num", C.c_uint64),
+                ("singleton_order", C.c_void_p), ("num_singletons", C.c_uint64)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("num_chains", C.c_uint32), ("unmatched", C.c_uint32), ("rounds", C.c_uint64),
+                ("lost_proposals", C.c_uint64), ("probes_issued", C.c_uint64), ("probes_seq", C.c_uint64),
+                ("compares", C.c_uint64), ("gpu_launches", C.c_uint64), ("ms_h2d", C.c_float), ("ms_dict", C.c_float),
+                ("ms_chains", C.c_float), ("ms_scatter", C.c_float), ("ms_encode", C.c_float), ("ms_d2h", C.c_float),
+                ("ms_total", C.c_float)]
+
+    def as_dict(self) -> dict:
+        return {f: getattr(self, f) for f, _ in self._fields_}
+
+
+_lib = None
+
+
+def load():
+    """dlopen the CUDA library; raises if it has not been built (python -m spring_b200.build)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise SpringB200Error(-2, f"{LIB_PATH} not built; run `python spring_b200/build.py` (needs nvcc)")
+        lib = C.CDLL(LIB_PATH)
+        lib.spring_b200_version.restype = C.c_char_p
+        lib.spring_b200_last_error.restype = C.c_char_p
+        lib.spring_b200_last_error.argtypes = [C.c_void_p]
+        lib.spring_b200_create.argtypes = [C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]
+        lib.spring_b200_destroy.argtypes = [C.c_void_p]
+        lib.spring_b200_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
+        lib.spring_b200_reorder_encode.argtypes = [C.c_void_p, C.POINTER(Input), C.c_uint32, C.POINTER(Streams)]
+        lib.spring_b200_reorder_encode_device.argtypes = [C.c_void_p, C.POINTER(Input), C.c_uint32, C.POINTER(Streams)]
+        lib.spring_b200_fetch_streams.argtypes = [C.c_void_p, C.POINTER(Streams)]
+        lib.spring_b200_build_dictionary.argtypes = [C.c_void_p, C.POINTER(Input), C.c_int, C.c_void_p, C.c_void_p,
+                                                     C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+        lib.spring_b200_reorder.argtypes = [C.c_void_p, C.POINTER(Input), C.c_uint32, C.POINTER(ReorderOut)]
+        lib.spring_b200_reorder_encode_files.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(CP), C.c_uint32]
+        lib.spring_b200_write_streams.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(Streams), C.c_int]
+        _lib = lib
+    return _lib
+
+
+def _view(ptr, n, dtype):
+    if not ptr or n == 0:
+        return np.zeros(0, dtype=dtype)
+    buf = (C.c_uint8 * (n * np.dtype(dtype).itemsize)).from_address(ptr)
+    return np.frombuffer(buf, dtype=dtype, count=n)
+
+
+@dataclass
+class StreamsResult:
+    """Host copy of spring_b200_streams (same fields as the oracle's EncodeResult)."""
+    seq_packed: np.ndarray
+    seq_len: int
+    pos: np.ndarray
+    noise: np.ndarray
+    noisepos: np.ndarray
+    rc: np.ndarray
+    order: np.ndarray
+    lengths: np.ndarray
+    unaligned: np.ndarray
+    unaligned_len: int
+    num_aligned: int
+    matched_s: int
+    matched_N: int
+
+    @property
+    def seq(self) -> np.ndarray:
+        """ASCII consensus (unpacked from 2 bits/base A0 C1 G2 T3)."""
+        b = self.seq_packed
+        codes = np.stack([(b >> (2 * j)) & 3 for j in range(4)], axis=1).reshape(-1)[: self.seq_len]
+        return np.frombuffer(b"ACGT", dtype=np.uint8)[codes]
+
+
+class Context:
+    """One per GPU.  `stream`: raw cudaStream_t handle (e.g. torch.cuda.current_stream().cuda_stream) or None."""
+
+    def __init__(self, device: int = 0, stream: int | None = None):
+        self._lib = load()
+        self._h = C.c_void_p()
+        rc = self._lib.spring_b200_create(device, C.c_void_p(stream) if stream else None, C.byref(self._h))
+        if rc != 0:
+            raise SpringB200Error(rc, self._lib.spring_b200_last_error(None).decode())
+        self._keep = []
+
+    def close(self):
+        if self._h:
+            self._lib.spring_b200_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise SpringB200Error(rc, self._lib.spring_b200_last_error(self._h).decode())
+
+    def stats(self) -> dict:
+        s = Stats()
+        self._check(self._lib.spring_b200_get_stats(self._h, C.byref(s)))
+        return s.as_dict()
+
+    def make_input(self, reads_ptr: int, lengths_ptr: int, num_clean: int, max_readlen: int, n_records: bytes = b"",
+                   order_n: np.ndarray | None = None, num_reads: int | None = None) -> Input:
+        order_n = np.zeros(0, np.uint32) if order_n is None else np.ascontiguousarray(order_n, dtype=np.uint32)
+        nbuf = np.frombuffer(n_records, dtype=np.uint8).copy() if n_records else np.zeros(0, np.uint8)
+        self._keep = [order_n, nbuf]
+        inp = Input()
+        inp.reads = reads_ptr
+        inp.lengths = lengths_ptr
+        inp.num_clean = num_clean
+        inp.max_readlen = max_readlen
+        inp.n_records = nbuf.ctypes.data if len(nbuf) else None
+        inp.n_record_bytes = len(nbuf)
+        inp.order_n = order_n.ctypes.data if len(order_n) else None
+        inp.num_n = len(order_n)
+        inp.num_reads = num_reads if num_reads is not None else num_clean + len(order_n)
+        return inp
+
+    def _input_from_numpy(self, packed, lengths, max_readlen, n_records, order_n, num_reads):
+        packed = np.ascontiguousarray(packed, dtype=np.uint64)
+        lengths = np.ascontiguousarray(lengths, dtype=np.uint16)
+        inp = self.make_input(packed.ctypes.data if packed.size else None, lengths.ctypes.data if lengths.size else None,
+                              len(lengths), max_readlen, n_records, order_n, num_reads)
+        self._keep += [packed, lengths]
+        return inp
+
+    @staticmethod
+    def _streams_to_result(s: Streams) -> StreamsResult:
+        return StreamsResult(
+            _view(s.seq_packed, (s.seq_len + 3) // 4, np.uint8).copy(), s.seq_len,
+            _view(s.pos, s.num_aligned, np.uint64).copy(), _view(s.noise, s.noise_bytes, np.uint8).copy(),
+            _view(s.noisepos, s.num_noise, np.uint16).copy(), _view(s.rev, s.num_aligned, np.uint8).copy(),
+            _view(s.order, s.num_reads, np.uint32).copy(), _view(s.lengths, s.num_reads, np.uint16).copy(),
+            _view(s.unaligned, s.unaligned_bytes, np.uint8).copy(), s.unaligned_len, s.num_aligned,
+            s.singletons_aligned, s.n_reads_aligned)
+
+    # ---- the hot path ------------------------------------------------------------------------
+    def reorder_encode(self, packed, lengths, max_readlen, n_records=b"", order_n=None, num_reads=None,
+                       num_chains: int = 0) -> StreamsResult:
+        """Host numpy in, host numpy out (H2D + kernels + D2H)."""
+        inp = self._input_from_numpy(packed, lengths, max_readlen, n_records, order_n, num_reads)
+        s = Streams()
+        self._check(self._lib.spring_b200_reorder_encode(self._h, C.byref(inp), num_chains, C.byref(s)))
+        return self._streams_to_result(s)
+
+    def reorder_encode_raw(self, inp: Input, num_chains: int = 0, device: bool = False) -> Streams:
+        """No copies of the result: returns the raw struct (pointers owned by the context)."""
+        s = Streams()
+        fn = self._lib.spring_b200_reorder_encode_device if device else self._lib.spring_b200_reorder_encode
+        self._check(fn(self._h, C.byref(inp), num_chains, C.byref(s)))
+        return s
+
+    def fetch_streams(self) -> StreamsResult:
+        s = Streams()
+        self._check(self._lib.spring_b200_fetch_streams(self._h, C.byref(s)))
+        return self._streams_to_result(s)
+
+    # ---- stages -------------------------------------------------------------------------------
+    def build_dictionary(self, packed, lengths, max_readlen, which: int):
+        inp = self._input_from_numpy(packed, lengths, max_readlen, b"", None, None)
+        n = len(lengths)
+        keys = np.zeros(max(n, 1), np.uint64)
+        bs = np.zeros(n + 1, np.uint32)
+        rid = np.zeros(max(n, 1), np.uint32)
+        nk, dn = C.c_uint32(0), C.c_uint32(0)
+        self._check(self._lib.spring_b200_build_dictionary(self._h, C.byref(inp), which, keys.ctypes.data, bs.ctypes.data,
+                                                           rid.ctypes.data, C.byref(nk), C.byref(dn)))
+        return keys[: nk.value], bs[: nk.value + 1], rid[: dn.value]
+
+    def reorder(self, packed, lengths, max_readlen, num_chains: int = 0):
+        inp = self._input_from_numpy(packed, lengths, max_readlen, b"", None, None)
+        o = ReorderOut()
+        self._check(self._lib.spring_b200_reorder(self._h, C.byref(inp), num_chains, C.byref(o)))
+        return (_view(o.order, o.num, np.uint32).copy(), _view(o.flag, o.num, np.uint8).copy(),
+                _view(o.pos, o.num, np.int64).copy(), _view(o.rev, o.num, np.uint8).copy(),
+                _view(o.singleton_order, o.num_singletons, np.uint32).copy())
+
+    # ---- files ---------------------------------------------------------------------------------
+    def reorder_encode_files(self, temp_dir: str, cp: CP, num_chains: int = 0) -> None:
+        self._check(self._lib.spring_b200_reorder_encode_files(self._h, temp_dir.encode(), C.byref(cp), num_chains))

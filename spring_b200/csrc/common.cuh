@@ -1,0 +1,177 @@
+// common.cuh -- shared definitions of the spring_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+#include <map>
+#include <stdexcept>
+
+namespace sb {
+
+// ---- constants of the path (reference: src/params.h:22-37) ---------------------------------
+constexpr int kMaxReadLen = 511;       // MAX_READ_LEN
+constexpr int kMaxWords = 16;          // ceil(2*511/64)
+constexpr int kNumDict = 2;            // NUM_DICT_REORDER / NUM_DICT_ENCODER
+constexpr int kMaxSearch = 1000;       // MAX_SEARCH_REORDER / MAX_SEARCH_ENCODER
+constexpr int kThreshReorder = 4;      // THRESH_REORDER
+constexpr int kThreshEncoder = 24;     // THRESH_ENCODER
+constexpr uint32_t kStopWindow = 1000000u;  // reorder.h:433
+constexpr uint32_t kStopUnmatched = 500000u;  // STOP_CRITERIA_REORDER * 1e6
+constexpr uint32_t kNoWinner = 0xFFFFFFFFu;
+
+struct CudaError : std::runtime_error {
+  explicit CudaError(const std::string &m) : std::runtime_error(m) {}
+};
+struct LimitError : std::runtime_error {
+  explicit LimitError(const std::string &m) : std::runtime_error(m) {}
+};
+
+#define SB_CUDA(expr)                                                                         \
+  do {                                                                                        \
+    cudaError_t _e = (expr);                                                                  \
+    if (_e != cudaSuccess)                                                                    \
+      throw sb::CudaError(std::string(#expr) + ": " + cudaGetErrorString(_e) + " (" + __FILE__ + ":" + \
+                          std::to_string(__LINE__) + ")");                                   \
+  } while (0)
+
+// ---- dictionary in HBM ------------------------------------------------------------------------
+// One open-addressing slot per unique key.  16 B so a probe is one aligned uint4 load (one 32 B
+// sector); count == 0 marks an empty slot.  Replaces BooPHF + startpos[] (bitset_util.h:22-41):
+// the key is stored, so the reference's "verify against the first read of the bin" step
+// (reorder.h:282-285) is folded into the probe.
+struct __align__(16) DictSlot {
+  uint64_t key;
+  uint32_t start;  // first index of the bin in read_id[]
+  uint32_t count;  // reads in the bin (0 = empty slot)
+};
+
+struct DictView {
+  const DictSlot *slots;
+  uint32_t slot_mask;       // capacity - 1 (power of two)
+  const uint32_t *read_id;  // ascending inside a bin
+  int start, end;           // base window [start, end]
+  int key_bits;             // bits per base * (end - start + 1)
+};
+
+__host__ __device__ inline uint64_t mix64(uint64_t x) {  // murmur3 finalizer
+  x ^= x >> 33; x *= 0xff51afd7ed558ccdULL;
+  x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL;
+  x ^= x >> 33;
+  return x;
+}
+
+__host__ __device__ inline int words_for(int max_readlen) { return (2 * max_readlen - 1) / 64 + 1; }
+
+// reorder dictionary windows (reorder.h:752-759)
+inline void reorder_windows(int L, int start[2], int end[2]) {
+  start[0] = L > 100 ? L / 2 - 32 : L / 2 - L * 32 / 100;
+  end[0] = L / 2 - 1;
+  start[1] = L / 2;
+  end[1] = L > 100 ? L / 2 - 1 + 32 : L / 2 - 1 + L * 32 / 100;
+}
+// encoder dictionary windows (encoder.h:609-620)
+inline void encoder_windows(int L, int start[2], int end[2]) {
+  if (L > 50) { start[0] = 0; end[0] = 20; start[1] = 21; end[1] = 41; }
+  else { start[0] = 0; end[0] = 20 * L / 50; start[1] = 20 * L / 50 + 1; end[1] = 41 * L / 50; }
+}
+
+#ifdef __CUDACC__
+// word i of (a >> bits) / (a << bits) for a W-word little-endian bitset (std::bitset semantics)
+__device__ __forceinline__ uint64_t shr_word(const uint64_t *a, int W, int i, int bits) {
+  int k = i + (bits >> 6), bs = bits & 63;
+  uint64_t lo = k < W ? a[k] : 0ull, hi = k + 1 < W ? a[k + 1] : 0ull;
+  return bs ? (lo >> bs) | (hi << (64 - bs)) : lo;
+}
+__device__ __forceinline__ uint64_t shl_word(const uint64_t *a, int W, int i, int bits) {
+  int k = i - (bits >> 6), bs = bits & 63;
+  uint64_t hi = (k >= 0 && k < W) ? a[k] : 0ull, lo = (k - 1 >= 0 && k - 1 < W) ? a[k - 1] : 0ull;
+  return bs ? (hi << bs) | (lo >> (64 - bs)) : hi;
+}
+// bits [pos, pos+nbits) of a, nbits <= 64
+__device__ __forceinline__ uint64_t extract_bits(const uint64_t *a, int W, int pos, int nbits) {
+  uint64_t v = shr_word(a, W, 0, pos);
+  return nbits < 64 ? v & ((1ull << nbits) - 1ull) : v;
+}
+// mask of word i covering bits [lo, hi)
+__device__ __forceinline__ uint64_t range_mask(int i, int lo, int hi) {
+  int b0 = i << 6;
+  int l = lo - b0, h = hi - b0;
+  if (h <= 0 || l >= 64 || hi <= lo) return 0ull;
+  uint64_t m = ~0ull;
+  if (l > 0) m &= ~0ull << l;
+  if (h < 64) m &= ~0ull >> (64 - h);
+  return m;
+}
+// spread the 32 bits of x to the even bit positions of a 64-bit word
+__device__ __forceinline__ uint64_t spread_bits(uint32_t x) {
+  uint64_t v = x;
+  v = (v | (v << 16)) & 0x0000FFFF0000FFFFull;
+  v = (v | (v << 8)) & 0x00FF00FF00FF00FFull;
+  v = (v | (v << 4)) & 0x0F0F0F0F0F0F0F0Full;
+  v = (v | (v << 2)) & 0x3333333333333333ull;
+  v = (v | (v << 1)) & 0x5555555555555555ull;
+  return v;
+}
+__device__ __forceinline__ int base_code(const uint64_t *w, int j) { return (int)((w[j >> 5] >> (2 * (j & 31))) & 3ull); }
+
+__device__ __forceinline__ DictSlot load_slot(const DictSlot *p) {
+  uint4 v = __ldg(reinterpret_cast<const uint4 *>(p));
+  DictSlot s;
+  s.key = (uint64_t)v.x | ((uint64_t)v.y << 32);
+  s.start = v.z;
+  s.count = v.w;
+  return s;
+}
+// exact lookup: returns count (0 = absent) and sets start
+__device__ __forceinline__ uint32_t dict_find(const DictView &d, uint64_t key, uint32_t &start) {
+  uint32_t h = (uint32_t)mix64(key) & d.slot_mask;
+  for (;;) {
+    DictSlot s = load_slot(d.slots + h);
+    if (s.count == 0) return 0;
+    if (s.key == key) { start = s.start; return s.count; }
+    h = (h + 1) & d.slot_mask;
+  }
+}
+#endif
+
+// ---- grow-only named device / pinned buffers owned by a context --------------------------------
+class BufferPool {
+ public:
+  ~BufferPool() { release(); }
+  void *device(const char *name, size_t bytes) {
+    Buf &b = dev_[name];
+    if (bytes > b.cap) {
+      if (b.p) SB_CUDA(cudaFree(b.p));
+      b.p = nullptr; b.cap = 0;
+      size_t want = bytes + bytes / 8 + 256;
+      SB_CUDA(cudaMalloc(&b.p, want));
+      b.cap = want;
+    }
+    return b.p;
+  }
+  void *pinned(const char *name, size_t bytes) {
+    Buf &b = pin_[name];
+    if (bytes > b.cap) {
+      if (b.p) SB_CUDA(cudaFreeHost(b.p));
+      b.p = nullptr; b.cap = 0;
+      size_t want = bytes + bytes / 8 + 256;
+      SB_CUDA(cudaMallocHost(&b.p, want));
+      b.cap = want;
+    }
+    return b.p;
+  }
+  template <typename T> T *dev(const char *name, size_t n) { return static_cast<T *>(device(name, n * sizeof(T))); }
+  template <typename T> T *pin(const char *name, size_t n) { return static_cast<T *>(pinned(name, n * sizeof(T))); }
+  void release() {
+    for (auto &kv : dev_) if (kv.second.p) cudaFree(kv.second.p);
+    for (auto &kv : pin_) if (kv.second.p) cudaFreeHost(kv.second.p);
+    dev_.clear(); pin_.clear();
+  }
+ private:
+  struct Buf { void *p = nullptr; size_t cap = 0; };
+  std::map<std::string, Buf> dev_, pin_;
+};
+
+}  // namespace sb

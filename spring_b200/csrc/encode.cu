@@ -1,0 +1,608 @@
+// encode.cu -- the contig encoder (reference src/encoder.h:124-494, src/encoder.cpp:32-156).
+//
+// The reference walks each reorder thread's stream contig by contig with std::list<std::string>;
+// here the same result is produced by data-parallel passes over flat arrays in HBM:
+//
+//   1. contig index of every stream record = prefix sum of "flag == 0"      (encoder.h:215)
+//   2. per-contig min(pos) / max(pos+len) -> contig length, prefix sum -> the contig's start in
+//      the concatenated consensus (abs_pos in writecontig, encoder.cpp:98,107)
+//   3. absolute position of every read; stable radix sort by it.  Contigs occupy disjoint
+//      ascending ranges, so this one sort is list::sort per contig (encoder.h:221) for all contigs.
+//   4. consensus: one thread per consensus column, the reads overlapping a 256-column tile are
+//      staged in shared memory, majority vote in registers                   (buildcontig)
+//   5. singleton/N re-alignment: one thread per consensus window position; 4 dictionary probes
+//      (2 strands x 2 dicts) against a dictionary of the singleton pool; a passing candidate
+//      records min(priority) with atomicMin, priority = (window position, strand, dict), i.e.
+//      the first window that would have taken it in the reference's sequential sweep
+//      (encoder.h:242-351)
+//   6. merge aligned singletons into the sorted order (second list::sort, encoder.h:354-356)
+//   7. noise: one warp per read, ballot of mismatching bases -> noise symbols (enc_noise,
+//      encoder.h:518-537) and u16 delta positions                            (writecontig)
+//   8. unaligned reads as 4-bit records (write_dnaN_in_bits, util.cpp:322-348), consensus packed
+//      2 bits/base A0 C1 G2 T3 (pack_compress_seq, encoder.cpp:126-141)
+//
+// Encoder reads are 3 bits/base in the reference (A0 N1 G2 C4 T6) so that N fits; bits 1,2 of that
+// code are exactly the 2-bit reorder code, hence Hamming3(window, read) = popcount(window2 ^ read2)
+// over the read's length + (number of N in the read) when N is stored as 00 -- the pool keeps the
+// 2-bit layout plus an N bit-plane, and THRESH_ENCODER = 24 applies unchanged.
+//
+// Deviation (documented in DESIGN.md): MAX_SEARCH_ENCODER limits a bin scan to its 1000 highest
+// *live* ids and the reference deletes matched singletons as it goes; the parallel sweep scans the
+// 1000 highest ids of the bin as built.  Identical unless a singleton bin holds > 1000 reads.
+#include <cub/cub.cuh>
+#include "kernels.cuh"
+
+namespace sb {
+namespace {
+
+constexpr unsigned FULL = 0xFFFFFFFFu;
+constexpr unsigned long long kNoPrio = ~0ull;
+
+static inline uint32_t grid_for(uint64_t n, int block) { return (uint32_t)((n + block - 1) / block); }
+
+// encoder.cpp:177-222: clean index -> index in the original FASTQ; order_n ascending
+__device__ __forceinline__ uint32_t corrected_order(uint32_t k, const uint32_t *__restrict__ order_n, uint32_t nn) {
+  uint32_t lo = 0, hi = nn;
+  while (lo < hi) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (order_n[mid] - mid <= k) lo = mid + 1; else hi = mid;
+  }
+  return k + lo;
+}
+__device__ __forceinline__ uint32_t lower_bound_u64(const uint64_t *__restrict__ a, uint32_t n, uint64_t v) {
+  uint32_t lo = 0, hi = n;
+  while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (a[mid] < v) lo = mid + 1; else hi = mid; }
+  return lo;
+}
+__device__ __forceinline__ uint32_t upper_bound_u64(const uint64_t *__restrict__ a, uint32_t n, uint64_t v) {
+  uint32_t lo = 0, hi = n;
+  while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (a[mid] <= v) lo = mid + 1; else hi = mid; }
+  return lo;
+}
+
+// ---- pool of singleton + N reads (readsingletons, encoder.h:541-570) -------------------------
+__global__ void k_gather_pool(const uint64_t *__restrict__ reads, const uint16_t *__restrict__ lens,
+                              const uint32_t *__restrict__ s_order, uint32_t S, NReads nr, int W,
+                              uint64_t *pool_codes, uint64_t *pool_nflag, uint16_t *pool_len, uint32_t *pool_order,
+                              uint32_t *pool_ncount) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= S + nr.num) return;
+  uint32_t nc = 0;
+  if (i < S) {
+    const uint32_t rid = s_order[i];
+    for (int w = 0; w < W; w++) { pool_codes[(size_t)i * W + w] = reads[(size_t)rid * W + w]; pool_nflag[(size_t)i * W + w] = 0; }
+    pool_len[i] = lens[rid];
+    pool_order[i] = corrected_order(rid, nr.order, nr.num);
+  } else {
+    const uint32_t j = i - S;
+    for (int w = 0; w < W; w++) {
+      pool_codes[(size_t)i * W + w] = nr.codes[(size_t)j * W + w];
+      const uint64_t f = nr.nflag[(size_t)j * W + w];
+      pool_nflag[(size_t)i * W + w] = f;
+      nc += __popcll(f);
+    }
+    pool_len[i] = nr.lens[j];
+    pool_order[i] = nr.order[j];
+  }
+  pool_ncount[i] = nc;
+}
+
+// ---- contigs ----------------------------------------------------------------------------------------
+__global__ void k_heads(const uint8_t *__restrict__ flag, uint32_t m, uint32_t *head) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < m) head[i] = flag[i] == 0 ? 1u : 0u;
+}
+
+// per contig min(pos), max(pos+len): warp-segmented reduction, one atomic per (warp, contig)
+__global__ void k_contig_bounds(const uint32_t *__restrict__ cidx1, const int64_t *__restrict__ pos,
+                                const uint32_t *__restrict__ order, const uint16_t *__restrict__ lens, uint32_t m,
+                                long long *cmin, long long *cmaxend) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const bool v = i < m;
+  uint32_t c = v ? cidx1[i] - 1 : 0xFFFFFFFFu;
+  long long lo = v ? pos[i] : 0x7FFFFFFFFFFFFFFFll;
+  long long hi = v ? pos[i] + lens[order[i]] : (long long)0x8000000000000000ull;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t c2 = __shfl_up_sync(FULL, c, d);
+    const long long lo2 = __shfl_up_sync(FULL, lo, d), hi2 = __shfl_up_sync(FULL, hi, d);
+    if (lane >= d && c2 == c) { lo = lo2 < lo ? lo2 : lo; hi = hi2 > hi ? hi2 : hi; }
+  }
+  const uint32_t cn = __shfl_down_sync(FULL, c, 1);
+  if (v && (lane == 31 || cn != c)) { atomicMin(cmin + c, lo); atomicMax(cmaxend + c, hi); }
+}
+
+__global__ void k_contig_len(const long long *__restrict__ cmin, const long long *__restrict__ cmaxend, uint32_t nc,
+                             unsigned long long *clen) {
+  const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < nc) clen[c] = (unsigned long long)(cmaxend[c] - cmin[c]);
+  if (c == nc) clen[c] = 0;
+}
+
+__global__ void k_abs_pos(const uint32_t *__restrict__ cidx1, const int64_t *__restrict__ pos,
+                          const long long *__restrict__ cmin, const unsigned long long *__restrict__ cstart, uint32_t m,
+                          uint64_t *ap, uint32_t *idx) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  const uint32_t c = cidx1[i] - 1;
+  ap[i] = cstart[c] + (uint64_t)(pos[i] - cmin[c]);
+  idx[i] = i;
+}
+
+// ---- consensus (buildcontig, encoder.cpp:32-74) ---------------------------------------------------
+constexpr int kTile = 256, kStage = 64;
+__global__ void __launch_bounds__(kTile) k_consensus(const uint64_t *__restrict__ reads, const uint16_t *__restrict__ lens,
+                                                     const uint32_t *__restrict__ order, const uint8_t *__restrict__ rev,
+                                                     const uint64_t *__restrict__ sorted_ap, const uint32_t *__restrict__ perm,
+                                                     uint32_t m, int W, int L, uint64_t seq_len, uint8_t *cons) {
+  __shared__ uint64_t s_words[kStage * kMaxWords];
+  __shared__ uint64_t s_ap[kStage];
+  __shared__ uint32_t s_rid[kStage];
+  __shared__ uint16_t s_len[kStage];
+  __shared__ uint8_t s_rev[kStage];
+  __shared__ uint32_t s_range[2];
+  const uint64_t x0 = (uint64_t)blockIdx.x * kTile;
+  const uint64_t x = x0 + threadIdx.x;
+  if (threadIdx.x == 0) {
+    const uint64_t lo_ap = x0 >= (uint64_t)(L - 1) ? x0 - (uint64_t)(L - 1) : 0;  // reads with ap + L > x0
+    s_range[0] = lower_bound_u64(sorted_ap, m, lo_ap);
+    s_range[1] = lower_bound_u64(sorted_ap, m, x0 + kTile);
+  }
+  __syncthreads();
+  const uint32_t r_lo = s_range[0], r_hi = s_range[1];
+  uint32_t cA = 0, cC = 0, cG = 0, cT = 0;
+  for (uint32_t base = r_lo; base < r_hi; base += kStage) {
+    const uint32_t cnt = min((uint32_t)kStage, r_hi - base);
+    if (threadIdx.x < cnt) {
+      const uint32_t r = base + threadIdx.x, p = perm[r], rid = order[p];
+      s_ap[threadIdx.x] = sorted_ap[r];
+      s_rid[threadIdx.x] = rid;
+      s_len[threadIdx.x] = lens[rid];
+      s_rev[threadIdx.x] = rev[p] == 'r';
+    }
+    __syncthreads();
+    for (uint32_t t = threadIdx.x; t < cnt * (uint32_t)W; t += kTile) {
+      const uint32_t q = t / W, w = t - q * W;
+      s_words[q * kMaxWords + w] = reads[(size_t)s_rid[q] * W + w];
+    }
+    __syncthreads();
+    if (x < seq_len) {
+      for (uint32_t q = 0; q < cnt; q++) {
+        const uint64_t a = s_ap[q];
+        const int len = s_len[q];
+        if (x >= a && x < a + (uint64_t)len) {
+          const int off = (int)(x - a);
+          const uint64_t *w = s_words + q * kMaxWords;
+          const int code = s_rev[q] ? 3 - base_code(w, len - 1 - off) : base_code(w, off);
+          cA += code == 0; cG += code == 1; cC += code == 2; cT += code == 3;
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (x < seq_len) {  // first strict maximum in A,C,G,T order (encoder.cpp:62-71); uncovered -> 'A'
+    uint32_t mx = 0; int code = 0;
+    if (cA > mx) { mx = cA; code = 0; }
+    if (cC > mx) { mx = cC; code = 2; }
+    if (cG > mx) { mx = cG; code = 1; }
+    if (cT > mx) { mx = cT; code = 3; }
+    cons[x] = (uint8_t)code;
+  }
+}
+
+// ---- singleton re-alignment (encoder.h:231-352) ---------------------------------------------------
+struct AlignArgs {
+  const uint8_t *cons; uint64_t seq_len;
+  const unsigned long long *cstart; uint32_t num_contigs;  // cstart[num_contigs] == seq_len
+  DictView dict[2];
+  const uint64_t *pool_codes; const uint16_t *pool_len; const uint32_t *pool_ncount;
+  int W, L;
+  unsigned long long *best;
+};
+__global__ void k_align_singletons(AlignArgs a) {
+  const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j + (uint64_t)a.L > a.seq_len) return;
+  // contig of column j: last c with cstart[c] <= j
+  uint32_t lo = 0, hi = a.num_contigs;
+  while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (a.cstart[mid] <= j) lo = mid; else hi = mid; }
+  if (j + (uint64_t)a.L > a.cstart[lo + 1]) return;  // window leaves the contig (or contig shorter than max_readlen)
+  const uint8_t *win = a.cons + j;
+  const int L = a.L, W = a.W;
+#pragma unroll 1
+  for (int kind = 0; kind < 4; kind++) {
+    const int rev = kind >> 1, l = kind & 1;
+    const DictView &d = a.dict[l];
+    uint64_t key = 0;
+    if (!rev) for (int t = d.start; t <= d.end; t++) key |= (uint64_t)win[t] << (2 * (t - d.start));
+    else for (int t = d.start; t <= d.end; t++) key |= (uint64_t)(3 - win[L - 1 - t]) << (2 * (t - d.start));
+    uint32_t bs, bc = dict_find(d, key, bs);
+    if (!bc) continue;
+    const unsigned long long prio = (j << 2) | (unsigned long long)(rev << 1) | (unsigned long long)l;
+    const uint32_t lim = bc < (uint32_t)kMaxSearch ? bc : (uint32_t)kMaxSearch;
+    for (uint32_t t = 0; t < lim; t++) {
+      const uint32_t rid = d.read_id[bs + bc - 1 - t];
+      const int len = a.pool_len[rid];
+      const uint64_t *r = a.pool_codes + (size_t)rid * W;
+      int h = (int)a.pool_ncount[rid];
+      for (int b = 0; b < len && h <= kThreshEncoder; b++) {
+        const int wc = rev ? 3 - win[L - 1 - b] : win[b];
+        h += __popc((unsigned)(wc ^ base_code(r, b)));
+      }
+      if (h <= kThreshEncoder) atomicMin(a.best + rid, prio);
+    }
+  }
+}
+
+__global__ void k_pool_flags(const unsigned long long *__restrict__ best, uint32_t p, uint8_t *aligned, uint8_t *unaligned) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p) return;
+  const bool al = best[i] != kNoPrio;
+  aligned[i] = al; unaligned[i] = !al;
+}
+
+// sort keys of the aligned singletons: (final position, discovery order), see header comment
+__global__ void k_single_keys(const uint32_t *__restrict__ a_idx, uint32_t k, const unsigned long long *__restrict__ best,
+                              const uint16_t *__restrict__ pool_len, int L, uint32_t *key_rid, uint32_t *ent) {
+  const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= k) return;
+  key_rid[e] = ~a_idx[e];  // bins are scanned from the highest id down (encoder.h:270-272)
+  ent[e] = e;
+}
+__global__ void k_single_keys2(const uint32_t *__restrict__ a_idx, const uint32_t *__restrict__ ent, uint32_t k,
+                               const unsigned long long *__restrict__ best, const uint16_t *__restrict__ pool_len, int L,
+                               uint64_t *key) {
+  const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= k) return;
+  const uint32_t pi = a_idx[ent[e]];
+  const unsigned long long pr = best[pi];
+  const uint64_t j = pr >> 2;
+  const int rev = (int)((pr >> 1) & 1);
+  const uint64_t d = rev ? (uint64_t)(L - (int)pool_len[pi]) : 0;  // pos = j + L - len (encoder.h:297-299)
+  key[e] = ((j + d) << 12) | ((uint64_t)(511 - (int)d) << 2) | (pr & 3ull);  // same pos: ascending j, then strand, dict
+}
+
+// final stream order: originals (sorted by abs pos) merged with aligned singletons; originals first on ties
+struct FinalArrays {
+  uint64_t *pos; uint32_t *order; uint16_t *len; uint8_t *rev; uint32_t *src; uint8_t *kind;
+};
+__global__ void k_place_originals(const uint64_t *__restrict__ sorted_ap, const uint32_t *__restrict__ perm, uint32_t m,
+                                  const uint64_t *__restrict__ skey, uint32_t k, const uint32_t *__restrict__ order,
+                                  const uint8_t *__restrict__ rev, const uint16_t *__restrict__ lens,
+                                  const uint32_t *__restrict__ order_n, uint32_t nn, FinalArrays f) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  const uint64_t ap = sorted_ap[i];
+  const uint32_t q = i + lower_bound_u64(skey, k, ap << 12);
+  const uint32_t p = perm[i], rid = order[p];
+  f.pos[q] = ap; f.order[q] = corrected_order(rid, order_n, nn); f.len[q] = lens[rid]; f.rev[q] = rev[p];
+  f.src[q] = rid; f.kind[q] = 0;
+}
+__global__ void k_place_singles(const uint64_t *__restrict__ skey, const uint32_t *__restrict__ ent,
+                                const uint32_t *__restrict__ a_idx, uint32_t k, const uint64_t *__restrict__ sorted_ap,
+                                uint32_t m, const uint16_t *__restrict__ pool_len, const uint32_t *__restrict__ pool_order,
+                                FinalArrays f) {
+  const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= k) return;
+  const uint64_t key = skey[e], ap = key >> 12;
+  const uint32_t q = e + upper_bound_u64(sorted_ap, m, ap);
+  const uint32_t pi = a_idx[ent[e]];
+  f.pos[q] = ap; f.order[q] = pool_order[pi]; f.len[q] = pool_len[pi]; f.rev[q] = (key & 2) ? 'r' : 'd';
+  f.src[q] = pi; f.kind[q] = 1;
+}
+
+// ---- noise (writecontig, encoder.cpp:76-109) ----------------------------------------------------------
+// reorder 2-bit codes A0 G1 C2 T3; table[ref][read] from encoder.h:518-533
+__constant__ char kEncNoise[4][4] = {
+    /* ref A */ {0, '1', '0', '2'},
+    /* ref G */ {'1', 0, '2', '0'},
+    /* ref C */ {'0', '1', 0, '2'},
+    /* ref T */ {'2', '0', '1', 0}};
+
+struct NoiseArgs {
+  const uint64_t *reads; const uint64_t *pool_codes; const uint64_t *pool_nflag; int W;
+  const uint8_t *cons; FinalArrays f; uint32_t m;
+  uint32_t *nmis;                  // pass 1 out / pass 2 in (exclusive scan)
+  const uint64_t *noise_off;       // exclusive scan of nmis
+  uint8_t *noise; uint16_t *noisepos;
+};
+template <bool WRITE>
+__global__ void k_noise(NoiseArgs a) {
+  const uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (q >= a.m) return;
+  const int len = a.f.len[q];
+  const bool rev = a.f.rev[q] == 'r';
+  const bool pool = a.f.kind[q] != 0;
+  const uint64_t *r = (pool ? a.pool_codes : a.reads) + (size_t)a.f.src[q] * a.W;
+  const uint64_t *nf = pool ? a.pool_nflag + (size_t)a.f.src[q] * a.W : nullptr;
+  const uint8_t *ref = a.cons + a.f.pos[q];
+  uint32_t total = 0;
+  int prevj = 0;
+  uint64_t off = 0;
+  if (WRITE) off = a.noise_off[q];
+  for (int base = 0; base < len; base += 32) {
+    const int t = base + lane;
+    bool mis = false; char sym = 0;
+    if (t < len) {
+      const int src = rev ? len - 1 - t : t;
+      int code = base_code(r, src);
+      if (rev) code = 3 - code;
+      const bool isn = nf && ((nf[src >> 5] >> (2 * (src & 31))) & 1ull);
+      const int rc = ref[t];
+      if (isn) { mis = true; sym = '3'; }
+      else if (code != rc) { mis = true; sym = kEncNoise[rc][code]; }
+    }
+    const unsigned mm = __ballot_sync(FULL, mis);
+    if (WRITE && mis) {
+      const unsigned below = mm & ((1u << lane) - 1u);
+      const uint32_t rank = total + __popc(below);
+      const int pj = below ? base + (31 - __clz(below)) : prevj;
+      a.noise[off + q + rank] = (uint8_t)sym;       // + q: one '\n' per earlier read
+      a.noisepos[off + rank] = (uint16_t)(t - pj);
+    }
+    if (mm) prevj = base + (31 - __clz(mm));
+    total += __popc(mm);
+  }
+  if (lane == 0) {
+    if (WRITE) a.noise[off + q + total] = '\n';
+    else a.nmis[q] = total;
+  }
+}
+
+// ---- unaligned tail (encoder.h:426-453) --------------------------------------------------------------
+__global__ void k_unaligned_sizes(const uint32_t *__restrict__ u_idx, uint32_t u, const uint16_t *__restrict__ pool_len,
+                                  unsigned long long *rec_bytes, unsigned long long *bases) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= u) { if (i == u) { rec_bytes[i] = 0; bases[i] = 0; } return; }
+  const uint32_t len = pool_len[u_idx[i]];
+  rec_bytes[i] = 2 + (len + 1) / 2;
+  bases[i] = len;
+}
+__global__ void k_unaligned_write(const uint32_t *__restrict__ u_idx, uint32_t u, const uint64_t *__restrict__ pool_codes,
+                                  const uint64_t *__restrict__ pool_nflag, const uint16_t *__restrict__ pool_len,
+                                  const uint32_t *__restrict__ pool_order, int W, const unsigned long long *__restrict__ rec_off,
+                                  uint8_t *out, uint32_t *order_out, uint16_t *len_out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= u) return;
+  const uint32_t pi = u_idx[i];
+  const int len = pool_len[pi];
+  const uint64_t *r = pool_codes + (size_t)pi * W, *nf = pool_nflag + (size_t)pi * W;
+  uint8_t *o = out + rec_off[i];
+  o[0] = (uint8_t)(len & 0xFF); o[1] = (uint8_t)(len >> 8);
+  for (int b = 0; b < (len + 1) / 2; b++) {
+    uint8_t v = 0;
+    for (int h = 0; h < 2; h++) {
+      const int t = 2 * b + h;
+      if (t < len) {
+        const int code = ((nf[t >> 5] >> (2 * (t & 31))) & 1ull) ? 4 : base_code(r, t);
+        v |= (uint8_t)(code << (4 * h));
+      }
+    }
+    o[2 + b] = v;
+  }
+  order_out[i] = pool_order[pi];
+  len_out[i] = (uint16_t)len;
+}
+
+// consensus bytes (reorder codes A0 G1 C2 T3) -> 2 bits/base A0 C1 G2 T3, LSB first (encoder.cpp:126-141)
+__global__ void k_pack_seq(const uint8_t *__restrict__ cons, uint64_t seq_len, uint8_t *packed) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i * 4 >= seq_len) return;
+  uint8_t v = 0;
+  for (int j = 0; j < 4; j++) {
+    const uint64_t x = i * 4 + j;
+    if (x < seq_len) { const int c = cons[x]; v |= (uint8_t)((((c & 1) << 1) | (c >> 1)) << (2 * j)); }
+  }
+  packed[i] = v;
+}
+
+__global__ void k_fill_u64(unsigned long long *p, uint64_t n, unsigned long long v) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+__global__ void k_count_below(const uint32_t *__restrict__ a_idx, uint32_t k, uint32_t s, uint32_t *out) {
+  uint32_t lo = 0, hi = k;
+  while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (a_idx[mid] < s) lo = mid + 1; else hi = mid; }
+  *out = lo;
+}
+
+template <typename T> T d2h(Ctx &c, const T *dptr) {
+  T v;
+  SB_CUDA(cudaMemcpyAsync(&v, dptr, sizeof(T), cudaMemcpyDeviceToHost, c.stream));
+  SB_CUDA(cudaStreamSynchronize(c.stream));
+  return v;
+}
+static int bits_for(uint64_t v) { int b = 1; while (b < 64 && (v >> b)) b++; return b; }
+
+}  // namespace
+
+void run_encode(Ctx &c, const uint64_t *reads, const uint16_t *lens, uint32_t n, int L, const ReorderDev &ro,
+                const NReads &nr, uint32_t num_total, EncodeDev &out) {
+  cudaStream_t st = c.stream;
+  out = EncodeDev{};
+  const int W = words_for(L);
+  const uint32_t M = (uint32_t)ro.num, S = (uint32_t)ro.num_singletons, P = S + nr.num;
+  const uint32_t Mn = M ? M : 1, Pn = P ? P : 1;
+  (void)n;
+  size_t cub_bytes = 1 << 20;
+  void *cub_tmp = c.pool.device("en.cubtmp", cub_bytes);
+  auto cub_need = [&](size_t need) { if (need > cub_bytes) { cub_bytes = need; cub_tmp = c.pool.device("en.cubtmp", cub_bytes); } };
+
+  // ---- pool --------------------------------------------------------------------------------------
+  uint64_t *pool_codes = c.pool.dev<uint64_t>("en.pool_codes", (size_t)Pn * W);
+  uint64_t *pool_nflag = c.pool.dev<uint64_t>("en.pool_nflag", (size_t)Pn * W);
+  uint16_t *pool_len = c.pool.dev<uint16_t>("en.pool_len", Pn);
+  uint32_t *pool_order = c.pool.dev<uint32_t>("en.pool_order", Pn);
+  uint32_t *pool_ncount = c.pool.dev<uint32_t>("en.pool_ncount", Pn);
+  if (P) { k_gather_pool<<<grid_for(P, 128), 128, 0, st>>>(reads, lens, ro.s_order, S, nr, W, pool_codes, pool_nflag, pool_len, pool_order, pool_ncount); c.launches++; }
+
+  // ---- contigs -------------------------------------------------------------------------------------
+  uint32_t *cidx1 = c.pool.dev<uint32_t>("en.cidx1", Mn);
+  uint32_t num_contigs = 0;
+  if (M) {
+    uint32_t *head = c.pool.dev<uint32_t>("en.head", Mn);
+    k_heads<<<grid_for(M, 256), 256, 0, st>>>(ro.flag, M, head);
+    size_t need = 0;
+    cub::DeviceScan::InclusiveSum(nullptr, need, head, cidx1, (int)M, st); cub_need(need);
+    need = cub_bytes; cub::DeviceScan::InclusiveSum(cub_tmp, need, head, cidx1, (int)M, st);
+    c.launches += 2;
+    num_contigs = d2h(c, cidx1 + (M - 1));
+  }
+  const uint32_t NC = num_contigs;
+  long long *cmin = c.pool.dev<long long>("en.cmin", NC + 1);
+  long long *cmaxend = c.pool.dev<long long>("en.cmaxend", NC + 1);
+  unsigned long long *clen = c.pool.dev<unsigned long long>("en.clen", NC + 1);
+  unsigned long long *cstart = c.pool.dev<unsigned long long>("en.cstart", NC + 1);
+  uint64_t seq_len = 0;
+  uint64_t *ap = c.pool.dev<uint64_t>("en.ap", Mn), *sorted_ap = c.pool.dev<uint64_t>("en.sorted_ap", Mn);
+  uint32_t *idx = c.pool.dev<uint32_t>("en.idx", Mn), *perm = c.pool.dev<uint32_t>("en.perm", Mn);
+  if (M) {
+    k_fill_u64<<<grid_for(NC + 1, 256), 256, 0, st>>>((unsigned long long *)cmin, NC + 1, 0x7FFFFFFFFFFFFFFFull);
+    k_fill_u64<<<grid_for(NC + 1, 256), 256, 0, st>>>((unsigned long long *)cmaxend, NC + 1, 0x8000000000000000ull);
+    k_contig_bounds<<<grid_for(M, 256), 256, 0, st>>>(cidx1, ro.pos, ro.order, lens, M, cmin, cmaxend);
+    k_contig_len<<<grid_for(NC + 1, 256), 256, 0, st>>>(cmin, cmaxend, NC, clen);
+    size_t need = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, need, clen, cstart, (int)NC + 1, st); cub_need(need);
+    need = cub_bytes; cub::DeviceScan::ExclusiveSum(cub_tmp, need, clen, cstart, (int)NC + 1, st);
+    c.launches += 5;
+    seq_len = d2h(c, cstart + NC);
+    k_abs_pos<<<grid_for(M, 256), 256, 0, st>>>(cidx1, ro.pos, cmin, cstart, M, ap, idx);
+    const int kb = bits_for(seq_len);
+    need = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, need, ap, sorted_ap, idx, perm, (int)M, 0, kb, st); cub_need(need);
+    need = cub_bytes; cub::DeviceRadixSort::SortPairs(cub_tmp, need, ap, sorted_ap, idx, perm, (int)M, 0, kb, st);
+    c.launches += 2 + 2 * ((kb + 7) / 8);
+  }
+  out.seq_len = seq_len;
+
+  // ---- consensus ------------------------------------------------------------------------------------
+  uint8_t *cons = c.pool.dev<uint8_t>("en.cons", seq_len + 8);
+  if (seq_len) {
+    k_consensus<<<grid_for(seq_len, kTile), kTile, 0, st>>>(reads, lens, ro.order, ro.rev, sorted_ap, perm, M, W, L, seq_len, cons);
+    c.launches++;
+  }
+
+  // ---- singleton / N re-alignment ------------------------------------------------------------------
+  unsigned long long *best = c.pool.dev<unsigned long long>("en.best", Pn);
+  uint32_t K = 0, U = P;
+  uint32_t *a_idx = c.pool.dev<uint32_t>("en.a_idx", Pn), *u_idx = c.pool.dev<uint32_t>("en.u_idx", Pn);
+  uint32_t *d_cnt = c.pool.dev<uint32_t>("en.cnt", 8);
+  uint32_t *ent_a = c.pool.dev<uint32_t>("en.ent_a", Pn), *ent_b = c.pool.dev<uint32_t>("en.ent_b", Pn);
+  uint64_t *skey_a = c.pool.dev<uint64_t>("en.skey_a", Pn), *skey = c.pool.dev<uint64_t>("en.skey", Pn);
+  uint32_t *ent = ent_a;
+  if (P) {
+    k_fill_u64<<<grid_for(P, 256), 256, 0, st>>>(best, P, kNoPrio);
+    c.launches++;
+    if ((int64_t)seq_len >= L && NC) {
+      DictBuild ed[2];
+      int es[2], ee[2];
+      encoder_windows(L, es, ee);
+      build_dictionary(c, pool_codes, pool_len, pool_nflag, P, W, es[0], ee[0], "en.dict0", ed[0]);
+      build_dictionary(c, pool_codes, pool_len, pool_nflag, P, W, es[1], ee[1], "en.dict1", ed[1]);
+      AlignArgs aa{};
+      aa.cons = cons; aa.seq_len = seq_len; aa.cstart = cstart; aa.num_contigs = NC;
+      aa.dict[0] = ed[0].view; aa.dict[1] = ed[1].view;
+      aa.pool_codes = pool_codes; aa.pool_len = pool_len; aa.pool_ncount = pool_ncount; aa.W = W; aa.L = L; aa.best = best;
+      k_align_singletons<<<grid_for(seq_len, 256), 256, 0, st>>>(aa);
+      c.launches++;
+    }
+    uint8_t *fl_a = c.pool.dev<uint8_t>("en.fl_a", Pn), *fl_u = c.pool.dev<uint8_t>("en.fl_u", Pn);
+    k_pool_flags<<<grid_for(P, 256), 256, 0, st>>>(best, P, fl_a, fl_u);
+    cub::CountingInputIterator<uint32_t> cnt(0);
+    size_t need = 0;
+    cub::DeviceSelect::Flagged(nullptr, need, cnt, fl_a, a_idx, d_cnt, (int)P, st); cub_need(need);
+    need = cub_bytes; cub::DeviceSelect::Flagged(cub_tmp, need, cnt, fl_a, a_idx, d_cnt, (int)P, st);
+    need = cub_bytes; cub::DeviceSelect::Flagged(cub_tmp, need, cnt, fl_u, u_idx, d_cnt + 1, (int)P, st);
+    c.launches += 3;
+    K = d2h(c, d_cnt);
+    U = P - K;
+    if (K) {
+      k_count_below<<<1, 1, 0, st>>>(a_idx, K, S, d_cnt + 2);
+      c.launches++;
+      out.singletons_aligned = d2h(c, d_cnt + 2);
+      out.n_reads_aligned = K - out.singletons_aligned;
+      // discovery order: (window position, strand, dict), then highest id first -> two stable sorts
+      uint32_t *krid = c.pool.dev<uint32_t>("en.krid", Pn), *krid2 = c.pool.dev<uint32_t>("en.krid2", Pn);
+      k_single_keys<<<grid_for(K, 256), 256, 0, st>>>(a_idx, K, best, pool_len, L, krid, ent_a);
+      need = 0;
+      cub::DeviceRadixSort::SortPairs(nullptr, need, krid, krid2, ent_a, ent_b, (int)K, 0, 32, st); cub_need(need);
+      need = cub_bytes; cub::DeviceRadixSort::SortPairs(cub_tmp, need, krid, krid2, ent_a, ent_b, (int)K, 0, 32, st);
+      k_single_keys2<<<grid_for(K, 256), 256, 0, st>>>(a_idx, ent_b, K, best, pool_len, L, skey_a);
+      const int kb = bits_for(seq_len) + 12;
+      need = 0;
+      cub::DeviceRadixSort::SortPairs(nullptr, need, skey_a, skey, ent_b, ent_a, (int)K, 0, kb, st); cub_need(need);
+      need = cub_bytes; cub::DeviceRadixSort::SortPairs(cub_tmp, need, skey_a, skey, ent_b, ent_a, (int)K, 0, kb, st);
+      c.launches += 2 + 4 + 4 + 2 * ((kb + 7) / 8);
+      ent = ent_a;
+    }
+  }
+
+  // ---- final order + streams --------------------------------------------------------------------------
+  const uint32_t MA = M + K;  // aligned reads
+  if ((uint64_t)MA + U != num_total) throw LimitError("encode: aligned + unaligned != cp.num_reads");
+  out.num_aligned = MA;
+  out.num_reads = num_total;
+  const uint32_t NT = num_total ? num_total : 1, MAn = MA ? MA : 1;
+  out.pos = c.pool.dev<uint64_t>("en.out_pos", MAn);
+  out.order = c.pool.dev<uint32_t>("en.out_order", NT);
+  out.lengths = c.pool.dev<uint16_t>("en.out_len", NT);
+  out.rev = c.pool.dev<uint8_t>("en.out_rev", MAn);
+  FinalArrays f{out.pos, out.order, out.lengths, out.rev, c.pool.dev<uint32_t>("en.f_src", MAn), c.pool.dev<uint8_t>("en.f_kind", MAn)};
+  if (M) { k_place_originals<<<grid_for(M, 256), 256, 0, st>>>(sorted_ap, perm, M, skey, K, ro.order, ro.rev, lens, nr.order, nr.num, f); c.launches++; }
+  if (K) { k_place_singles<<<grid_for(K, 256), 256, 0, st>>>(skey, ent, a_idx, K, sorted_ap, M, pool_len, pool_order, f); c.launches++; }
+
+  uint32_t *nmis = c.pool.dev<uint32_t>("en.nmis", MAn + 1);
+  uint64_t *noise_off = c.pool.dev<uint64_t>("en.noise_off", MAn + 1);
+  uint64_t total_noise = 0;
+  NoiseArgs na{};
+  na.reads = reads; na.pool_codes = pool_codes; na.pool_nflag = pool_nflag; na.W = W; na.cons = cons; na.f = f; na.m = MA;
+  na.nmis = nmis; na.noise_off = noise_off;
+  if (MA) {
+    SB_CUDA(cudaMemsetAsync(nmis + MA, 0, sizeof(uint32_t), st));
+    k_noise<false><<<grid_for((uint64_t)MA * 32, 256), 256, 0, st>>>(na);
+    size_t need = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, need, nmis, noise_off, (int)MA + 1, st); cub_need(need);
+    need = cub_bytes; cub::DeviceScan::ExclusiveSum(cub_tmp, need, nmis, noise_off, (int)MA + 1, st);
+    c.launches += 3;
+    total_noise = d2h(c, noise_off + MA);
+  }
+  out.num_noise = total_noise;
+  out.noise_bytes = total_noise + MA;
+  out.noise = c.pool.dev<uint8_t>("en.out_noise", out.noise_bytes + 1);
+  out.noisepos = c.pool.dev<uint16_t>("en.out_noisepos", total_noise + 1);
+  if (MA) {
+    na.noise = out.noise; na.noisepos = out.noisepos;
+    k_noise<true><<<grid_for((uint64_t)MA * 32, 256), 256, 0, st>>>(na);
+    c.launches++;
+  }
+
+  // ---- unaligned --------------------------------------------------------------------------------------
+  unsigned long long *rec_bytes = c.pool.dev<unsigned long long>("en.rec_bytes", (size_t)U + 1);
+  unsigned long long *rec_off = c.pool.dev<unsigned long long>("en.rec_off", (size_t)U + 1);
+  unsigned long long *ubases = c.pool.dev<unsigned long long>("en.ubases", (size_t)U + 1);
+  unsigned long long *ubases_off = c.pool.dev<unsigned long long>("en.ubases_off", (size_t)U + 1);
+  if (U) {
+    k_unaligned_sizes<<<grid_for((uint64_t)U + 1, 256), 256, 0, st>>>(u_idx, U, pool_len, rec_bytes, ubases);
+    size_t need = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, need, rec_bytes, rec_off, (int)U + 1, st); cub_need(need);
+    need = cub_bytes; cub::DeviceScan::ExclusiveSum(cub_tmp, need, rec_bytes, rec_off, (int)U + 1, st);
+    need = cub_bytes; cub::DeviceScan::ExclusiveSum(cub_tmp, need, ubases, ubases_off, (int)U + 1, st);
+    c.launches += 3;
+    out.unaligned_bytes = d2h(c, rec_off + U);
+    out.unaligned_len = d2h(c, ubases_off + U);
+  }
+  out.unaligned = c.pool.dev<uint8_t>("en.out_unaligned", out.unaligned_bytes + 1);
+  if (U) {
+    k_unaligned_write<<<grid_for(U, 128), 128, 0, st>>>(u_idx, U, pool_codes, pool_nflag, pool_len, pool_order, W, rec_off,
+                                                        out.unaligned, out.order + MA, out.lengths + MA);
+    c.launches++;
+  }
+
+  // ---- consensus packing --------------------------------------------------------------------------------
+  out.seq_packed = c.pool.dev<uint8_t>("en.out_seq", seq_len / 4 + 2);
+  if (seq_len) { k_pack_seq<<<grid_for((seq_len + 3) / 4, 256), 256, 0, st>>>(cons, seq_len, out.seq_packed); c.launches++; }
+  SB_CUDA(cudaGetLastError());
+}
+
+}  // namespace sb

@@ -1,0 +1,64 @@
+// kernels.cuh -- host-callable stages of the pipeline (each implemented in its own .cu).
+#pragma once
+#include "common.cuh"
+
+namespace sb {
+
+struct Ctx {
+  int device = 0;
+  int num_sms = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  BufferPool pool;
+  std::string err;
+  uint64_t launches = 0;  // kernels launched since the last reset (ours + CUB passes)
+};
+
+// ---- dict.cu : constructdictionary (bitset_util.h:74-221) ---------------------------------------
+struct DictBuild {
+  DictView view{};
+  uint32_t capacity = 0;
+  uint32_t numkeys = 0;
+  uint32_t dict_numreads = 0;
+  const uint64_t *sorted_keys = nullptr;   // [dict_numreads] keys in sorted order (device)
+  const uint32_t *bin_start_idx = nullptr; // [numkeys] index of each bin's first entry (device)
+};
+// reads: [n][W] 2-bit packed; nflag: optional [n][W] (bit 2j set where base j is N; such reads are
+// left out of the dictionary when the N falls inside the window).  tag names the pool buffers.
+void build_dictionary(Ctx &c, const uint64_t *reads, const uint16_t *lens, const uint64_t *nflag, uint32_t n, int W,
+                      int start, int end, const char *tag, DictBuild &out);
+
+// ---- reorder.cu : reorder<>() (reorder.h:320-641) ------------------------------------------------
+struct ReorderDev {
+  // aligned stream in chain order (device)
+  uint32_t *order = nullptr; uint8_t *flag = nullptr; int64_t *pos = nullptr; uint8_t *rev = nullptr;
+  uint64_t num = 0;
+  uint32_t *s_order = nullptr; uint64_t num_singletons = 0;
+  // stats
+  uint32_t num_chains = 0, unmatched = 0;
+  uint64_t rounds = 0, lost = 0, probes_issued = 0, probes_seq = 0, compares = 0;
+};
+void run_reorder(Ctx &c, const uint64_t *reads, const uint16_t *lens, uint32_t n, int L, uint32_t num_chains,
+                 const DictBuild dict[2], ReorderDev &out);
+
+// ---- encode.cu : encoder_main (encoder.h:572-633) ----------------------------------------------
+struct EncodeDev {
+  uint8_t *seq_packed = nullptr; uint64_t seq_len = 0;
+  uint64_t *pos = nullptr; uint8_t *noise = nullptr; uint64_t noise_bytes = 0;
+  uint16_t *noisepos = nullptr; uint64_t num_noise = 0;
+  uint8_t *rev = nullptr; uint32_t *order = nullptr; uint16_t *lengths = nullptr;
+  uint8_t *unaligned = nullptr; uint64_t unaligned_bytes = 0, unaligned_len = 0;
+  uint64_t num_aligned = 0, num_reads = 0;
+  uint32_t singletons_aligned = 0, n_reads_aligned = 0;
+};
+struct NReads {  // reads with N, parsed from input_N.dna on the host and uploaded
+  const uint64_t *codes = nullptr;  // [num][W] 2-bit, N stored as 00
+  const uint64_t *nflag = nullptr;  // [num][W] bit 2j set where base j is N
+  const uint16_t *lens = nullptr;
+  const uint32_t *order = nullptr;  // original index (read_order_N.bin)
+  uint32_t num = 0;
+};
+void run_encode(Ctx &c, const uint64_t *reads, const uint16_t *lens, uint32_t n, int L, const ReorderDev &ro,
+                const NReads &nr, uint32_t num_total, EncodeDev &out);
+
+}  // namespace sb

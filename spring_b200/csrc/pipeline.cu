@@ -1,0 +1,444 @@
+// pipeline.cu -- context, orchestration and the C ABI (include/spring_b200.h).
+#include <errno.h>
+#include <string.h>
+#include <sys/stat.h>
+#include <unistd.h>
+#include <algorithm>
+#include <cstddef>
+#include <fstream>
+#include "../../include/spring_b200.h"
+#include "kernels.cuh"
+
+using namespace sb;
+
+// cp.bin layout (reference src/util.h:30-51; offsets in SURVEY.md section 8b)
+static_assert(sizeof(spring_b200_cp) == 64, "compression_params is 64 bytes");
+static_assert(offsetof(spring_b200_cp, qvz_ratio) == 8, "cp layout");
+static_assert(offsetof(spring_b200_cp, num_reads) == 28, "cp layout");
+static_assert(offsetof(spring_b200_cp, num_reads_clean) == 32, "cp layout");
+static_assert(offsetof(spring_b200_cp, max_readlen) == 40, "cp layout");
+static_assert(offsetof(spring_b200_cp, paired_id_code) == 44, "cp layout");
+static_assert(offsetof(spring_b200_cp, num_reads_per_block) == 48, "cp layout");
+static_assert(offsetof(spring_b200_cp, num_thr) == 56, "cp layout");
+
+struct spring_b200_ctx {
+  Ctx c;
+  spring_b200_stats stats{};
+  EncodeDev last_enc{};
+  bool have_enc = false;
+  cudaEvent_t ev[8]{};
+};
+
+static thread_local std::string g_create_err;
+
+namespace {
+
+struct IoError : std::runtime_error {
+  explicit IoError(const std::string &m) : std::runtime_error(m) {}
+};
+struct ArgError : std::runtime_error {
+  explicit ArgError(const std::string &m) : std::runtime_error(m) {}
+};
+
+template <typename F> int guarded(spring_b200_ctx *ctx, F &&f) {
+  if (!ctx) return SPRING_B200_EINVAL;
+  try {
+    SB_CUDA(cudaSetDevice(ctx->c.device));
+    f();
+    ctx->c.err.clear();
+    return SPRING_B200_OK;
+  } catch (const ArgError &e) { ctx->c.err = e.what(); return SPRING_B200_EINVAL;
+  } catch (const IoError &e) { ctx->c.err = e.what(); return SPRING_B200_EIO;
+  } catch (const LimitError &e) { ctx->c.err = e.what(); return SPRING_B200_ELIMIT;
+  } catch (const CudaError &e) { ctx->c.err = e.what(); cudaGetLastError(); return SPRING_B200_ECUDA;
+  } catch (const std::exception &e) { ctx->c.err = e.what(); return SPRING_B200_ECUDA; }
+}
+
+void check_input(const spring_b200_input *in) {
+  if (!in) throw ArgError("null input");
+  if (in->max_readlen < 1 || in->max_readlen > (uint32_t)kMaxReadLen)
+    throw ArgError("Wrong bitset size. (max_readlen must be 1..511)");  // call_template_functions.cpp:61
+  if ((uint64_t)in->num_clean + in->num_n != in->num_reads) throw ArgError("num_clean + num_n != num_reads");
+  if (in->num_clean && (!in->reads || !in->lengths)) throw ArgError("null reads/lengths");
+  if (in->num_n && (!in->n_records || !in->order_n)) throw ArgError("null n_records/order_n");
+  if (in->num_reads >= 0x7FFFFFF0u) throw ArgError("too many reads for one GPU shard (>= 2^31)");
+}
+
+// input_N.dna records (util.cpp:322-374) -> 2-bit codes (N as 00) + N bit-plane, uploaded
+NReads upload_n_reads(Ctx &c, const spring_b200_input *in, int W) {
+  NReads nr{};
+  nr.num = in->num_n;
+  if (!in->num_n) return nr;
+  const uint32_t nn = in->num_n;
+  uint64_t *h_codes = c.pool.pin<uint64_t>("n.h_codes", (size_t)nn * W);
+  uint64_t *h_flag = c.pool.pin<uint64_t>("n.h_flag", (size_t)nn * W);
+  uint16_t *h_len = c.pool.pin<uint16_t>("n.h_len", nn);
+  uint32_t *h_order = c.pool.pin<uint32_t>("n.h_order", nn);
+  memset(h_codes, 0, sizeof(uint64_t) * (size_t)nn * W);
+  memset(h_flag, 0, sizeof(uint64_t) * (size_t)nn * W);
+  uint64_t off = 0;
+  for (uint32_t i = 0; i < nn; i++) {
+    if (off + 2 > in->n_record_bytes) throw ArgError("input_N.dna truncated");
+    uint16_t len; memcpy(&len, in->n_records + off, 2); off += 2;
+    if (len > in->max_readlen) throw ArgError("N read longer than max_readlen");
+    const uint64_t nb = ((uint64_t)len + 1) / 2;
+    if (off + nb > in->n_record_bytes) throw ArgError("input_N.dna truncated");
+    for (int j = 0; j < len; j++) {
+      const int v = (in->n_records[off + j / 2] >> (4 * (j & 1))) & 15;
+      if (v >= 4) h_flag[(size_t)i * W + (j >> 5)] |= 1ull << (2 * (j & 31));
+      else h_codes[(size_t)i * W + (j >> 5)] |= (uint64_t)v << (2 * (j & 31));
+    }
+    off += nb;
+    h_len[i] = len;
+    h_order[i] = in->order_n[i];
+    if (i && h_order[i] <= h_order[i - 1]) throw ArgError("read_order_N.bin must be strictly ascending");
+  }
+  uint64_t *d_codes = c.pool.dev<uint64_t>("n.codes", (size_t)nn * W);
+  uint64_t *d_flag = c.pool.dev<uint64_t>("n.flag", (size_t)nn * W);
+  uint16_t *d_len = c.pool.dev<uint16_t>("n.len", nn);
+  uint32_t *d_order = c.pool.dev<uint32_t>("n.order", nn);
+  SB_CUDA(cudaMemcpyAsync(d_codes, h_codes, sizeof(uint64_t) * (size_t)nn * W, cudaMemcpyHostToDevice, c.stream));
+  SB_CUDA(cudaMemcpyAsync(d_flag, h_flag, sizeof(uint64_t) * (size_t)nn * W, cudaMemcpyHostToDevice, c.stream));
+  SB_CUDA(cudaMemcpyAsync(d_len, h_len, sizeof(uint16_t) * nn, cudaMemcpyHostToDevice, c.stream));
+  SB_CUDA(cudaMemcpyAsync(d_order, h_order, sizeof(uint32_t) * nn, cudaMemcpyHostToDevice, c.stream));
+  nr.codes = d_codes; nr.nflag = d_flag; nr.lens = d_len; nr.order = d_order;
+  return nr;
+}
+
+struct DevInput { const uint64_t *reads; const uint16_t *lens; };
+
+DevInput upload_reads(Ctx &c, const spring_b200_input *in, int W) {
+  const size_t n = in->num_clean ? in->num_clean : 1;
+  uint64_t *d_reads = c.pool.dev<uint64_t>("in.reads", n * W);
+  uint16_t *d_lens = c.pool.dev<uint16_t>("in.lens", n);
+  if (in->num_clean) {
+    SB_CUDA(cudaMemcpyAsync(d_reads, in->reads, sizeof(uint64_t) * (size_t)in->num_clean * W, cudaMemcpyHostToDevice, c.stream));
+    SB_CUDA(cudaMemcpyAsync(d_lens, in->lengths, sizeof(uint16_t) * (size_t)in->num_clean, cudaMemcpyHostToDevice, c.stream));
+  }
+  return {d_reads, d_lens};
+}
+
+void rec(spring_b200_ctx *ctx, int i) { SB_CUDA(cudaEventRecord(ctx->ev[i], ctx->c.stream)); }
+float ms(spring_b200_ctx *ctx, int i, int j) {
+  float t = 0;
+  SB_CUDA(cudaEventElapsedTime(&t, ctx->ev[i], ctx->ev[j]));
+  return t;
+}
+
+// dictionaries + chains (reorder_main, reorder.h:732-786) on device-resident reads
+void reorder_on_device(spring_b200_ctx *ctx, DevInput d, const spring_b200_input *in, uint32_t num_chains, ReorderDev &ro) {
+  Ctx &c = ctx->c;
+  const int L = (int)in->max_readlen, W = words_for(L);
+  int s[2], e[2];
+  reorder_windows(L, s, e);
+  DictBuild dict[2];
+  rec(ctx, 1);
+  build_dictionary(c, d.reads, d.lens, nullptr, in->num_clean, W, s[0], e[0], "rd.dict0", dict[0]);
+  build_dictionary(c, d.reads, d.lens, nullptr, in->num_clean, W, s[1], e[1], "rd.dict1", dict[1]);
+  rec(ctx, 2);
+  run_reorder(c, d.reads, d.lens, in->num_clean, L, num_chains, dict, ro);
+  rec(ctx, 3);
+  spring_b200_stats &st = ctx->stats;
+  st.num_chains = ro.num_chains; st.unmatched = ro.unmatched; st.rounds = ro.rounds; st.lost_proposals = ro.lost;
+  st.probes_issued = ro.probes_issued; st.probes_seq = ro.probes_seq; st.compares = ro.compares;
+}
+
+void fill_scalars(const EncodeDev &e, spring_b200_streams *o) {
+  o->seq_len = e.seq_len; o->noise_bytes = e.noise_bytes; o->num_noise = e.num_noise;
+  o->unaligned_bytes = e.unaligned_bytes; o->unaligned_len = e.unaligned_len;
+  o->num_aligned = e.num_aligned; o->num_reads = e.num_reads;
+  o->singletons_aligned = e.singletons_aligned; o->n_reads_aligned = e.n_reads_aligned;
+}
+
+void fetch(spring_b200_ctx *ctx, spring_b200_streams *o) {
+  Ctx &c = ctx->c;
+  const EncodeDev &e = ctx->last_enc;
+  fill_scalars(e, o);
+  auto get = [&](const char *name, const void *dptr, size_t bytes) -> void * {
+    void *h = c.pool.pinned(name, bytes ? bytes : 1);
+    if (bytes) SB_CUDA(cudaMemcpyAsync(h, dptr, bytes, cudaMemcpyDeviceToHost, c.stream));
+    return h;
+  };
+  o->seq_packed = (const uint8_t *)get("out.seq", e.seq_packed, (e.seq_len + 3) / 4);
+  o->pos = (const uint64_t *)get("out.pos", e.pos, e.num_aligned * 8);
+  o->noise = (const uint8_t *)get("out.noise", e.noise, e.noise_bytes);
+  o->noisepos = (const uint16_t *)get("out.noisepos", e.noisepos, e.num_noise * 2);
+  o->rev = (const uint8_t *)get("out.rev", e.rev, e.num_aligned);
+  o->order = (const uint32_t *)get("out.order", e.order, e.num_reads * 4);
+  o->lengths = (const uint16_t *)get("out.lengths", e.lengths, e.num_reads * 2);
+  o->unaligned = (const uint8_t *)get("out.unaligned", e.unaligned, e.unaligned_bytes);
+  SB_CUDA(cudaStreamSynchronize(c.stream));
+}
+
+void run_all(spring_b200_ctx *ctx, const spring_b200_input *in, uint32_t num_chains, bool host_in, spring_b200_streams *out) {
+  check_input(in);
+  if (!out) throw ArgError("null output");
+  Ctx &c = ctx->c;
+  c.launches = 0;
+  ctx->stats = spring_b200_stats{};
+  const int L = (int)in->max_readlen, W = words_for(L);
+  rec(ctx, 0);
+  DevInput d = host_in ? upload_reads(c, in, W) : DevInput{in->reads, in->lengths};
+  NReads nr = upload_n_reads(c, in, W);
+  ReorderDev ro;
+  reorder_on_device(ctx, d, in, num_chains, ro);
+  run_encode(c, d.reads, d.lens, in->num_clean, L, ro, nr, in->num_reads, ctx->last_enc);
+  ctx->have_enc = true;
+  rec(ctx, 4);
+  memset(out, 0, sizeof(*out));
+  if (host_in) {
+    fetch(ctx, out);
+  } else {
+    const EncodeDev &e = ctx->last_enc;
+    fill_scalars(e, out);
+    out->seq_packed = e.seq_packed; out->pos = e.pos; out->noise = e.noise; out->noisepos = e.noisepos;
+    out->rev = e.rev; out->order = e.order; out->lengths = e.lengths; out->unaligned = e.unaligned;
+  }
+  rec(ctx, 5);
+  SB_CUDA(cudaStreamSynchronize(c.stream));
+  spring_b200_stats &st = ctx->stats;
+  st.ms_h2d = ms(ctx, 0, 1); st.ms_dict = ms(ctx, 1, 2); st.ms_chains = ms(ctx, 2, 3); st.ms_scatter = 0;
+  st.ms_encode = ms(ctx, 3, 4); st.ms_d2h = ms(ctx, 4, 5); st.ms_total = ms(ctx, 0, 5);
+  st.gpu_launches = c.launches;
+}
+
+// ---- files ---------------------------------------------------------------------------------------
+std::vector<uint8_t> slurp(const std::string &p, bool must_exist) {
+  std::ifstream f(p, std::ios::binary);
+  if (!f.is_open()) { if (must_exist) throw IoError("cannot open " + p); return {}; }
+  f.seekg(0, std::ios::end);
+  const std::streamoff n = f.tellg();
+  f.seekg(0);
+  std::vector<uint8_t> v((size_t)n);
+  if (n) f.read((char *)v.data(), n);
+  return v;
+}
+void spill(const std::string &p, const void *data, size_t n) {
+  std::ofstream f(p, std::ios::binary);
+  if (!f.is_open()) throw IoError("cannot create " + p);
+  if (n) f.write((const char *)data, (std::streamsize)n);
+  if (!f.good()) throw IoError("write failed: " + p);
+}
+
+// readDnaFile (reorder.h:222-244): records {u16 len; ceil(len/4) B} copied into bitset storage
+void parse_dna(const std::vector<uint8_t> &buf, uint32_t num, int W, uint32_t max_readlen, uint64_t *reads, uint16_t *lens,
+               const std::string &name) {
+  size_t off = 0;
+  for (uint32_t i = 0; i < num; i++) {
+    if (off + 2 > buf.size()) throw IoError(name + " truncated");
+    uint16_t len; memcpy(&len, buf.data() + off, 2); off += 2;
+    if (len > max_readlen) throw IoError(name + ": read longer than cp.max_readlen");
+    const size_t nb = ((size_t)len + 3) / 4;
+    if (off + nb > buf.size()) throw IoError(name + " truncated");
+    uint64_t *r = reads + (size_t)i * W;
+    for (int w = 0; w < W; w++) r[w] = 0;
+    memcpy(r, buf.data() + off, nb);
+    off += nb;
+    lens[i] = len;
+  }
+}
+
+void write_streams(const std::string &dir, const spring_b200_streams *s, int num_shards) {
+  if (num_shards < 1) throw ArgError("num_shards < 1");
+  // read_seq.bin.<t> + .tail (encoder.cpp:111-156, decompress.cpp:106-120): the consensus is cut
+  // into num_shards pieces at multiples of 4 bases; only the last piece can have a tail
+  static const char code2char[4] = {'A', 'C', 'G', 'T'};
+  const uint64_t full = s->seq_len / 4;
+  for (int t = 0; t < num_shards; t++) {
+    const uint64_t b0 = full * t / num_shards, b1 = full * (t + 1) / num_shards;
+    const std::string base = dir + "/read_seq.bin." + std::to_string(t);
+    spill(base, s->seq_packed + b0, b1 - b0);
+    std::string tail;
+    if (t == num_shards - 1)
+      for (uint64_t x = full * 4; x < s->seq_len; x++) tail.push_back(code2char[(s->seq_packed[x / 4] >> (2 * (x & 3))) & 3]);
+    spill(base + ".tail", tail.data(), tail.size());
+  }
+  spill(dir + "/read_pos.bin", s->pos, s->num_aligned * 8);
+  spill(dir + "/read_noise.txt", s->noise, s->noise_bytes);
+  spill(dir + "/read_noisepos.bin", s->noisepos, s->num_noise * 2);
+  spill(dir + "/read_rev.txt", s->rev, s->num_aligned);
+  spill(dir + "/read_order.bin", s->order, s->num_reads * 4);
+  spill(dir + "/read_lengths.bin", s->lengths, s->num_reads * 2);
+  spill(dir + "/read_unaligned.txt", s->unaligned, s->unaligned_bytes);
+  spill(dir + "/read_unaligned.txt.count", &s->unaligned_len, 8);
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *spring_b200_version(void) { return "spring_b200 0.1.0 (sm_100a)"; }
+
+int spring_b200_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+int spring_b200_create(int device, void *stream, spring_b200_ctx **out) {
+  if (!out) return SPRING_B200_EINVAL;
+  *out = nullptr;
+  int n = spring_b200_device_count();
+  if (n <= 0 || device < 0 || device >= n) {
+    g_create_err = "no usable CUDA device (spring_b200 has no CPU fallback)";
+    return SPRING_B200_ENODEV;
+  }
+  spring_b200_ctx *ctx = nullptr;
+  try {
+    SB_CUDA(cudaSetDevice(device));
+    ctx = new spring_b200_ctx();
+    ctx->c.device = device;
+    cudaDeviceProp prop;
+    SB_CUDA(cudaGetDeviceProperties(&prop, device));
+    ctx->c.num_sms = prop.multiProcessorCount;
+    if (!prop.cooperativeLaunch) throw CudaError("device lacks cooperative launch");
+    if (stream) { ctx->c.stream = (cudaStream_t)stream; ctx->c.own_stream = false; }
+    else { SB_CUDA(cudaStreamCreateWithFlags(&ctx->c.stream, cudaStreamNonBlocking)); ctx->c.own_stream = true; }
+    for (auto &e : ctx->ev) SB_CUDA(cudaEventCreate(&e));
+  } catch (const std::exception &e) {
+    g_create_err = e.what();
+    delete ctx;
+    return SPRING_B200_ECUDA;
+  }
+  *out = ctx;
+  return SPRING_B200_OK;
+}
+
+void spring_b200_destroy(spring_b200_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->c.device);
+  cudaStreamSynchronize(ctx->c.stream);
+  ctx->c.pool.release();
+  for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
+  if (ctx->c.own_stream) cudaStreamDestroy(ctx->c.stream);
+  delete ctx;
+}
+
+const char *spring_b200_last_error(const spring_b200_ctx *ctx) { return ctx ? ctx->c.err.c_str() : g_create_err.c_str(); }
+
+int spring_b200_get_stats(const spring_b200_ctx *ctx, spring_b200_stats *out) {
+  if (!ctx || !out) return SPRING_B200_EINVAL;
+  *out = ctx->stats;
+  return SPRING_B200_OK;
+}
+
+int spring_b200_reorder_encode(spring_b200_ctx *ctx, const spring_b200_input *in, uint32_t num_chains, spring_b200_streams *out) {
+  return guarded(ctx, [&] { run_all(ctx, in, num_chains, true, out); });
+}
+
+int spring_b200_reorder_encode_device(spring_b200_ctx *ctx, const spring_b200_input *in, uint32_t num_chains,
+                                      spring_b200_streams *out) {
+  return guarded(ctx, [&] { run_all(ctx, in, num_chains, false, out); });
+}
+
+int spring_b200_fetch_streams(spring_b200_ctx *ctx, spring_b200_streams *out) {
+  return guarded(ctx, [&] {
+    if (!ctx->have_enc || !out) throw ArgError("no streams to fetch");
+    fetch(ctx, out);
+  });
+}
+
+int spring_b200_build_dictionary(spring_b200_ctx *ctx, const spring_b200_input *in, int which, uint64_t *keys,
+                                 uint32_t *bin_start, uint32_t *read_id, uint32_t *num_keys, uint32_t *dict_numreads) {
+  return guarded(ctx, [&] {
+    check_input(in);
+    if (which < 0 || which > 1 || !keys || !bin_start || !read_id || !num_keys || !dict_numreads) throw ArgError("bad argument");
+    Ctx &c = ctx->c;
+    c.launches = 0;
+    const int L = (int)in->max_readlen, W = words_for(L);
+    DevInput d = upload_reads(c, in, W);
+    int s[2], e[2];
+    reorder_windows(L, s, e);
+    DictBuild db;
+    build_dictionary(c, d.reads, d.lens, nullptr, in->num_clean, W, s[which], e[which], "rd.dict0", db);
+    *num_keys = db.numkeys;
+    *dict_numreads = db.dict_numreads;
+    // unique keys = sorted_keys[bin_start_idx[k]]
+    std::vector<uint64_t> sk(db.dict_numreads);
+    std::vector<uint32_t> bsi(db.numkeys);
+    if (db.dict_numreads) {
+      SB_CUDA(cudaMemcpyAsync(sk.data(), db.sorted_keys, sizeof(uint64_t) * db.dict_numreads, cudaMemcpyDeviceToHost, c.stream));
+      SB_CUDA(cudaMemcpyAsync(read_id, db.view.read_id, sizeof(uint32_t) * db.dict_numreads, cudaMemcpyDeviceToHost, c.stream));
+    }
+    if (db.numkeys) SB_CUDA(cudaMemcpyAsync(bsi.data(), db.bin_start_idx, sizeof(uint32_t) * db.numkeys, cudaMemcpyDeviceToHost, c.stream));
+    SB_CUDA(cudaStreamSynchronize(c.stream));
+    for (uint32_t k = 0; k < db.numkeys; k++) { keys[k] = sk[bsi[k]]; bin_start[k] = bsi[k]; }
+    bin_start[db.numkeys] = db.dict_numreads;
+    ctx->stats = spring_b200_stats{};
+    ctx->stats.gpu_launches = c.launches;
+  });
+}
+
+int spring_b200_reorder(spring_b200_ctx *ctx, const spring_b200_input *in, uint32_t num_chains, spring_b200_reorder_out *out) {
+  return guarded(ctx, [&] {
+    check_input(in);
+    if (!out) throw ArgError("null output");
+    Ctx &c = ctx->c;
+    c.launches = 0;
+    ctx->stats = spring_b200_stats{};
+    const int W = words_for((int)in->max_readlen);
+    rec(ctx, 0);
+    DevInput d = upload_reads(c, in, W);
+    ReorderDev ro;
+    reorder_on_device(ctx, d, in, num_chains, ro);
+    const size_t m = ro.num, s = ro.num_singletons;
+    uint32_t *h_order = c.pool.pin<uint32_t>("ro.h_order", m + 1);
+    uint8_t *h_flag = c.pool.pin<uint8_t>("ro.h_flag", m + 1);
+    int64_t *h_pos = c.pool.pin<int64_t>("ro.h_pos", m + 1);
+    uint8_t *h_rev = c.pool.pin<uint8_t>("ro.h_rev", m + 1);
+    uint32_t *h_s = c.pool.pin<uint32_t>("ro.h_s", s + 1);
+    if (m) {
+      SB_CUDA(cudaMemcpyAsync(h_order, ro.order, m * 4, cudaMemcpyDeviceToHost, c.stream));
+      SB_CUDA(cudaMemcpyAsync(h_flag, ro.flag, m, cudaMemcpyDeviceToHost, c.stream));
+      SB_CUDA(cudaMemcpyAsync(h_pos, ro.pos, m * 8, cudaMemcpyDeviceToHost, c.stream));
+      SB_CUDA(cudaMemcpyAsync(h_rev, ro.rev, m, cudaMemcpyDeviceToHost, c.stream));
+    }
+    if (s) SB_CUDA(cudaMemcpyAsync(h_s, ro.s_order, s * 4, cudaMemcpyDeviceToHost, c.stream));
+    rec(ctx, 4);
+    SB_CUDA(cudaStreamSynchronize(c.stream));
+    out->order = h_order; out->flag = h_flag; out->pos = h_pos; out->rev = h_rev; out->num = m;
+    out->singleton_order = h_s; out->num_singletons = s;
+    ctx->stats.ms_h2d = ms(ctx, 0, 1); ctx->stats.ms_dict = ms(ctx, 1, 2); ctx->stats.ms_chains = ms(ctx, 2, 3);
+    ctx->stats.ms_total = ms(ctx, 0, 4);
+    ctx->stats.gpu_launches = c.launches;
+  });
+}
+
+int spring_b200_write_streams(spring_b200_ctx *ctx, const char *temp_dir, const spring_b200_streams *s, int num_shards) {
+  return guarded(ctx, [&] {
+    if (!temp_dir || !s) throw ArgError("null argument");
+    write_streams(temp_dir, s, num_shards);
+  });
+}
+
+int spring_b200_reorder_encode_files(spring_b200_ctx *ctx, const char *temp_dir, const spring_b200_cp *cp, uint32_t num_chains) {
+  return guarded(ctx, [&] {
+    if (!temp_dir || !cp) throw ArgError("null argument");
+    if (cp->long_flag) throw ArgError("long mode has no reorder/encode stage (spring.cpp:150)");
+    const std::string dir(temp_dir);
+    const uint32_t L = cp->max_readlen;
+    if (L < 1 || L > (uint32_t)kMaxReadLen) throw ArgError("Wrong bitset size.");
+    const int W = words_for((int)L);
+    const uint32_t n0 = cp->num_reads_clean[0], n1 = cp->num_reads_clean[1], n = n0 + n1;
+    Ctx &c = ctx->c;
+    uint64_t *h_reads = c.pool.pin<uint64_t>("file.reads", (size_t)(n ? n : 1) * W);
+    uint16_t *h_lens = c.pool.pin<uint16_t>("file.lens", n ? n : 1);
+    const std::string f1 = dir + "/input_clean_1.dna", f2 = dir + "/input_clean_2.dna";
+    const std::string fn = dir + "/input_N.dna", fo = dir + "/read_order_N.bin";
+    { auto b = slurp(f1, true); parse_dna(b, n0, W, L, h_reads, h_lens, "input_clean_1.dna"); }
+    if (cp->paired_end) { auto b = slurp(f2, true); parse_dna(b, n1, W, L, h_reads + (size_t)n0 * W, h_lens + n0, "input_clean_2.dna"); }
+    std::vector<uint8_t> nrec = slurp(fn, false), nord = slurp(fo, false);
+    spring_b200_input in{};
+    in.reads = h_reads; in.lengths = h_lens; in.num_clean = n; in.max_readlen = L;
+    in.n_records = nrec.data(); in.n_record_bytes = nrec.size();
+    in.order_n = (const uint32_t *)nord.data(); in.num_n = cp->num_reads - n; in.num_reads = cp->num_reads;
+    if (nord.size() != (size_t)in.num_n * 4) throw IoError("read_order_N.bin size does not match cp.num_reads");
+    spring_b200_streams s{};
+    run_all(ctx, &in, num_chains, true, &s);
+    // inputs are consumed, as in the reference (reorder.h:232,241; encoder.h:606; encoder.cpp:218)
+    unlink(f1.c_str()); unlink(f2.c_str()); unlink(fn.c_str()); unlink(fo.c_str());
+    write_streams(dir, &s, cp->num_thr > 0 ? cp->num_thr : 1);
+  });
+}
+
+}  // extern "C"

@@ -1,0 +1,531 @@
+// reorder.cu -- the greedy overlap search (reference src/reorder.h:320-641) as one persistent,
+// cooperative sm_100a kernel.
+//
+// Mapping.  One warp = one "chain" = one reference OpenMP thread (reorder.h:351): it owns a
+// consensus window (per-column base counts in shared memory, ref / revref bitsets), and repeats
+// { search the dictionaries for an overlapping read, claim it, fold it into the consensus }.
+//   * the reference tries shift 0,1,2,... one after the other, 4 dictionary probes per shift
+//     (search_match, reorder.h:246-318).  Here the 32 lanes take 32 consecutive shifts at once:
+//     each lane extracts its 4 window keys from the shared-memory bitsets, issues its 4 slot loads
+//     back to back (128 independent 16 B loads in flight per warp) and the warp then walks the hits
+//     in the reference's priority order (shift, forward before reverse, dict 0 before dict 1,
+//     highest read id first) so the read it picks is the one the sequential search would pick.
+//   * candidates of a bin are verified 32 at a time: lane t loads candidate t's packed words,
+//     XORs them with the shifted reference, masks the overlap and popcounts (THRESH_REORDER = 4).
+//   * updaterefcount (reorder.h:110-220): the four count-shift cases collapse to one remap
+//     "new column i <- old column i+delta" done 32 columns per step; majority bases are turned
+//     back into the 2-bit bitsets with two ballots per 32 columns.
+//
+// Scheduling.  The reference is racy (try-locks) and non-reproducible for more than one thread.
+// Chains here run in lock step: phase A every chain searches against the claim bitmap as of the
+// round start and proposes one read (atomicMin of its chain id into winner[rid]); grid barrier;
+// phase B the winner claims and updates, losers retry; grid barrier.  The result is a pure
+// function of (input, num_chains) and is restated exactly by oracle/spring_oracle.c, which for
+// one chain is the reference's single-thread execution.
+//
+// Memory traffic per claimed read (L = 150): ~128 slot probes x 32 B sectors per round, one
+// read_id sector + one or two 40 B candidate rows per hit, 17 B of records; all other state stays
+// in shared memory / registers for the life of the kernel.
+#include <cooperative_groups.h>
+#include <cub/cub.cuh>
+#include "kernels.cuh"
+
+namespace sb {
+
+namespace {
+
+constexpr unsigned FULL = 0xFFFFFFFFu;
+constexpr int kWarpsPerBlock = 8;
+enum { ST_SEARCH = 0, ST_NEWREAD = 1, ST_DONE = 2 };
+enum { CTR_UNMATCHED = 0, CTR_ROUNDS, CTR_LOST, CTR_PROBES_ISSUED, CTR_PROBES_SEQ, CTR_COMPARES, CTR_ABORT, CTR_N };
+
+struct ChainArgs {
+  const uint64_t *reads; const uint16_t *lens; uint32_t N; int L, W, Lp, maxshift;
+  DictView dict[2];
+  uint32_t *claimed;   // bitmap, one bit per read
+  uint32_t *winner;    // [N], kNoWinner until proposed
+  uint32_t *rec_chain; uint32_t *rec_k; int64_t *rec_pos; uint8_t *rec_meta;
+  uint32_t *chain_aligned; uint32_t *chain_single;
+  uint32_t num_chains, per;
+  unsigned long long *barrier; int *active; unsigned long long *ctr;
+  unsigned long long max_rounds;
+};
+
+__device__ __forceinline__ bool is_claimed(const uint32_t *claimed, uint32_t rid) {
+  return (__ldcg(claimed + (rid >> 5)) >> (rid & 31)) & 1u;
+}
+
+__device__ __forceinline__ void grid_barrier(unsigned long long *ctr, unsigned long long &target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    target += gridDim.x;
+    __threadfence();
+    atomicAdd(ctr, 1ull);
+    while (*(volatile unsigned long long *)ctr < target) { __nanosleep(20); }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+// Fold the read staged in curw (cur_len bases; rev: use its reverse complement) into the window.
+// new column i takes old column i+delta when that lies in [0, old_len), else starts from zero;
+// the read covers new columns [cs, cs+cur_len).  Then majority -> ref, RC(ref) -> revref.
+//
+// fold > 0 reproduces a quirk of the reference that the output depends on: in the reverse case
+// where the new read covers the whole window (reorder.h:159-165) the counts are moved UP by
+// fold = cur_len - shift - old_len columns with an ascending in-place loop, so a source column
+// that was already rewritten is read again: column i = q*fold + r ends up as
+// old[r] + sum_{t=1..q} e(read base at t*fold + r) rather than old[i - fold] + e(read base at i).
+__device__ void update_ref(uint64_t *ref, uint64_t *revref, const uint64_t *curw, uint32_t *cnt, int Lp, int W, int lane,
+                           int old_len, int delta, int cs, int cur_len, bool rev, int new_len, int fold = 0) {
+  const int nchunks = (new_len + 31) >> 5;
+  for (int cc = 0; cc < nchunks; cc++) {
+    const int ck = delta >= 0 ? cc : nchunks - 1 - cc;  // move direction decides the safe order
+    const int i = (ck << 5) + lane;
+    const bool in = i < new_len;
+    const int src = i + delta;
+    uint32_t v0 = 0, v1 = 0, v2 = 0, v3 = 0;
+    if (in && src >= 0 && src < old_len) {
+      if (fold > 0) {
+        const int r = i % fold, q = i / fold;
+        v0 = cnt[r]; v1 = cnt[Lp + r]; v2 = cnt[2 * Lp + r]; v3 = cnt[3 * Lp + r];
+        for (int t = 1; t < q; t++) {  // the t == q term is the read's own base at column i, added below
+          const int b = 3 - base_code(curw, cur_len - 1 - (t * fold + r));
+          if (b == 0) v0++; else if (b == 2) v1++; else if (b == 3) v2++; else v3++;
+        }
+      } else {
+        v0 = cnt[src]; v1 = cnt[Lp + src]; v2 = cnt[2 * Lp + src]; v3 = cnt[3 * Lp + src];
+      }
+    }
+    __syncwarp();
+    int code = 0;
+    if (in) {
+      const int ci = i - cs;
+      if (ci >= 0 && ci < cur_len) {
+        const int b = rev ? 3 - base_code(curw, cur_len - 1 - ci) : base_code(curw, ci);
+        // count rows are A,C,T,G (reorder.h:120-123); 2-bit codes are A0 G1 C2 T3
+        if (b == 0) v0++; else if (b == 2) v1++; else if (b == 3) v2++; else v3++;
+      }
+      cnt[i] = v0; cnt[Lp + i] = v1; cnt[2 * Lp + i] = v2; cnt[3 * Lp + i] = v3;
+      uint32_t mx = 0; int ind = 0;  // first strict maximum (reorder.h:204-212)
+      if (v0 > mx) { mx = v0; ind = 0; }
+      if (v1 > mx) { mx = v1; ind = 1; }
+      if (v2 > mx) { mx = v2; ind = 2; }
+      if (v3 > mx) { mx = v3; ind = 3; }
+      code = ind == 0 ? 0 : ind == 1 ? 2 : ind == 2 ? 3 : 1;
+    }
+    const unsigned b0 = __ballot_sync(FULL, code & 1), b1 = __ballot_sync(FULL, code & 2);
+    if (lane == 0) ref[ck] = spread_bits(b0) | (spread_bits(b1) << 1);
+    __syncwarp();
+  }
+  if (lane >= nchunks && lane < W) ref[lane] = 0ull;
+  __syncwarp();
+  for (int ck = 0; ck < nchunks; ck++) {
+    const int i = (ck << 5) + lane;
+    const int code = i < new_len ? 3 - base_code(ref, new_len - 1 - i) : 0;
+    const unsigned b0 = __ballot_sync(FULL, code & 1), b1 = __ballot_sync(FULL, code & 2);
+    if (lane == 0) revref[ck] = spread_bits(b0) | (spread_bits(b1) << 1);
+  }
+  if (lane >= nchunks && lane < W) revref[lane] = 0ull;
+  __syncwarp();
+}
+
+// Verify the live reads of one bin, highest id first, at most MAX_SEARCH of them (reorder.h:287-311).
+__device__ bool scan_bin(const ChainArgs &a, const DictView &d, uint32_t bs, uint32_t bc, const uint64_t *refsm, bool rev,
+                         int s, int ref_len, int lane, uint32_t &rid_out, unsigned long long &compares) {
+  const int W = a.W;
+  int live_before = 0;
+  for (uint32_t off = 0; off < bc; off += 32) {
+    const uint32_t t = off + lane;
+    uint32_t rid = 0;
+    bool live = false;
+    if (t < bc) { rid = __ldg(d.read_id + bs + (bc - 1 - t)); live = !is_claimed(a.claimed, rid); }
+    const unsigned lm = __ballot_sync(FULL, live);
+    const int rank = live_before + __popc(lm & ((1u << lane) - 1u));
+    const bool ev = live && rank < kMaxSearch;
+    bool pass = false;
+    if (ev) {
+      const int len = __ldg(a.lens + rid);
+      int lo, hi;
+      if (!rev) { lo = 0; hi = 2 * min(ref_len - s, len); }
+      else { lo = 2 * s; hi = 2 * min(ref_len + s, len); }
+      const uint64_t *cand = a.reads + (size_t)rid * W;
+      int h = 0;
+      for (int i = 0; i < W; i++) {
+        const uint64_t m = range_mask(i, lo, hi);
+        if (m) {
+          const uint64_t r = rev ? shl_word(refsm, W, i, 2 * s) : shr_word(refsm, W, i, 2 * s);
+          h += __popcll((r ^ __ldg(cand + i)) & m);
+        }
+      }
+      pass = h <= kThreshReorder;
+    }
+    const unsigned em = __ballot_sync(FULL, ev), pm = __ballot_sync(FULL, pass);
+    if (pm) {
+      const int wl = __ffs(pm) - 1;
+      rid_out = __shfl_sync(FULL, rid, wl);
+      compares += __popc(em & ((2u << wl) - 1u));
+      return true;
+    }
+    compares += __popc(em);
+    live_before += __popc(lm);
+    if (live_before >= kMaxSearch) break;
+  }
+  return false;
+}
+
+// Phase A for a searching chain: the first read, in the reference's order, that matches.
+__device__ bool chain_search(const ChainArgs &a, const uint64_t *ref, const uint64_t *revref, int ref_len, int lane,
+                             uint32_t &prop_rid, int &prop_shift, int &prop_rev, unsigned long long &probes_issued,
+                             unsigned long long &probes_seq, unsigned long long &compares) {
+  const int W = a.W;
+  for (int base = 0; base < a.maxshift; base += 32) {
+    const int s = base + lane;
+    const bool sv = s < a.maxshift;
+    uint64_t key[4];
+    uint32_t h[4];
+    DictSlot sl[4];
+    unsigned okmask = 0;
+#pragma unroll
+    for (int kind = 0; kind < 4; kind++) {  // kind = 2*rev + dict
+      const int rev = kind >> 1;
+      const DictView &d = a.dict[kind & 1];
+      bool ok = sv;
+      if (!rev) ok = ok && !(d.end + s >= ref_len);                          // reorder.h:264-265
+      else ok = ok && !(d.end >= ref_len + s || d.start <= s);               // reorder.h:266-267
+      if (ok) {
+        okmask |= 1u << kind;
+        key[kind] = rev ? extract_bits(revref, W, 2 * (d.start - s), d.key_bits)
+                        : extract_bits(ref, W, 2 * (d.start + s), d.key_bits);
+        h[kind] = (uint32_t)mix64(key[kind]) & d.slot_mask;
+        sl[kind] = load_slot(d.slots + h[kind]);
+      }
+    }
+    unsigned pend = 0;
+    uint32_t bstart[4], bcount[4];
+#pragma unroll
+    for (int kind = 0; kind < 4; kind++) {
+      bstart[kind] = 0; bcount[kind] = 0;
+      if (okmask & (1u << kind)) {
+        const DictView &d = a.dict[kind & 1];
+        while (sl[kind].count != 0 && sl[kind].key != key[kind]) {
+          h[kind] = (h[kind] + 1) & d.slot_mask;
+          sl[kind] = load_slot(d.slots + h[kind]);
+        }
+        if (sl[kind].count) { bstart[kind] = sl[kind].start; bcount[kind] = sl[kind].count; pend |= 1u << kind; }
+      }
+    }
+    probes_issued += __popc(okmask);
+    int found_p = -1;
+    for (;;) {
+      const int myp = pend ? (s << 2) + (__ffs(pend) - 1) : 0x7FFFFFFF;
+      const int p = __reduce_min_sync(FULL, myp);
+      if (p == 0x7FFFFFFF) break;
+      const int owner = (p >> 2) - base, kind = p & 3;
+      uint32_t mb = kind == 0 ? bstart[0] : kind == 1 ? bstart[1] : kind == 2 ? bstart[2] : bstart[3];
+      uint32_t mc = kind == 0 ? bcount[0] : kind == 1 ? bcount[1] : kind == 2 ? bcount[2] : bcount[3];
+      mb = __shfl_sync(FULL, mb, owner);
+      mc = __shfl_sync(FULL, mc, owner);
+      const int rev = kind >> 1, ps = p >> 2;
+      uint32_t rid;
+      if (scan_bin(a, a.dict[kind & 1], mb, mc, rev ? revref : ref, rev, ps, ref_len, lane, rid, compares)) {
+        prop_rid = rid; prop_shift = ps; prop_rev = rev; found_p = p;
+        break;
+      }
+      if (lane == owner) pend &= ~(1u << kind);
+    }
+    // lookups a sequential search would have issued: all of this batch, or those up to the hit
+    unsigned seqmask = okmask;
+    if (found_p >= 0) {
+      const int fs = found_p >> 2, fk = found_p & 3;
+      if (s > fs) seqmask = 0;
+      else if (s == fs) seqmask &= (2u << fk) - 1u;
+    }
+    probes_seq += __reduce_add_sync(FULL, (unsigned)__popc(seqmask));
+    if (found_p >= 0) return true;
+  }
+  return false;
+}
+
+// Highest unclaimed read in [lo, cursor] (reorder.h:576-592), 32 bitmap words per step.
+__device__ bool find_unclaimed(const uint32_t *claimed, long long lo, long long cursor, int lane, uint32_t &rid) {
+  if (cursor < lo) return false;
+  const long long whi = cursor >> 5, wlo = lo >> 5;
+  for (long long wbase = whi; wbase >= wlo; wbase -= 32) {
+    const long long wi = wbase - lane;
+    uint32_t fb = 0;
+    if (wi >= wlo) {
+      fb = ~__ldcg(claimed + wi);
+      if (wi == whi) { const int top = (int)(cursor & 31); if (top < 31) fb &= (1u << (top + 1)) - 1u; }
+      if (wi == wlo) fb &= ~0u << (int)(lo & 31);
+    }
+    const unsigned m = __ballot_sync(FULL, fb != 0);
+    if (m) {
+      const int wl = __ffs(m) - 1;
+      const uint32_t f = __shfl_sync(FULL, fb, wl);
+      rid = (uint32_t)((wbase - wl) * 32 + (31 - __clz(f)));
+      return true;
+    }
+  }
+  return false;
+}
+
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) k_chains(ChainArgs a) {
+  extern __shared__ uint64_t smem[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const uint32_t cid = blockIdx.x * kWarpsPerBlock + wib;
+  const int W = a.W, Lp = a.Lp;
+  const size_t per_chain = 3 * (size_t)W + 2 * (size_t)Lp;  // uint64 words: ref, revref, cur, 4*Lp u32 counts
+  uint64_t *ref = smem + wib * per_chain, *revref = ref + W, *curw = revref + W;
+  uint32_t *cnt = reinterpret_cast<uint32_t *>(curw + W);
+
+  int state = cid < a.num_chains ? ST_SEARCH : ST_DONE;
+  int ref_len = 0, prev_unmatched = 0, left_search = 0, iter_started = 0, stop_searching = 0;
+  long long ref_pos = 0, cur_read_pos = 0, cursor = -1, slice_lo = 0;
+  uint32_t first_rid = 0, prev = 0, num_reads_thr = 0, num_unmatched_1m = 0, n_aligned = 0, n_single = 0;
+  unsigned long long c_unmatched = 0, c_lost = 0, c_issued = 0, c_seq = 0, c_cmp = 0, target = 0, round = 0;
+
+  auto stage_read = [&](uint32_t rid) {
+    if (lane < W) curw[lane] = __ldg(a.reads + (size_t)rid * W + lane);
+    __syncwarp();
+  };
+  auto new_contig = [&](uint32_t rid) {  // updaterefcount(..., resetcount = true, rev = false) + reorder.h:426-430,:601-612
+    stage_read(rid);
+    const int len = __ldg(a.lens + rid);
+    update_ref(ref, revref, curw, cnt, Lp, W, lane, 0, 0, 0, len, false, len);
+    ref_len = len; ref_pos = 0; cur_read_pos = 0;
+    prev_unmatched = 1; first_rid = rid; prev = rid; left_search = 0;
+    state = ST_SEARCH; iter_started = 0;
+  };
+
+  if (state == ST_SEARCH) {  // reorder.h:405-431
+    const uint32_t first = cid * a.per;
+    slice_lo = first;
+    cursor = cid == a.num_chains - 1 ? (long long)a.N - 1 : (long long)(cid + 1) * a.per - 1;
+    if (lane == 0) atomicOr(a.claimed + (first >> 5), 1u << (first & 31));
+    c_unmatched++;
+    new_contig(first);
+  }
+  grid_barrier(a.barrier, target);
+
+  for (;;) {
+    // ---------------- phase A: search / pick against the round-start claim state -------------
+    bool has_prop = false;
+    uint32_t prop_rid = 0;
+    int prop_shift = 0, prop_rev = 0;
+    if (state == ST_SEARCH) {
+      if (!iter_started) {  // loop top, reorder.h:433-439
+        if (num_reads_thr % kStopWindow == 0) {
+          if (num_unmatched_1m > kStopUnmatched) stop_searching = 1;
+          num_unmatched_1m = 0;
+        }
+        num_reads_thr++;
+        iter_started = 1;
+      }
+      if (!stop_searching)
+        has_prop = chain_search(a, ref, revref, ref_len, lane, prop_rid, prop_shift, prop_rev, c_issued, c_seq, c_cmp);
+    } else if (state == ST_NEWREAD) {
+      has_prop = find_unclaimed(a.claimed, slice_lo, cursor, lane, prop_rid);
+    }
+    if (has_prop && lane == 0) atomicMin(a.winner + prop_rid, cid);
+    grid_barrier(a.barrier, target);
+
+    // ---------------- phase B: winners claim and update ----------------------------------------
+    if (state == ST_SEARCH) {
+      if (has_prop) {
+        if (__ldcg(a.winner + prop_rid) == cid) {
+          const uint32_t k = prop_rid;
+          if (lane == 0) atomicOr(a.claimed + (k >> 5), 1u << (k & 31));
+          stage_read(k);
+          const int len = __ldg(a.lens + k), shift = prop_shift, old = ref_len;
+          int delta, cs, nl, fold = 0;
+          if (!prop_rev) { delta = shift; cs = 0; nl = max(old - shift, len); }                 // reorder.h:144-156
+          else if (len - shift >= old) { fold = len - shift - old; delta = -fold; cs = 0; nl = len; }  // :159-174
+          else if (old + shift <= a.L) { delta = 0; cs = old - len + shift; nl = old + shift; } // :175-184
+          else { delta = old + shift - a.L; cs = a.L - len; nl = a.L; }                         // :185-199
+          update_ref(ref, revref, curw, cnt, Lp, W, lane, old, delta, cs, len, prop_rev != 0, nl, fold);
+          ref_len = nl;
+          if (!prop_rev) {  // reorder.h:490-497
+            if (!left_search) { cur_read_pos = ref_pos + shift; ref_pos = cur_read_pos; }
+            else { cur_read_pos = ref_pos + old - shift - len; ref_pos = ref_pos + old - shift - nl; }
+          } else {          // reorder.h:528-535
+            if (!left_search) { cur_read_pos = ref_pos + old + shift - len; ref_pos = ref_pos + old + shift - nl; }
+            else { cur_read_pos = ref_pos - shift; ref_pos = cur_read_pos; }
+          }
+          if (lane == 0) {
+            if (prev_unmatched) {  // the contig's first read is written lazily, reorder.h:498-507
+              a.rec_chain[prev] = cid; a.rec_k[prev] = n_aligned; a.rec_pos[prev] = 0; a.rec_meta[prev] = 0;
+            }
+            const uint32_t kk = n_aligned + (prev_unmatched ? 1u : 0u);
+            const int is_r = prop_rev ? !left_search : left_search;  // reorder.h:508, :546
+            a.rec_chain[k] = cid; a.rec_k[k] = kk; a.rec_pos[k] = cur_read_pos; a.rec_meta[k] = (uint8_t)(2 | (is_r ? 1 : 0));
+          }
+          n_aligned += prev_unmatched ? 2u : 1u;
+          prev_unmatched = 0;
+          iter_started = 0;
+        } else {
+          c_lost++;
+        }
+      } else {  // no match, reorder.h:559-615
+        num_unmatched_1m++;
+        if (!left_search) {
+          left_search = 1;
+          stage_read(first_rid);
+          const int len = __ldg(a.lens + first_rid);
+          update_ref(ref, revref, curw, cnt, Lp, W, lane, 0, 0, 0, len, true, len);
+          ref_len = len; ref_pos = 0; cur_read_pos = 0;
+          iter_started = 0;
+        } else {
+          left_search = 0;
+          state = ST_NEWREAD;
+        }
+      }
+    } else if (state == ST_NEWREAD) {
+      if (has_prop) {
+        if (__ldcg(a.winner + prop_rid) == cid) {
+          const uint32_t j = prop_rid;
+          if (lane == 0) {
+            atomicOr(a.claimed + (j >> 5), 1u << (j & 31));
+            if (prev_unmatched) { a.rec_chain[prev] = cid; a.rec_k[prev] = n_single; a.rec_meta[prev] = 4; }
+          }
+          if (prev_unmatched) n_single++;
+          cursor = (long long)j - 1;
+          c_unmatched++;
+          new_contig(j);
+        } else {
+          c_lost++;
+        }
+      } else {
+        if (prev_unmatched) {
+          if (lane == 0) { a.rec_chain[prev] = cid; a.rec_k[prev] = n_single; a.rec_meta[prev] = 4; }
+          n_single++;
+        }
+        state = ST_DONE;
+        if (lane == 0) atomicSub(a.active, 1);
+      }
+    }
+    round++;
+    grid_barrier(a.barrier, target);
+    if (__ldcg(a.active) <= 0) break;
+    if (round >= a.max_rounds) {  // watchdog: uniform across the grid
+      if (cid == 0 && lane == 0) a.ctr[CTR_ABORT] = 1ull;
+      break;
+    }
+  }
+  if (lane == 0) {
+    a.chain_aligned[cid] = n_aligned;
+    a.chain_single[cid] = n_single;
+    atomicAdd(a.ctr + CTR_UNMATCHED, c_unmatched);
+    atomicAdd(a.ctr + CTR_LOST, c_lost);
+    atomicAdd(a.ctr + CTR_PROBES_ISSUED, c_issued);
+    atomicAdd(a.ctr + CTR_PROBES_SEQ, c_seq);
+    atomicAdd(a.ctr + CTR_COMPARES, c_cmp);
+    if (cid == 0) a.ctr[CTR_ROUNDS] = round;
+  }
+}
+
+// Chain logs -> one stream, chain after chain (what the merge of per-thread files gives,
+// encoder.h:386-423): record k of chain c lands at offset[c] + k.
+__global__ void k_scatter_records(const uint32_t *__restrict__ rec_chain, const uint32_t *__restrict__ rec_k,
+                                  const int64_t *__restrict__ rec_pos, const uint8_t *__restrict__ rec_meta, uint32_t n,
+                                  const uint32_t *__restrict__ off_aligned, const uint32_t *__restrict__ off_single,
+                                  uint32_t *order, uint8_t *flag, int64_t *pos, uint8_t *rev, uint32_t *s_order) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint8_t m = rec_meta[i];
+  const uint32_t c = rec_chain[i], k = rec_k[i];
+  if (m & 4) {
+    s_order[off_single[c] + k] = i;
+  } else {
+    const uint32_t o = off_aligned[c] + k;
+    order[o] = i;
+    flag[o] = (m >> 1) & 1;
+    pos[o] = rec_pos[i];
+    rev[o] = (m & 1) ? 'r' : 'd';
+  }
+}
+
+}  // namespace
+
+void run_reorder(Ctx &c, const uint64_t *reads, const uint16_t *lens, uint32_t n, int L, uint32_t num_chains,
+                 const DictBuild dict[2], ReorderDev &out) {
+  cudaStream_t st = c.stream;
+  out = ReorderDev{};
+  const int W = words_for(L), Lp = (L + 31) & ~31;
+  const uint32_t nn = n ? n : 1;
+  out.order = c.pool.dev<uint32_t>("ro.order", nn);
+  out.flag = c.pool.dev<uint8_t>("ro.flag", nn);
+  out.pos = c.pool.dev<int64_t>("ro.pos", nn);
+  out.rev = c.pool.dev<uint8_t>("ro.rev", nn);
+  out.s_order = c.pool.dev<uint32_t>("ro.s_order", nn);
+  if (n == 0) return;
+
+  const size_t smem = kWarpsPerBlock * (3 * (size_t)W + 2 * (size_t)Lp) * sizeof(uint64_t);
+  SB_CUDA(cudaFuncSetAttribute(k_chains, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  SB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_chains, kWarpsPerBlock * 32, smem));
+  if (per_sm < 1) throw CudaError("k_chains does not fit on an SM");
+  const uint32_t max_chains = (uint32_t)per_sm * c.num_sms * kWarpsPerBlock;
+  uint32_t C = num_chains;
+  if (C == 0) { C = n / 256; if (C < 1) C = 1; if (C > max_chains) C = max_chains; }  // auto: >= 256 reads per slice
+  if (C > max_chains) C = max_chains;
+  if (C > n) C = n;
+  const uint32_t grid = (C + kWarpsPerBlock - 1) / kWarpsPerBlock;
+  out.num_chains = C;
+
+  ChainArgs a{};
+  a.reads = reads; a.lens = lens; a.N = n; a.L = L; a.W = W; a.Lp = Lp; a.maxshift = L / 2;
+  a.dict[0] = dict[0].view; a.dict[1] = dict[1].view;
+  const size_t bm_words = ((size_t)n + 31) / 32;
+  a.claimed = c.pool.dev<uint32_t>("ro.claimed", bm_words);
+  a.winner = c.pool.dev<uint32_t>("ro.winner", nn);
+  a.rec_chain = c.pool.dev<uint32_t>("ro.rec_chain", nn);
+  a.rec_k = c.pool.dev<uint32_t>("ro.rec_k", nn);
+  a.rec_pos = c.pool.dev<int64_t>("ro.rec_pos", nn);
+  a.rec_meta = c.pool.dev<uint8_t>("ro.rec_meta", nn);
+  const uint32_t nslots = grid * kWarpsPerBlock;
+  a.chain_aligned = c.pool.dev<uint32_t>("ro.chain_aligned", nslots + 1);
+  a.chain_single = c.pool.dev<uint32_t>("ro.chain_single", nslots + 1);
+  uint32_t *off_aligned = c.pool.dev<uint32_t>("ro.off_aligned", nslots + 1);
+  uint32_t *off_single = c.pool.dev<uint32_t>("ro.off_single", nslots + 1);
+  unsigned long long *sync = c.pool.dev<unsigned long long>("ro.sync", 2 + CTR_N);
+  a.barrier = sync; a.active = reinterpret_cast<int *>(sync + 1); a.ctr = sync + 2;
+  a.num_chains = C; a.per = n / C;
+  a.max_rounds = 8ull * n + 4096ull;
+  SB_CUDA(cudaMemsetAsync(a.claimed, 0, bm_words * sizeof(uint32_t), st));
+  SB_CUDA(cudaMemsetAsync(a.winner, 0xFF, (size_t)n * sizeof(uint32_t), st));
+  SB_CUDA(cudaMemsetAsync(sync, 0, (2 + CTR_N) * sizeof(unsigned long long), st));
+  SB_CUDA(cudaMemsetAsync(a.chain_aligned, 0, (nslots + 1) * sizeof(uint32_t), st));
+  SB_CUDA(cudaMemsetAsync(a.chain_single, 0, (nslots + 1) * sizeof(uint32_t), st));
+  int active = (int)C;
+  SB_CUDA(cudaMemcpyAsync(a.active, &active, sizeof(int), cudaMemcpyHostToDevice, st));
+  void *args[] = {&a};
+  SB_CUDA(cudaLaunchCooperativeKernel((void *)k_chains, dim3(grid), dim3(kWarpsPerBlock * 32), args, smem, st));
+  c.launches++;
+
+  size_t need = 0, tmp_bytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, need, a.chain_aligned, off_aligned, (int)nslots + 1, st); tmp_bytes = need;
+  void *tmp = c.pool.device("ro.cubtmp", tmp_bytes);
+  need = tmp_bytes; cub::DeviceScan::ExclusiveSum(tmp, need, a.chain_aligned, off_aligned, (int)nslots + 1, st);
+  need = tmp_bytes; cub::DeviceScan::ExclusiveSum(tmp, need, a.chain_single, off_single, (int)nslots + 1, st);
+  c.launches += 2;
+  k_scatter_records<<<(n + 255) / 256, 256, 0, st>>>(a.rec_chain, a.rec_k, a.rec_pos, a.rec_meta, n, off_aligned, off_single,
+                                                     out.order, out.flag, out.pos, out.rev, out.s_order);
+  c.launches++;
+  unsigned long long *h = c.pool.pin<unsigned long long>("ro.hsync", CTR_N + 2);
+  SB_CUDA(cudaMemcpyAsync(h, a.ctr, CTR_N * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+  uint32_t *htot = reinterpret_cast<uint32_t *>(h + CTR_N);
+  SB_CUDA(cudaMemcpyAsync(htot, off_aligned + nslots, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  SB_CUDA(cudaMemcpyAsync(htot + 1, off_single + nslots, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  SB_CUDA(cudaStreamSynchronize(st));
+  SB_CUDA(cudaGetLastError());
+  if (h[CTR_ABORT]) throw LimitError("reorder: watchdog hit (round limit) -- chain kernel did not converge");
+  out.num = htot[0];
+  out.num_singletons = htot[1];
+  if (out.num + out.num_singletons != n) throw LimitError("reorder: records do not cover all reads");
+  out.unmatched = (uint32_t)h[CTR_UNMATCHED];
+  out.rounds = h[CTR_ROUNDS]; out.lost = h[CTR_LOST];
+  out.probes_issued = h[CTR_PROBES_ISSUED]; out.probes_seq = h[CTR_PROBES_SEQ]; out.compares = h[CTR_COMPARES];
+}
+
+}  // namespace sb

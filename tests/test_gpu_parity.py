@@ -1,0 +1,125 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle."""
+import os
+import tempfile
+
+import numpy as np
+import pytest
+
+from helpers import CASES, assert_streams_equal, check_roundtrip, make_input
+from oracle import pyoracle as po
+from spring_b200 import capi, dnaio
+
+pytestmark = pytest.mark.gpu
+
+CHAINS = (1, 5, 64)
+
+
+@pytest.mark.parametrize("name", ["se150", "var250", "short40", "long511"])
+def test_dictionary_matches_oracle(ctx, name):
+    """constructdictionary: same unique keys, same bins, read ids ascending per bin (bit-exact)."""
+    hp = make_input(**CASES[name])
+    for which in (0, 1):
+        k, b, r = ctx.build_dictionary(hp.packed, hp.lengths, hp.max_readlen, which)
+        ok, ob, orr = po.reorder_dict(hp.packed, hp.lengths, hp.max_readlen, which)
+        assert (k == ok).all() and (b == ob).all() and (r == orr).all()
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_reorder_stream_matches_oracle(ctx, name):
+    """reorder<>(): order / flag / pos / rev / singleton lists bit-exact for 1 and many chains."""
+    hp = make_input(**CASES[name])
+    for chains in CHAINS:
+        order, flag, pos, rev, s_order = ctx.reorder(hp.packed, hp.lengths, hp.max_readlen, chains)
+        st = ctx.stats()
+        ro = po.reorder(hp.packed, hp.lengths, hp.max_readlen, st["num_chains"])
+        assert (order == ro.order).all() and (flag == ro.flag).all() and (pos == ro.pos).all()
+        assert (rev == ro.rc).all() and (s_order == ro.s_order).all()
+        assert st["unmatched"] == ro.counters["unmatched"]
+        assert st["rounds"] == ro.counters["rounds"]
+        assert st["probes_seq"] == ro.counters["probes"]      # sequential-equivalent lookups
+        assert st["compares"] == ro.counters["compares"]
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_streams_match_oracle(ctx, name):
+    """call_reorder + call_encoder: every output stream bit-exact against the oracle."""
+    hp = make_input(**CASES[name])
+    for chains in CHAINS:
+        got = ctx.reorder_encode(hp.packed, hp.lengths, hp.max_readlen, hp.n_records, hp.order_n, hp.num_reads, chains)
+        c = ctx.stats()["num_chains"]
+        _, er = po.reorder_encode(hp.packed, hp.lengths, hp.max_readlen, hp.n_records, hp.order_n, hp.num_reads, c)
+        assert_streams_equal(got, er, f"{name} chains={c}")
+        assert got.matched_s == er.matched_s and got.matched_N == er.matched_N
+        sp, tail = er.packed_seq()
+        assert got.seq_packed[: len(sp)].tobytes() == sp
+
+
+def test_golden_vectors(ctx):
+    """Streams produced by the reference itself at -t 1 (tests/golden/make_golden.py)."""
+    import json
+    gdir = os.path.join(os.path.dirname(__file__), "golden")
+    for fn in sorted(f for f in os.listdir(gdir) if f.endswith(".npz")):
+        g = np.load(os.path.join(gdir, fn))
+        meta = json.loads(bytes(g["meta"]).decode())
+        got = ctx.reorder_encode(g["packed"], g["lengths"], meta["max_readlen"], bytes(g["n_records"]), g["order_n"],
+                                 meta["num_reads"], 1)
+        for f in ("seq", "pos", "noise", "noisepos", "rc", "order", "lengths", "unaligned"):
+            assert (np.asarray(getattr(got, f)) == g["ref_" + f]).all(), f"{fn}: {f}"
+        assert got.unaligned_len == meta["unaligned_len"]
+
+
+def test_auto_chains_roundtrip_and_determinism(ctx):
+    """Default chain count (as many as co-reside): decode == input, and two runs are identical."""
+    hp = make_input(num_reads=200000, read_len=150, seed=21, n_frac=0.002)
+    a = ctx.reorder_encode(hp.packed, hp.lengths, hp.max_readlen, hp.n_records, hp.order_n, hp.num_reads, 0)
+    st = ctx.stats()
+    assert st["num_chains"] > 64
+    check_roundtrip(a, hp, po.decode)
+    b = ctx.reorder_encode(hp.packed, hp.lengths, hp.max_readlen, hp.n_records, hp.order_n, hp.num_reads, 0)
+    assert_streams_equal(a, b, "determinism")
+    # match rate stays in the reference's range: oracle with one chain is the reference at -t 1
+    ro = po.reorder(hp.packed, hp.lengths, hp.max_readlen, 1)
+    assert st["unmatched"] < 1.5 * ro.counters["unmatched"] + st["num_chains"]
+
+
+def test_edge_cases(ctx):
+    # empty input
+    got = ctx.reorder_encode(np.zeros((0, 4), np.uint64), np.zeros(0, np.uint16), 100)
+    assert len(got.order) == 0 and got.seq_len == 0
+    # one read
+    p, l = dnaio.seqs_to_packed([b"ACGTACGTAC"], 10)
+    got = ctx.reorder_encode(p, l, 10)
+    assert list(got.order) == [0] and got.num_aligned == 0 and po.decode(got) == [b"ACGTACGTAC"]
+    # only reads with N
+    nrec = dnaio.write_dnaN_records([b"ACGNNACGT", b"NNNN"])
+    got = ctx.reorder_encode(np.zeros((0, 1), np.uint64), np.zeros(0, np.uint16), 9, nrec, np.array([0, 1], np.uint32), 2)
+    assert po.decode(got) == [b"ACGNNACGT", b"NNNN"]
+    # identical reads (every shift-0 candidate passes), zero-length read among them
+    seqs = [b"ACGTTGCAACGTTGCAACGTTGCAACGTTGCAACGTTGCAACGT"] * 50 + [b""]
+    p, l = dnaio.seqs_to_packed(seqs, 44)
+    got = ctx.reorder_encode(p, l, 44, num_chains=3)
+    _, er = po.reorder_encode(p, l, 44, num_chains=ctx.stats()["num_chains"])
+    assert_streams_equal(got, er, "identical reads")
+    # bad arguments are refused with the reference's message
+    with pytest.raises(capi.SpringB200Error) as e:
+        ctx.reorder_encode(np.zeros((1, 16), np.uint64), np.array([600], np.uint16), 600)
+    assert e.value.code == -1 and "Wrong bitset size" in str(e.value)
+
+
+def test_file_level_drop_in(ctx):
+    """spring_b200_reorder_encode_files on a temp_dir laid out by preprocess: same files the
+    reference's call_reorder + call_encoder leave, inputs consumed."""
+    hp = make_input(**CASES["pe100_illumina"])
+    _, er = po.reorder_encode(hp.packed, hp.lengths, hp.max_readlen, hp.n_records, hp.order_n, hp.num_reads, 1)
+    with tempfile.TemporaryDirectory() as d:
+        cpy = dnaio.write_hotpath_inputs(d, hp.packed, hp.lengths, max_readlen=hp.max_readlen, n_seqs=hp.n_seqs,
+                                         order_n=hp.order_n, num_reads=hp.num_reads, paired_split=hp.num_clean[0], num_thr=3)
+        os.remove(os.path.join(d, "cp_in.bin"))
+        cp = capi.CP.from_buffer_copy(cpy.pack())
+        ctx.reorder_encode_files(d, cp, 1)
+        left = sorted(os.listdir(d))
+        assert "input_clean_1.dna" not in left and "input_N.dna" not in left and "read_order_N.bin" not in left
+        for t in range(3):
+            assert f"read_seq.bin.{t}" in left and f"read_seq.bin.{t}.tail" in left
+        got = po.load_reference_streams(d, 3)
+    assert_streams_equal(got, er, "file-level")

@@ -113,6 +113,9 @@ typedef struct spring_b200_stats {
   uint64_t compares;         /* Hamming evaluations counted as the sequential scan would */
   uint64_t gpu_launches;     /* kernels launched by the last call (ours + CUB) */
   float ms_h2d, ms_dict, ms_chains, ms_scatter, ms_encode, ms_d2h, ms_total;
+  float ms_chain_kernel;     /* k_chains alone (CUDA events around the cooperative launch) */
+  uint64_t cyc_search, cyc_wait_a, cyc_commit, cyc_wait_b; /* SM cycles summed over blocks, per phase of a round */
+  uint64_t slot_probes;      /* lookups that passed the L2-resident key filter and read the slot table in HBM */
 } spring_b200_stats;
 
 /* ---- context ---------------------------------------------------------------------------- */
@@ -147,6 +150,13 @@ int spring_b200_build_dictionary(spring_b200_ctx *ctx, const spring_b200_input *
 /* reorder<>() alone (src/reorder.h:320-641), host inputs, host outputs owned by the context. */
 int spring_b200_reorder(spring_b200_ctx *ctx, const spring_b200_input *in, uint32_t num_chains,
                         spring_b200_reorder_out *out);
+
+/* ---- multi-GPU partitioning ------------------------------------------------------------------ */
+/* DEVICE pointers.  bucket[i] = hash(strand-canonical 16-mer minimizer of read i) mod num_buckets:
+ * the owner GPU of read i.  No reference counterpart (the reference is single-process,
+ * SURVEY.md section 2.4); see DESIGN.md "multi-GPU". */
+int spring_b200_bucket_reads(spring_b200_ctx *ctx, const uint64_t *reads, const uint16_t *lengths, uint32_t num_reads,
+                             uint32_t max_readlen, uint32_t num_buckets, uint32_t *bucket);
 
 /* ---- file-level drop-in -------------------------------------------------------------------- */
 /* Replaces call_reorder + call_encoder (src/call_template_functions.cpp:9-143) on a temp_dir:

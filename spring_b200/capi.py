@@ -19,6 +19,7 @@ EXPORTS = [
     "spring_b200_last_error", "spring_b200_get_stats", "spring_b200_reorder_encode",
     "spring_b200_reorder_encode_device", "spring_b200_fetch_streams", "spring_b200_build_dictionary",
     "spring_b200_reorder", "spring_b200_reorder_encode_files", "spring_b200_write_streams",
+    "spring_b200_bucket_reads",
 ]
 
 
@@ -63,7 +64,9 @@ class Stats(C.Structure):
                 ("lost_proposals", C.c_uint64), ("probes_issued", C.c_uint64), ("probes_seq", C.c_uint64),
                 ("compares", C.c_uint64), ("gpu_launches", C.c_uint64), ("ms_h2d", C.c_float), ("ms_dict", C.c_float),
                 ("ms_chains", C.c_float), ("ms_scatter", C.c_float), ("ms_encode", C.c_float), ("ms_d2h", C.c_float),
-                ("ms_total", C.c_float)]
+                ("ms_total", C.c_float), ("ms_chain_kernel", C.c_float), ("cyc_search", C.c_uint64),
+                ("cyc_wait_a", C.c_uint64), ("cyc_commit", C.c_uint64), ("cyc_wait_b", C.c_uint64),
+                ("slot_probes", C.c_uint64)]
 
     def as_dict(self) -> dict:
         return {f: getattr(self, f) for f, _ in self._fields_}
@@ -92,6 +95,7 @@ def load():
                                                      C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
         lib.spring_b200_reorder.argtypes = [C.c_void_p, C.POINTER(Input), C.c_uint32, C.POINTER(ReorderOut)]
         lib.spring_b200_reorder_encode_files.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(CP), C.c_uint32]
+        lib.spring_b200_bucket_reads.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
         lib.spring_b200_write_streams.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(Streams), C.c_int]
         _lib = lib
     return _lib
@@ -211,6 +215,11 @@ class Context:
         self._check(fn(self._h, C.byref(inp), num_chains, C.byref(s)))
         return s
 
+    def fetch_streams_raw(self) -> Streams:
+        s = Streams()
+        self._check(self._lib.spring_b200_fetch_streams(self._h, C.byref(s)))
+        return s
+
     def fetch_streams(self) -> StreamsResult:
         s = Streams()
         self._check(self._lib.spring_b200_fetch_streams(self._h, C.byref(s)))
@@ -235,6 +244,10 @@ class Context:
         return (_view(o.order, o.num, np.uint32).copy(), _view(o.flag, o.num, np.uint8).copy(),
                 _view(o.pos, o.num, np.int64).copy(), _view(o.rev, o.num, np.uint8).copy(),
                 _view(o.singleton_order, o.num_singletons, np.uint32).copy())
+
+    def bucket_reads(self, reads_ptr: int, lengths_ptr: int, num_reads: int, max_readlen: int, num_buckets: int, out_ptr: int) -> None:
+        """Device pointers; out: uint32[num_reads] owner bucket of every read (multi-GPU partitioning)."""
+        self._check(self._lib.spring_b200_bucket_reads(self._h, reads_ptr, lengths_ptr, num_reads, max_readlen, num_buckets, out_ptr))
 
     # ---- files ---------------------------------------------------------------------------------
     def reorder_encode_files(self, temp_dir: str, cp: CP, num_chains: int = 0) -> None:

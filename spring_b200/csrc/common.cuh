@@ -38,21 +38,32 @@ struct LimitError : std::runtime_error {
 
 // ---- dictionary in HBM ------------------------------------------------------------------------
 // One open-addressing slot per unique key.  16 B so a probe is one aligned uint4 load (one 32 B
-// sector); count == 0 marks an empty slot.  Replaces BooPHF + startpos[] (bitset_util.h:22-41):
-// the key is stored, so the reference's "verify against the first read of the bin" step
-// (reorder.h:282-285) is folded into the probe.
-struct __align__(16) DictSlot {
+// sector).  Replaces BooPHF + startpos[] + empty_bin[] (bitset_util.h:22-41): the key is stored,
+// so the reference's "verify against the first read of the bin" step (reorder.h:282-285) is folded
+// into the probe, and `live` -- decremented when a read of the bin is claimed -- plays the role of
+// bbhashdict::remove / empty_bin (bitset_util.cpp:37-63): a bin whose reads are all gone is skipped
+// by the probe itself, without touching the bin.
+// 32 B = one sector: the bin's size and its three highest read ids ride along with the key, so a
+// hit on a bin of <= 3 reads (almost all of them) needs no access to bins[] at all.
+struct __align__(32) DictSlot {
   uint64_t key;
-  uint32_t start;  // first index of the bin in read_id[]
-  uint32_t count;  // reads in the bin (0 = empty slot)
+  uint32_t start1;  // 1 + index of the bin header in bins[]; 0 = empty slot
+  uint32_t live;    // reads of the bin not yet claimed
+  uint32_t count;   // reads in the bin
+  uint32_t rid[3];  // the bin's highest ids, descending (bins[start1 .. start1+2])
 };
 
+// bins[]: per unique key {count, read ids in DESCENDING order}: the reference scans a bin from its
+// highest id down (reorder.h:287-288), so a scan is a forward walk from the header.
 struct DictView {
-  const DictSlot *slots;
-  uint32_t slot_mask;       // capacity - 1 (power of two)
-  const uint32_t *read_id;  // ascending inside a bin
-  int start, end;           // base window [start, end]
-  int key_bits;             // bits per base * (end - start + 1)
+  DictSlot *slots;
+  uint32_t slot_mask;            // capacity - 1 (power of two)
+  const uint32_t *bins;
+  const uint32_t *slot_of_read;  // [n] slot index holding read i's key, 0xFFFFFFFF if the read is not indexed
+  const uint32_t *filter;        // one bit per hash bucket: set iff some key hashes there (kept L2-resident)
+  uint32_t filter_mask;          // number of filter bits - 1 (power of two)
+  int start, end;                // base window [start, end]
+  int key_bits;                  // bits per base * (end - start + 1)
 };
 
 __host__ __device__ inline uint64_t mix64(uint64_t x) {  // murmur3 finalizer
@@ -116,21 +127,33 @@ __device__ __forceinline__ uint64_t spread_bits(uint32_t x) {
 }
 __device__ __forceinline__ int base_code(const uint64_t *w, int j) { return (int)((w[j >> 5] >> (2 * (j & 31))) & 3ull); }
 
+// L2 (.cg) load: `live` is updated by other SMs between rounds, L1 must not serve it
 __device__ __forceinline__ DictSlot load_slot(const DictSlot *p) {
-  uint4 v = __ldg(reinterpret_cast<const uint4 *>(p));
+  const uint4 v = __ldcg(reinterpret_cast<const uint4 *>(p));
+  const uint4 w = __ldcg(reinterpret_cast<const uint4 *>(p) + 1);
   DictSlot s;
   s.key = (uint64_t)v.x | ((uint64_t)v.y << 32);
-  s.start = v.z;
-  s.count = v.w;
+  s.start1 = v.z;
+  s.live = v.w;
+  s.count = w.x; s.rid[0] = w.y; s.rid[1] = w.z; s.rid[2] = w.w;
   return s;
 }
-// exact lookup: returns count (0 = absent) and sets start
-__device__ __forceinline__ uint32_t dict_find(const DictView &d, uint64_t key, uint32_t &start) {
+__device__ __forceinline__ DictSlot load_slot_head(const DictSlot *p) {  // key / start1 / live only
+  const uint4 v = __ldcg(reinterpret_cast<const uint4 *>(p));
+  DictSlot s;
+  s.key = (uint64_t)v.x | ((uint64_t)v.y << 32);
+  s.start1 = v.z;
+  s.live = v.w;
+  s.count = 0; s.rid[0] = s.rid[1] = s.rid[2] = 0;
+  return s;
+}
+// exact lookup in a dictionary nobody is updating: header index of the bin, or -1
+__device__ __forceinline__ long long dict_find(const DictView &d, uint64_t key) {
   uint32_t h = (uint32_t)mix64(key) & d.slot_mask;
   for (;;) {
-    DictSlot s = load_slot(d.slots + h);
-    if (s.count == 0) return 0;
-    if (s.key == key) { start = s.start; return s.count; }
+    DictSlot s = load_slot_head(d.slots + h);
+    if (s.start1 == 0) return -1;
+    if (s.key == key) return (long long)s.start1 - 1;
     h = (h + 1) & d.slot_mask;
   }
 }

@@ -216,12 +216,15 @@ __global__ void k_align_singletons(AlignArgs a) {
     uint64_t key = 0;
     if (!rev) for (int t = d.start; t <= d.end; t++) key |= (uint64_t)win[t] << (2 * (t - d.start));
     else for (int t = d.start; t <= d.end; t++) key |= (uint64_t)(3 - win[L - 1 - t]) << (2 * (t - d.start));
-    uint32_t bs, bc = dict_find(d, key, bs);
-    if (!bc) continue;
+    const uint32_t fi = (uint32_t)(mix64(key) >> 32) & d.filter_mask;
+    if (!((__ldg(d.filter + (fi >> 5)) >> (fi & 31)) & 1u)) continue;
+    const long long hdr = dict_find(d, key);
+    if (hdr < 0) continue;
+    const uint32_t bc = d.bins[hdr];
     const unsigned long long prio = (j << 2) | (unsigned long long)(rev << 1) | (unsigned long long)l;
     const uint32_t lim = bc < (uint32_t)kMaxSearch ? bc : (uint32_t)kMaxSearch;
     for (uint32_t t = 0; t < lim; t++) {
-      const uint32_t rid = d.read_id[bs + bc - 1 - t];
+      const uint32_t rid = d.bins[hdr + 1 + t];
       const int len = a.pool_len[rid];
       const uint64_t *r = a.pool_codes + (size_t)rid * W;
       int h = (int)a.pool_ncount[rid];

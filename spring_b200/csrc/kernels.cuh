@@ -12,6 +12,7 @@ struct Ctx {
   BufferPool pool;
   std::string err;
   uint64_t launches = 0;  // kernels launched since the last reset (ours + CUB passes)
+  cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;  // around the chain kernel
 };
 
 // ---- dict.cu : constructdictionary (bitset_util.h:74-221) ---------------------------------------
@@ -22,6 +23,7 @@ struct DictBuild {
   uint32_t dict_numreads = 0;
   const uint64_t *sorted_keys = nullptr;   // [dict_numreads] keys in sorted order (device)
   const uint32_t *bin_start_idx = nullptr; // [numkeys] index of each bin's first entry (device)
+  const uint32_t *sorted_rids = nullptr;   // [dict_numreads] read ids in (key, id) order (device)
 };
 // reads: [n][W] 2-bit packed; nflag: optional [n][W] (bit 2j set where base j is N; such reads are
 // left out of the dictionary when the N falls inside the window).  tag names the pool buffers.
@@ -37,6 +39,9 @@ struct ReorderDev {
   // stats
   uint32_t num_chains = 0, unmatched = 0;
   uint64_t rounds = 0, lost = 0, probes_issued = 0, probes_seq = 0, compares = 0;
+  float ms_kernel = 0;
+  uint64_t slot_probes = 0;  // probes that passed the key filter and went to the slot table
+  uint64_t cyc[4] = {0, 0, 0, 0};  // SM cycles summed over chains: search, wait A, commit, wait B
 };
 void run_reorder(Ctx &c, const uint64_t *reads, const uint16_t *lens, uint32_t n, int L, uint32_t num_chains,
                  const DictBuild dict[2], ReorderDev &out);
@@ -60,5 +65,8 @@ struct NReads {  // reads with N, parsed from input_N.dna on the host and upload
 };
 void run_encode(Ctx &c, const uint64_t *reads, const uint16_t *lens, uint32_t n, int L, const ReorderDev &ro,
                 const NReads &nr, uint32_t num_total, EncodeDev &out);
+
+// ---- bucket.cu : multi-GPU partitioning key --------------------------------------------------
+void bucket_reads(Ctx &c, const uint64_t *reads, const uint16_t *lens, uint32_t n, int L, uint32_t num_buckets, uint32_t *bucket);
 
 }  // namespace sb

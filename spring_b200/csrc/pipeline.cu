@@ -141,6 +141,8 @@ void reorder_on_device(spring_b200_ctx *ctx, DevInput d, const spring_b200_input
   spring_b200_stats &st = ctx->stats;
   st.num_chains = ro.num_chains; st.unmatched = ro.unmatched; st.rounds = ro.rounds; st.lost_proposals = ro.lost;
   st.probes_issued = ro.probes_issued; st.probes_seq = ro.probes_seq; st.compares = ro.compares;
+  st.ms_chain_kernel = ro.ms_kernel; st.slot_probes = ro.slot_probes;
+  st.cyc_search = ro.cyc[0]; st.cyc_wait_a = ro.cyc[1]; st.cyc_commit = ro.cyc[2]; st.cyc_wait_b = ro.cyc[3];
 }
 
 void fill_scalars(const EncodeDev &e, spring_b200_streams *o) {
@@ -309,6 +311,7 @@ void spring_b200_destroy(spring_b200_ctx *ctx) {
   cudaSetDevice(ctx->c.device);
   cudaStreamSynchronize(ctx->c.stream);
   ctx->c.pool.release();
+  if (ctx->c.ev_k0) { cudaEventDestroy(ctx->c.ev_k0); cudaEventDestroy(ctx->c.ev_k1); }
   for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
   if (ctx->c.own_stream) cudaStreamDestroy(ctx->c.stream);
   delete ctx;
@@ -358,7 +361,7 @@ int spring_b200_build_dictionary(spring_b200_ctx *ctx, const spring_b200_input *
     std::vector<uint32_t> bsi(db.numkeys);
     if (db.dict_numreads) {
       SB_CUDA(cudaMemcpyAsync(sk.data(), db.sorted_keys, sizeof(uint64_t) * db.dict_numreads, cudaMemcpyDeviceToHost, c.stream));
-      SB_CUDA(cudaMemcpyAsync(read_id, db.view.read_id, sizeof(uint32_t) * db.dict_numreads, cudaMemcpyDeviceToHost, c.stream));
+      SB_CUDA(cudaMemcpyAsync(read_id, db.sorted_rids, sizeof(uint32_t) * db.dict_numreads, cudaMemcpyDeviceToHost, c.stream));
     }
     if (db.numkeys) SB_CUDA(cudaMemcpyAsync(bsi.data(), db.bin_start_idx, sizeof(uint32_t) * db.numkeys, cudaMemcpyDeviceToHost, c.stream));
     SB_CUDA(cudaStreamSynchronize(c.stream));
@@ -401,6 +404,15 @@ int spring_b200_reorder(spring_b200_ctx *ctx, const spring_b200_input *in, uint3
     ctx->stats.ms_h2d = ms(ctx, 0, 1); ctx->stats.ms_dict = ms(ctx, 1, 2); ctx->stats.ms_chains = ms(ctx, 2, 3);
     ctx->stats.ms_total = ms(ctx, 0, 4);
     ctx->stats.gpu_launches = c.launches;
+  });
+}
+
+int spring_b200_bucket_reads(spring_b200_ctx *ctx, const uint64_t *reads, const uint16_t *lengths, uint32_t num_reads,
+                             uint32_t max_readlen, uint32_t num_buckets, uint32_t *bucket) {
+  return guarded(ctx, [&] {
+    if (max_readlen < 1 || max_readlen > (uint32_t)kMaxReadLen || !num_buckets) throw ArgError("bad argument");
+    if (num_reads && (!reads || !lengths || !bucket)) throw ArgError("null pointer");
+    bucket_reads(ctx->c, reads, lengths, num_reads, (int)max_readlen, num_buckets, bucket);
   });
 }
 

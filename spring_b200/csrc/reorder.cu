@@ -37,7 +37,8 @@ namespace {
 constexpr unsigned FULL = 0xFFFFFFFFu;
 constexpr int kWarpsPerBlock = 8;
 enum { ST_SEARCH = 0, ST_NEWREAD = 1, ST_DONE = 2 };
-enum { CTR_UNMATCHED = 0, CTR_ROUNDS, CTR_LOST, CTR_PROBES_ISSUED, CTR_PROBES_SEQ, CTR_COMPARES, CTR_ABORT, CTR_N };
+enum { CTR_UNMATCHED = 0, CTR_ROUNDS, CTR_LOST, CTR_PROBES_ISSUED, CTR_PROBES_SEQ, CTR_COMPARES, CTR_ABORT,
+       CTR_CYC_SEARCH, CTR_CYC_WAIT_A, CTR_CYC_COMMIT, CTR_CYC_WAIT_B, CTR_SLOT_PROBES, CTR_N };
 
 struct ChainArgs {
   const uint64_t *reads; const uint16_t *lens; uint32_t N; int L, W, Lp, maxshift;
@@ -55,14 +56,21 @@ __device__ __forceinline__ bool is_claimed(const uint32_t *claimed, uint32_t rid
   return (__ldcg(claimed + (rid >> 5)) >> (rid & 31)) & 1u;
 }
 
-__device__ __forceinline__ void grid_barrier(unsigned long long *ctr, unsigned long long &target) {
+// work/wait: SM cycles thread 0 of the block spent between barriers / spinning in this one
+__device__ __forceinline__ void grid_barrier(unsigned long long *ctr, unsigned long long &target, long long &t_last,
+                                             unsigned long long &work, unsigned long long &wait) {
   __syncthreads();
   if (threadIdx.x == 0) {
+    const long long t_arr = clock64();
+    work += t_arr - t_last;
     target += gridDim.x;
-    __threadfence();
-    atomicAdd(ctr, 1ull);
-    while (*(volatile unsigned long long *)ctr < target) { __nanosleep(20); }
-    __threadfence();
+    unsigned long long v;
+    asm volatile("red.release.gpu.global.add.u64 [%0], 1;" ::"l"(ctr) : "memory");
+    do {
+      asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(ctr) : "memory");
+    } while (v < target);
+    t_last = clock64();
+    wait += t_last - t_arr;
   }
   __syncthreads();
 }
@@ -76,7 +84,7 @@ __device__ __forceinline__ void grid_barrier(unsigned long long *ctr, unsigned l
 // fold = cur_len - shift - old_len columns with an ascending in-place loop, so a source column
 // that was already rewritten is read again: column i = q*fold + r ends up as
 // old[r] + sum_{t=1..q} e(read base at t*fold + r) rather than old[i - fold] + e(read base at i).
-__device__ void update_ref(uint64_t *ref, uint64_t *revref, const uint64_t *curw, uint32_t *cnt, int Lp, int W, int lane,
+__device__ void update_ref(uint64_t *ref, uint64_t *revref, const uint64_t *curw, uint4 *cnt, int W, int lane,
                            int old_len, int delta, int cs, int cur_len, bool rev, int new_len, int fold = 0) {
   const int nchunks = (new_len + 31) >> 5;
   for (int cc = 0; cc < nchunks; cc++) {
@@ -88,13 +96,15 @@ __device__ void update_ref(uint64_t *ref, uint64_t *revref, const uint64_t *curw
     if (in && src >= 0 && src < old_len) {
       if (fold > 0) {
         const int r = i % fold, q = i / fold;
-        v0 = cnt[r]; v1 = cnt[Lp + r]; v2 = cnt[2 * Lp + r]; v3 = cnt[3 * Lp + r];
+        const uint4 c4 = cnt[r];
+        v0 = c4.x; v1 = c4.y; v2 = c4.z; v3 = c4.w;
         for (int t = 1; t < q; t++) {  // the t == q term is the read's own base at column i, added below
           const int b = 3 - base_code(curw, cur_len - 1 - (t * fold + r));
           if (b == 0) v0++; else if (b == 2) v1++; else if (b == 3) v2++; else v3++;
         }
       } else {
-        v0 = cnt[src]; v1 = cnt[Lp + src]; v2 = cnt[2 * Lp + src]; v3 = cnt[3 * Lp + src];
+        const uint4 c4 = cnt[src];
+        v0 = c4.x; v1 = c4.y; v2 = c4.z; v3 = c4.w;
       }
     }
     __syncwarp();
@@ -106,7 +116,7 @@ __device__ void update_ref(uint64_t *ref, uint64_t *revref, const uint64_t *curw
         // count rows are A,C,T,G (reorder.h:120-123); 2-bit codes are A0 G1 C2 T3
         if (b == 0) v0++; else if (b == 2) v1++; else if (b == 3) v2++; else v3++;
       }
-      cnt[i] = v0; cnt[Lp + i] = v1; cnt[2 * Lp + i] = v2; cnt[3 * Lp + i] = v3;
+      cnt[i] = make_uint4(v0, v1, v2, v3);
       uint32_t mx = 0; int ind = 0;  // first strict maximum (reorder.h:204-212)
       if (v0 > mx) { mx = v0; ind = 0; }
       if (v1 > mx) { mx = v1; ind = 1; }
@@ -131,15 +141,16 @@ __device__ void update_ref(uint64_t *ref, uint64_t *revref, const uint64_t *curw
 }
 
 // Verify the live reads of one bin, highest id first, at most MAX_SEARCH of them (reorder.h:287-311).
-__device__ bool scan_bin(const ChainArgs &a, const DictView &d, uint32_t bs, uint32_t bc, const uint64_t *refsm, bool rev,
-                         int s, int ref_len, int lane, uint32_t &rid_out, unsigned long long &compares) {
+// in3: the bin's first three entries (from the slot); bins[] is only read for bins of > 3 reads.
+__device__ bool scan_bin(const ChainArgs &a, const DictView &d, uint32_t bs, uint32_t bc, uint32_t in3, const uint64_t *refsm,
+                         bool rev, int s, int ref_len, int lane, uint32_t &rid_out, unsigned long long &compares) {
   const int W = a.W;
   int live_before = 0;
   for (uint32_t off = 0; off < bc; off += 32) {
     const uint32_t t = off + lane;
     uint32_t rid = 0;
     bool live = false;
-    if (t < bc) { rid = __ldg(d.read_id + bs + (bc - 1 - t)); live = !is_claimed(a.claimed, rid); }
+    if (t < bc) { rid = bc <= 3 ? in3 : __ldg(d.bins + bs + t); live = !is_claimed(a.claimed, rid); }
     const unsigned lm = __ballot_sync(FULL, live);
     const int rank = live_before + __popc(lm & ((1u << lane) - 1u));
     const bool ev = live && rank < kMaxSearch;
@@ -175,74 +186,95 @@ __device__ bool scan_bin(const ChainArgs &a, const DictView &d, uint32_t bs, uin
 }
 
 // Phase A for a searching chain: the first read, in the reference's order, that matches.
+//
+// Lane l of the warp owns probe kind (l & 3) = 2*strand + dict and shifts S + (l >> 2) + 8*j:
+// a batch covers 8*n consecutive shifts with n probes per lane, n = 1, 2, 4, 8, 16 (most matches sit
+// within the first 8 shifts, so most rounds cost 32 probes; a dead end walks all L/2 shifts in
+// log-many batches).  Every probe first tests one bit of the dictionary's key filter (32 MB per
+// dictionary at 10 M keys: L2-resident, no DRAM access); only filter positives (true keys + ~5 %
+// false positives) go on to the slot table in HBM.  The warp then walks its hits in the reference's
+// order (shift, forward before reverse, dict 0 before dict 1; bins from the highest id down).
 __device__ bool chain_search(const ChainArgs &a, const uint64_t *ref, const uint64_t *revref, int ref_len, int lane,
                              uint32_t &prop_rid, int &prop_shift, int &prop_rev, unsigned long long &probes_issued,
-                             unsigned long long &probes_seq, unsigned long long &compares) {
+                             unsigned long long &probes_seq, unsigned long long &compares, unsigned long long &slot_probes) {
   const int W = a.W;
-  for (int base = 0; base < a.maxshift; base += 32) {
-    const int s = base + lane;
-    const bool sv = s < a.maxshift;
-    uint64_t key[4];
-    uint32_t h[4];
-    DictSlot sl[4];
-    unsigned okmask = 0;
-#pragma unroll
-    for (int kind = 0; kind < 4; kind++) {  // kind = 2*rev + dict
-      const int rev = kind >> 1;
-      const DictView &d = a.dict[kind & 1];
-      bool ok = sv;
+  const int kind = lane & 3, rev = kind >> 1, sub = lane >> 2;
+  const DictView &d = a.dict[kind & 1];
+  const uint64_t *src = rev ? revref : ref;
+  int S = 0;
+  for (int b = 0; S < a.maxshift; b++) {
+    const int n = b < 4 ? 1 << b : 16;  // 8, 16, 32, 64, then 128 shifts per batch
+    // ---- pass 1: bounds + filter bit for this lane's n probes (independent 4-byte loads) ----
+    unsigned okm = 0, cand = 0;
+#pragma unroll 4
+    for (int j = 0; j < n; j++) {
+      const int s = S + sub + 8 * j;
+      bool ok = s < a.maxshift;
       if (!rev) ok = ok && !(d.end + s >= ref_len);                          // reorder.h:264-265
       else ok = ok && !(d.end >= ref_len + s || d.start <= s);               // reorder.h:266-267
       if (ok) {
-        okmask |= 1u << kind;
-        key[kind] = rev ? extract_bits(revref, W, 2 * (d.start - s), d.key_bits)
-                        : extract_bits(ref, W, 2 * (d.start + s), d.key_bits);
-        h[kind] = (uint32_t)mix64(key[kind]) & d.slot_mask;
-        sl[kind] = load_slot(d.slots + h[kind]);
+        okm |= 1u << j;
+        const uint64_t key = extract_bits(src, W, rev ? 2 * (d.start - s) : 2 * (d.start + s), d.key_bits);
+        const uint32_t fi = (uint32_t)(mix64(key) >> 32) & d.filter_mask;
+        if ((__ldg(d.filter + (fi >> 5)) >> (fi & 31)) & 1u) cand |= 1u << j;
       }
     }
-    unsigned pend = 0;
-    uint32_t bstart[4], bcount[4];
-#pragma unroll
-    for (int kind = 0; kind < 4; kind++) {
-      bstart[kind] = 0; bcount[kind] = 0;
-      if (okmask & (1u << kind)) {
-        const DictView &d = a.dict[kind & 1];
-        while (sl[kind].count != 0 && sl[kind].key != key[kind]) {
-          h[kind] = (h[kind] + 1) & d.slot_mask;
-          sl[kind] = load_slot(d.slots + h[kind]);
-        }
-        if (sl[kind].count) { bstart[kind] = sl[kind].start; bcount[kind] = sl[kind].count; pend |= 1u << kind; }
-      }
-    }
-    probes_issued += __popc(okmask);
-    int found_p = -1;
+    probes_issued += __reduce_add_sync(FULL, (unsigned)__popc(okm));
+    // ---- pass 2: resolve hits in priority order ----------------------------------------------------
+    int cur_j = -1, found_p = -1;
+    uint32_t cur_start1 = 0, cur_count = 0, cur_r0 = 0, cur_r1 = 0, cur_r2 = 0;
     for (;;) {
-      const int myp = pend ? (s << 2) + (__ffs(pend) - 1) : 0x7FFFFFFF;
+      while (cur_j < 0 && cand) {  // this lane's next filter positive -> slot table (HBM)
+        const int j = __ffs(cand) - 1;
+        cand &= cand - 1;
+        const int s = S + sub + 8 * j;
+        const uint64_t key = extract_bits(src, W, rev ? 2 * (d.start - s) : 2 * (d.start + s), d.key_bits);
+        uint32_t h = (uint32_t)mix64(key) & d.slot_mask;
+        slot_probes++;
+        for (;;) {
+          const DictSlot sl = load_slot(d.slots + h);
+          if (sl.start1 == 0) break;
+          if (sl.key == key) {
+            // a bin with no live read is an "empty_bin" (reorder.h:277-281): skipped without a visit
+            if (sl.live) { cur_j = j; cur_start1 = sl.start1; cur_count = sl.count; cur_r0 = sl.rid[0]; cur_r1 = sl.rid[1]; cur_r2 = sl.rid[2]; }
+            break;
+          }
+          h = (h + 1) & d.slot_mask;
+        }
+      }
+      const int myp = cur_j >= 0 ? (((S + sub + 8 * cur_j) << 2) | kind) : 0x7FFFFFFF;
       const int p = __reduce_min_sync(FULL, myp);
       if (p == 0x7FFFFFFF) break;
-      const int owner = (p >> 2) - base, kind = p & 3;
-      uint32_t mb = kind == 0 ? bstart[0] : kind == 1 ? bstart[1] : kind == 2 ? bstart[2] : bstart[3];
-      uint32_t mc = kind == 0 ? bcount[0] : kind == 1 ? bcount[1] : kind == 2 ? bcount[2] : bcount[3];
-      mb = __shfl_sync(FULL, mb, owner);
-      mc = __shfl_sync(FULL, mc, owner);
-      const int rev = kind >> 1, ps = p >> 2;
+      const int ps = p >> 2, pk = p & 3;
+      const int owner = (((ps - S) & 7) << 2) | pk;
+      const uint32_t mb = __shfl_sync(FULL, cur_start1, owner);  // entries follow the header at bins[mb - 1]
+      const uint32_t mc = __shfl_sync(FULL, cur_count, owner);
+      // lane t < 3 receives the owner's t-th inline id
+      const uint32_t r0 = __shfl_sync(FULL, cur_r0, owner), r1 = __shfl_sync(FULL, cur_r1, owner), r2 = __shfl_sync(FULL, cur_r2, owner);
+      const uint32_t in3 = lane == 0 ? r0 : lane == 1 ? r1 : r2;
+      const DictView &pd = a.dict[pk & 1];
       uint32_t rid;
-      if (scan_bin(a, a.dict[kind & 1], mb, mc, rev ? revref : ref, rev, ps, ref_len, lane, rid, compares)) {
-        prop_rid = rid; prop_shift = ps; prop_rev = rev; found_p = p;
+      if (scan_bin(a, pd, mb, mc, in3, (pk >> 1) ? revref : ref, pk >> 1, ps, ref_len, lane, rid, compares)) {
+        prop_rid = rid; prop_shift = ps; prop_rev = pk >> 1; found_p = p;
         break;
       }
-      if (lane == owner) pend &= ~(1u << kind);
+      if (lane == owner) cur_j = -1;
     }
     // lookups a sequential search would have issued: all of this batch, or those up to the hit
-    unsigned seqmask = okmask;
+    unsigned seqmask = okm;
     if (found_p >= 0) {
       const int fs = found_p >> 2, fk = found_p & 3;
-      if (s > fs) seqmask = 0;
-      else if (s == fs) seqmask &= (2u << fk) - 1u;
+      const int rel = fs - S - sub;  // this lane's shifts <= fs are j <= rel / 8
+      if (rel < 0) seqmask = 0;
+      else {
+        int jm = rel >> 3;
+        if ((rel & 7) == 0 && kind > fk) jm--;  // same shift, later kind: not reached
+        seqmask = jm < 0 ? 0u : (jm >= 31 ? seqmask : seqmask & ((2u << jm) - 1u));
+      }
     }
     probes_seq += __reduce_add_sync(FULL, (unsigned)__popc(seqmask));
     if (found_p >= 0) return true;
+    S += 8 * n;
   }
   return false;
 }
@@ -271,20 +303,28 @@ __device__ bool find_unclaimed(const uint32_t *claimed, long long lo, long long 
 }
 
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) k_chains(ChainArgs a) {
-  extern __shared__ uint64_t smem[];
+  extern __shared__ __align__(16) uint64_t smem[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const uint32_t cid = blockIdx.x * kWarpsPerBlock + wib;
   const int W = a.W, Lp = a.Lp;
-  const size_t per_chain = 3 * (size_t)W + 2 * (size_t)Lp;  // uint64 words: ref, revref, cur, 4*Lp u32 counts
+  const size_t per_chain = 3 * (size_t)W + (W & 1) + 2 * (size_t)Lp;  // uint64 words: ref, revref, cur, pad, Lp uint4 counts
   uint64_t *ref = smem + wib * per_chain, *revref = ref + W, *curw = revref + W;
-  uint32_t *cnt = reinterpret_cast<uint32_t *>(curw + W);
+  uint4 *cnt = reinterpret_cast<uint4 *>(curw + W + (W & 1));  // 16-byte aligned; one uint4 {A,C,T,G} per column
 
   int state = cid < a.num_chains ? ST_SEARCH : ST_DONE;
   int ref_len = 0, prev_unmatched = 0, left_search = 0, iter_started = 0, stop_searching = 0;
   long long ref_pos = 0, cur_read_pos = 0, cursor = -1, slice_lo = 0;
   uint32_t first_rid = 0, prev = 0, num_reads_thr = 0, num_unmatched_1m = 0, n_aligned = 0, n_single = 0;
-  unsigned long long c_unmatched = 0, c_lost = 0, c_issued = 0, c_seq = 0, c_cmp = 0, target = 0, round = 0;
+  unsigned long long c_unmatched = 0, c_lost = 0, c_issued = 0, c_seq = 0, c_cmp = 0, c_slot = 0, target = 0, round = 0;
 
+  // claim bit + "remove from both dictionaries" (reorder.h:458-472): one decrement per bin
+  auto claim = [&](uint32_t rid) {
+    if (lane == 0) atomicOr(a.claimed + (rid >> 5), 1u << (rid & 31));
+    if (lane < kNumDict) {
+      const uint32_t sidx = __ldg(a.dict[lane].slot_of_read + rid);
+      if (sidx != 0xFFFFFFFFu) atomicSub(&a.dict[lane].slots[sidx].live, 1u);
+    }
+  };
   auto stage_read = [&](uint32_t rid) {
     if (lane < W) curw[lane] = __ldg(a.reads + (size_t)rid * W + lane);
     __syncwarp();
@@ -292,7 +332,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) k_chains(ChainArgs a) 
   auto new_contig = [&](uint32_t rid) {  // updaterefcount(..., resetcount = true, rev = false) + reorder.h:426-430,:601-612
     stage_read(rid);
     const int len = __ldg(a.lens + rid);
-    update_ref(ref, revref, curw, cnt, Lp, W, lane, 0, 0, 0, len, false, len);
+    update_ref(ref, revref, curw, cnt, W, lane, 0, 0, 0, len, false, len);
     ref_len = len; ref_pos = 0; cur_read_pos = 0;
     prev_unmatched = 1; first_rid = rid; prev = rid; left_search = 0;
     state = ST_SEARCH; iter_started = 0;
@@ -302,12 +342,14 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) k_chains(ChainArgs a) 
     const uint32_t first = cid * a.per;
     slice_lo = first;
     cursor = cid == a.num_chains - 1 ? (long long)a.N - 1 : (long long)(cid + 1) * a.per - 1;
-    if (lane == 0) atomicOr(a.claimed + (first >> 5), 1u << (first & 31));
+    claim(first);
     c_unmatched++;
     new_contig(first);
   }
-  grid_barrier(a.barrier, target);
-
+  unsigned long long cy_search = 0, cy_wait_a = 0, cy_commit = 0, cy_wait_b = 0;
+  long long t_last = clock64();
+  grid_barrier(a.barrier, target, t_last, cy_commit, cy_wait_b);
+  cy_commit = 0; cy_wait_b = 0;
   for (;;) {
     // ---------------- phase A: search / pick against the round-start claim state -------------
     bool has_prop = false;
@@ -323,19 +365,19 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) k_chains(ChainArgs a) 
         iter_started = 1;
       }
       if (!stop_searching)
-        has_prop = chain_search(a, ref, revref, ref_len, lane, prop_rid, prop_shift, prop_rev, c_issued, c_seq, c_cmp);
+        has_prop = chain_search(a, ref, revref, ref_len, lane, prop_rid, prop_shift, prop_rev, c_issued, c_seq, c_cmp, c_slot);
     } else if (state == ST_NEWREAD) {
       has_prop = find_unclaimed(a.claimed, slice_lo, cursor, lane, prop_rid);
     }
     if (has_prop && lane == 0) atomicMin(a.winner + prop_rid, cid);
-    grid_barrier(a.barrier, target);
+    grid_barrier(a.barrier, target, t_last, cy_search, cy_wait_a);
 
     // ---------------- phase B: winners claim and update ----------------------------------------
     if (state == ST_SEARCH) {
       if (has_prop) {
         if (__ldcg(a.winner + prop_rid) == cid) {
           const uint32_t k = prop_rid;
-          if (lane == 0) atomicOr(a.claimed + (k >> 5), 1u << (k & 31));
+          claim(k);
           stage_read(k);
           const int len = __ldg(a.lens + k), shift = prop_shift, old = ref_len;
           int delta, cs, nl, fold = 0;
@@ -343,7 +385,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) k_chains(ChainArgs a) 
           else if (len - shift >= old) { fold = len - shift - old; delta = -fold; cs = 0; nl = len; }  // :159-174
           else if (old + shift <= a.L) { delta = 0; cs = old - len + shift; nl = old + shift; } // :175-184
           else { delta = old + shift - a.L; cs = a.L - len; nl = a.L; }                         // :185-199
-          update_ref(ref, revref, curw, cnt, Lp, W, lane, old, delta, cs, len, prop_rev != 0, nl, fold);
+          update_ref(ref, revref, curw, cnt, W, lane, old, delta, cs, len, prop_rev != 0, nl, fold);
           ref_len = nl;
           if (!prop_rev) {  // reorder.h:490-497
             if (!left_search) { cur_read_pos = ref_pos + shift; ref_pos = cur_read_pos; }
@@ -372,7 +414,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) k_chains(ChainArgs a) 
           left_search = 1;
           stage_read(first_rid);
           const int len = __ldg(a.lens + first_rid);
-          update_ref(ref, revref, curw, cnt, Lp, W, lane, 0, 0, 0, len, true, len);
+          update_ref(ref, revref, curw, cnt, W, lane, 0, 0, 0, len, true, len);
           ref_len = len; ref_pos = 0; cur_read_pos = 0;
           iter_started = 0;
         } else {
@@ -384,10 +426,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) k_chains(ChainArgs a) 
       if (has_prop) {
         if (__ldcg(a.winner + prop_rid) == cid) {
           const uint32_t j = prop_rid;
-          if (lane == 0) {
-            atomicOr(a.claimed + (j >> 5), 1u << (j & 31));
-            if (prev_unmatched) { a.rec_chain[prev] = cid; a.rec_k[prev] = n_single; a.rec_meta[prev] = 4; }
-          }
+          claim(j);
+          if (lane == 0 && prev_unmatched) { a.rec_chain[prev] = cid; a.rec_k[prev] = n_single; a.rec_meta[prev] = 4; }
           if (prev_unmatched) n_single++;
           cursor = (long long)j - 1;
           c_unmatched++;
@@ -405,14 +445,16 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) k_chains(ChainArgs a) 
       }
     }
     round++;
-    grid_barrier(a.barrier, target);
+    grid_barrier(a.barrier, target, t_last, cy_commit, cy_wait_b);
     if (__ldcg(a.active) <= 0) break;
     if (round >= a.max_rounds) {  // watchdog: uniform across the grid
       if (cid == 0 && lane == 0) a.ctr[CTR_ABORT] = 1ull;
       break;
     }
   }
+  for (int o = 16; o; o >>= 1) c_slot += __shfl_xor_sync(FULL, c_slot, o);
   if (lane == 0) {
+    atomicAdd(a.ctr + CTR_SLOT_PROBES, c_slot);
     a.chain_aligned[cid] = n_aligned;
     a.chain_single[cid] = n_single;
     atomicAdd(a.ctr + CTR_UNMATCHED, c_unmatched);
@@ -420,6 +462,12 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) k_chains(ChainArgs a) 
     atomicAdd(a.ctr + CTR_PROBES_ISSUED, c_issued);
     atomicAdd(a.ctr + CTR_PROBES_SEQ, c_seq);
     atomicAdd(a.ctr + CTR_COMPARES, c_cmp);
+    if (threadIdx.x == 0) {  // per-block numbers (thread 0 runs the barrier)
+      atomicAdd(a.ctr + CTR_CYC_SEARCH, cy_search);
+      atomicAdd(a.ctr + CTR_CYC_WAIT_A, cy_wait_a);
+      atomicAdd(a.ctr + CTR_CYC_COMMIT, cy_commit);
+      atomicAdd(a.ctr + CTR_CYC_WAIT_B, cy_wait_b);
+    }
     if (cid == 0) a.ctr[CTR_ROUNDS] = round;
   }
 }
@@ -460,7 +508,7 @@ void run_reorder(Ctx &c, const uint64_t *reads, const uint16_t *lens, uint32_t n
   out.s_order = c.pool.dev<uint32_t>("ro.s_order", nn);
   if (n == 0) return;
 
-  const size_t smem = kWarpsPerBlock * (3 * (size_t)W + 2 * (size_t)Lp) * sizeof(uint64_t);
+  const size_t smem = kWarpsPerBlock * (3 * (size_t)W + (W & 1) + 2 * (size_t)Lp) * sizeof(uint64_t);
   SB_CUDA(cudaFuncSetAttribute(k_chains, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
   SB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_chains, kWarpsPerBlock * 32, smem));
@@ -500,7 +548,10 @@ void run_reorder(Ctx &c, const uint64_t *reads, const uint16_t *lens, uint32_t n
   int active = (int)C;
   SB_CUDA(cudaMemcpyAsync(a.active, &active, sizeof(int), cudaMemcpyHostToDevice, st));
   void *args[] = {&a};
+  if (!c.ev_k0) { SB_CUDA(cudaEventCreate(&c.ev_k0)); SB_CUDA(cudaEventCreate(&c.ev_k1)); }
+  SB_CUDA(cudaEventRecord(c.ev_k0, st));
   SB_CUDA(cudaLaunchCooperativeKernel((void *)k_chains, dim3(grid), dim3(kWarpsPerBlock * 32), args, smem, st));
+  SB_CUDA(cudaEventRecord(c.ev_k1, st));
   c.launches++;
 
   size_t need = 0, tmp_bytes = 0;
@@ -525,6 +576,9 @@ void run_reorder(Ctx &c, const uint64_t *reads, const uint16_t *lens, uint32_t n
   if (out.num + out.num_singletons != n) throw LimitError("reorder: records do not cover all reads");
   out.unmatched = (uint32_t)h[CTR_UNMATCHED];
   out.rounds = h[CTR_ROUNDS]; out.lost = h[CTR_LOST];
+  SB_CUDA(cudaEventElapsedTime(&out.ms_kernel, c.ev_k0, c.ev_k1));
+  out.cyc[0] = h[CTR_CYC_SEARCH]; out.cyc[1] = h[CTR_CYC_WAIT_A]; out.cyc[2] = h[CTR_CYC_COMMIT]; out.cyc[3] = h[CTR_CYC_WAIT_B];
+  out.slot_probes = h[CTR_SLOT_PROBES];
   out.probes_issued = h[CTR_PROBES_ISSUED]; out.probes_seq = h[CTR_PROBES_SEQ]; out.compares = h[CTR_COMPARES];
 }
 

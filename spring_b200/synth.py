@@ -35,7 +35,7 @@ class ReadSet:
 def generate(num_reads: int, read_len: int = 150, genome_len: int | None = None, seed: int = 3,
              sub_rate: float = 0.005, error_model: str = "uniform", var_len: tuple[int, int] | None = None,
              paired: bool = False, n_frac: float = 0.0, device: str | torch.device = "cpu",
-             chunk: int = 1 << 20) -> ReadSet:
+             chunk: int = 1 << 20, read_seed: int | None = None) -> ReadSet:
     dev = torch.device(device)
     g = torch.Generator(device=dev)
     g.manual_seed(seed)
@@ -43,6 +43,8 @@ def generate(num_reads: int, read_len: int = 150, genome_len: int | None = None,
     if genome_len is None:
         genome_len = max(num_reads * L // 30, 4 * L + 600)       # 30x coverage
     genome = torch.randint(0, 4, (genome_len,), dtype=torch.uint8, device=dev, generator=g)
+    if read_seed is not None:  # same genome, different reads (one block of a larger read set)
+        g.manual_seed(read_seed)
     n_frag = num_reads // 2 if paired else num_reads
     out_codes = torch.empty((num_reads, L), dtype=torch.uint8, device=dev)
     out_len = torch.empty((num_reads,), dtype=torch.int32, device=dev)

@@ -1,0 +1,21 @@
+"""GPU box: per-phase cycle breakdown of the chain kernel on the bench workload."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from spring_b200 import capi, synth
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 10_000_000
+chains = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+dev = torch.device("cuda", 0)
+rs = synth.generate(n, 150, genome_len=n * 150 // 30, seed=3, sub_rate=0.005, device=dev)
+d_reads = synth.pack_reads(rs.codes, rs.lengths, 150).contiguous(); d_lens = rs.lengths.to(torch.int16).contiguous(); del rs
+ctx = capi.Context(0, torch.cuda.current_stream().cuda_stream)
+inp = ctx.make_input(d_reads.data_ptr(), d_lens.data_ptr(), n, 150)
+for it in range(3):
+    ctx.reorder_encode_raw(inp, chains, device=True)
+    st = ctx.stats()
+tot = st["rounds"] * ((st["num_chains"] + 7) // 8)
+print({k: st[k] for k in ("num_chains", "rounds", "unmatched", "lost_proposals", "probes_issued", "probes_seq", "slot_probes", "compares")})
+print({k: round(st[k], 3) for k in st if k.startswith("ms_")})
+print("avg cycles per block-round: search %.0f  waitA %.0f  commit %.0f  waitB %.0f  | round %.0f cycles; kernel us/round %.2f" % (
+    st["cyc_search"] / tot, st["cyc_wait_a"] / tot, st["cyc_commit"] / tot, st["cyc_wait_b"] / tot,
+    (st["cyc_search"] + st["cyc_wait_a"] + st["cyc_commit"] + st["cyc_wait_b"]) / tot, 1e3 * st["ms_chain_kernel"] / st["rounds"]))

@@ -15,6 +15,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "liboracle.so")
 REF_BIN = os.path.join(HERE, "_ref", "spring_ref")
+SPLICE_BIN = os.path.join(HERE, "_ref", "spring_b200_ref")
 REFERENCE_SRC = "/root/reference"
 
 
@@ -25,6 +26,10 @@ def build(force: bool = False) -> None:
         subprocess.check_call(["make", "-s", "-C", HERE, "oracle"])
     if os.path.isdir(os.path.join(REFERENCE_SRC, "src")) and (force or not os.path.exists(REF_BIN)):
         subprocess.check_call(["make", "-s", "-j8", "-C", HERE, "ref"])
+    # the reference host with our library spliced in at call_reorder / call_encoder (end-to-end parity)
+    b200 = os.path.join(HERE, "..", "spring_b200", "libspring_b200.so")
+    if os.path.isdir(os.path.join(REFERENCE_SRC, "src")) and os.path.exists(b200):
+        subprocess.check_call(["make", "-s", "-j8", "-C", HERE, "splice"])
 
 
 class _ByteVec(C.Structure):

@@ -59,10 +59,13 @@ def exchange_by_bucket(reads: torch.Tensor, lens: torch.Tensor, max_readlen: int
     n_recv = int(sum(rc))
 
     def a2a(x: torch.Tensor) -> torch.Tensor:
+        # rows travel as raw bytes: every backend moves uint8 (gloo has no int16 all-to-all)
         xs = x[order].contiguous()
-        out = torch.empty((n_recv,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
-        dist.all_to_all_single(out, xs, output_split_sizes=rc, input_split_sizes=sc, group=group)
-        return out
+        row = xs.element_size() * (xs[0].numel() if xs.shape[0] else int(np.prod(x.shape[1:], dtype=np.int64)))
+        xb = xs.view(torch.uint8).reshape(xs.shape[0], row)
+        out = torch.empty((n_recv, row), dtype=torch.uint8, device=x.device)
+        dist.all_to_all_single(out, xb, output_split_sizes=rc, input_split_sizes=sc, group=group)
+        return out.view(x.dtype).reshape((n_recv,) + tuple(x.shape[1:]))
 
     r, l = a2a(reads), a2a(lens)
     if ids is None:

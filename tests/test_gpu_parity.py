@@ -123,3 +123,51 @@ def test_file_level_drop_in(ctx):
             assert f"read_seq.bin.{t}" in left and f"read_seq.bin.{t}.tail" in left
         got = po.load_reference_streams(d, 3)
     assert_streams_equal(got, er, "file-level")
+
+
+def _fastq_records(path):
+    with open(path, "rb") as f:
+        lines = f.read().split(b"\n")
+    return [b"\n".join(lines[i:i + 4]) for i in range(0, len(lines) - 1, 4)]
+
+
+@pytest.mark.skipif(not (os.path.exists(po.SPLICE_BIN) and po.have_reference()), reason="oracle/_ref binaries not built")
+@pytest.mark.parametrize("paired", [False, True])
+def test_end_to_end_archive_decodes_with_reference(paired, tmp_path):
+    """The reference's own `spring -c -r` host pipeline with call_reorder / call_encoder replaced by
+    libspring_b200.so (oracle/_ref/spring_b200_ref) writes an archive; the UNMODIFIED reference
+    (`spring -d`) must decode it to the input, as a multiset of records (pairs kept together) --
+    the check of util/test_script.sh:78-82."""
+    import subprocess
+    from spring_b200 import synth
+    rs = synth.generate(30000, 120, seed=31, paired=paired, n_frac=0.01, var_len=(60, 120), error_model="illumina")
+    f1, f2 = str(tmp_path / "in_1.fastq"), str(tmp_path / "in_2.fastq")
+    synth.write_fastq(rs, f1, f2 if paired else None)
+    arc = str(tmp_path / "out.spring")
+    ins = [f1, f2] if paired else [f1]
+    r = subprocess.run([po.SPLICE_BIN, "-c", "-r", "-i", *ins, "-o", arc, "-t", "4", "-w", str(tmp_path)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "were unmatched" in r.stdout
+    out = str(tmp_path / "dec")
+    r = subprocess.run([po.REF_BIN, "-d", "-i", arc, "-o", out, "-t", "3", "-w", str(tmp_path)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    if not paired:
+        assert sorted(_fastq_records(out)) == sorted(_fastq_records(f1))
+    else:
+        got = sorted(zip(_fastq_records(out + ".1"), _fastq_records(out + ".2")))
+        want = sorted(zip(_fastq_records(f1), _fastq_records(f2)))
+        assert got == want
+
+
+def test_bucket_kernel_matches_numpy_mirror(ctx):
+    """k_bucket (multi-GPU owner of a read) against the numpy restatement used by the gloo CPU tests."""
+    import torch
+    from test_multigpu_cpu import bucket_numpy
+    hp = make_input(**CASES["var250"])
+    r = torch.from_numpy(hp.packed.view(np.int64).copy()).cuda()
+    l = torch.from_numpy(hp.lengths.view(np.int16).copy()).cuda()
+    out = torch.empty(len(hp.lengths), dtype=torch.int32, device="cuda")
+    for g in (2, 8):
+        ctx.bucket_reads(r.data_ptr(), l.data_ptr(), len(hp.lengths), hp.max_readlen, g, out.data_ptr())
+        torch.cuda.synchronize()
+        assert (out.cpu().numpy() == bucket_numpy(hp.packed, hp.lengths, g)).all()

@@ -127,6 +127,13 @@ int spring_b200_create(int device, void *stream, spring_b200_ctx **out);
 void spring_b200_destroy(spring_b200_ctx *ctx);
 const char *spring_b200_last_error(const spring_b200_ctx *ctx); /* ctx may be NULL: last create() error */
 int spring_b200_get_stats(const spring_b200_ctx *ctx, spring_b200_stats *out);
+/* Chain schedule of the reorder stage.  deterministic = 0 (default): free-running chains that claim
+ * reads with atomic test-and-set, like the reference's threads under their striped locks
+ * (src/reorder.h:303-309); fastest, but for more than one chain the output depends on timing, as the
+ * reference's does for -t > 1.  deterministic = 1: round-synchronous chains (propose / lowest chain
+ * id wins / commit); the output is a pure function of (input, num_chains).  With num_chains = 1 both
+ * reproduce the reference's single-thread result. */
+int spring_b200_set_schedule(spring_b200_ctx *ctx, int deterministic);
 
 /* ---- the hot path ------------------------------------------------------------------------ */
 /* reorder_main + encoder_main (src/reorder.h:732-786, src/encoder.h:572-633) on HOST buffers:
@@ -150,6 +157,11 @@ int spring_b200_build_dictionary(spring_b200_ctx *ctx, const spring_b200_input *
 /* reorder<>() alone (src/reorder.h:320-641), host inputs, host outputs owned by the context. */
 int spring_b200_reorder(spring_b200_ctx *ctx, const spring_b200_input *in, uint32_t num_chains,
                         spring_b200_reorder_out *out);
+
+/* The reorder stage's output of the last spring_b200_reorder_encode* call on this context (what the
+ * encoder consumed), copied to host memory owned by the context: lets a test feed the very same
+ * stream to an independent encoder. */
+int spring_b200_fetch_reorder(spring_b200_ctx *ctx, spring_b200_reorder_out *out);
 
 /* ---- multi-GPU partitioning ------------------------------------------------------------------ */
 /* DEVICE pointers.  bucket[i] = hash(strand-canonical 16-mer minimizer of read i) mod num_buckets:

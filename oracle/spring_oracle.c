@@ -263,6 +263,7 @@ typedef struct {
   int64_t first_rid, current, prev;
   int prev_unmatched, left_search;
   int state, iter_started, stop_searching;
+  int batch, batch_S, search_more; /* shift batching of the schedule, see chain_propose */
   uint32_t num_reads_thr, num_unmatched_past_1M;
   int64_t cursor, slice_lo;
   int has_prop, prop_shift, prop_rev;
@@ -405,7 +406,7 @@ static void chain_new_contig(reorder_ctx *x, chain_t *c, int64_t rid) {
   c->ref_pos = 0; c->cur_read_pos = 0;
   c->prev_unmatched = 1; c->first_rid = rid; c->prev = rid;
   c->left_search = 0;
-  c->state = ST_SEARCH; c->iter_started = 0;
+  c->state = ST_SEARCH; c->iter_started = 0; c->batch = 0; c->batch_S = 0;
 }
 
 /* phase A of a round for one chain */
@@ -420,15 +421,25 @@ static void chain_propose(reorder_ctx *x, chain_t *c) {
       c->num_reads_thr++;
       c->iter_started = 1;
     }
+    c->search_more = 0;
     if (c->stop_searching) return;
+    /* The shift loop of reorder.h:479-558 is cut into batches of 8, 16, 32, 64, 128, 128, ... shifts
+     * and a chain examines ONE batch per round (bounded work per round keeps the lock-step chains
+     * balanced).  Claims only ever grow, so a batch that found nothing in an earlier round would
+     * find nothing now either: the read proposed is exactly the one a full search against the
+     * current round's claim state returns. */
+    int nshift = 8 * (c->batch < 4 ? 1 << c->batch : 16);
+    int s_end = c->batch_S + nshift < x->maxshift ? c->batch_S + nshift : x->maxshift;
     uint64_t ref[MAXW], revref[MAXW];
     memcpy(ref, c->ref, sizeof(ref)); memcpy(revref, c->revref, sizeof(revref));
-    for (int shift = 0; shift < x->maxshift; shift++) { /* :479-558 */
+    mw_shr(ref, x->W, 2 * c->batch_S); mw_shl(revref, x->W, 2 * c->batch_S);
+    for (int shift = c->batch_S; shift < s_end; shift++) { /* :479-558 */
       uint32_t k;
       if (search_match(x, ref, 0, shift, c->ref_len, &k)) { c->has_prop = 1; c->prop_rid = k; c->prop_shift = shift; c->prop_rev = 0; return; }
       if (search_match(x, revref, 1, shift, c->ref_len, &k)) { c->has_prop = 1; c->prop_rid = k; c->prop_shift = shift; c->prop_rev = 1; return; }
       mw_shl(revref, x->W, 2); mw_shr(ref, x->W, 2);
     }
+    if (s_end < x->maxshift) { c->batch++; c->batch_S = s_end; c->search_more = 1; } /* next batch next round */
   } else if (c->state == ST_NEWREAD) { /* :576-592 */
     for (int64_t j = c->cursor; j >= c->slice_lo; j--)
       if (!x->claimed[j]) { c->has_prop = 1; c->prop_rid = (uint32_t)j; return; }
@@ -456,16 +467,17 @@ static void chain_commit(reorder_ctx *x, chain_t *c, const uint32_t *winner, int
       uint8_t rc = rev ? (c->left_search ? 'd' : 'r') : (c->left_search ? 'r' : 'd'); /* :508,:546 */
       chain_emit(c, k, 1, c->cur_read_pos, rc);
       c->prev_unmatched = 0;
-      c->iter_started = 0;
+      c->iter_started = 0; c->batch = 0; c->batch_S = 0;
       return;
     }
+    if (c->search_more) return; /* more shifts to examine next round */
     /* no match, :559-615 */
     c->num_unmatched_past_1M++;
     if (!c->left_search) {
       c->left_search = 1;
       updaterefcount(x, c, x->reads + (size_t)c->first_rid * x->W, 1, 1, 0, x->lens[c->first_rid]);
       c->ref_pos = 0; c->cur_read_pos = 0;
-      c->iter_started = 0;
+      c->iter_started = 0; c->batch = 0; c->batch_S = 0;
     } else {
       c->left_search = 0;
       c->state = ST_NEWREAD;

@@ -12,14 +12,14 @@ from dataclasses import dataclass
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libspring_b200.so")
+LIB_PATH = os.environ.get("SPRING_B200_LIB") or os.path.join(HERE, "libspring_b200.so")
 
 EXPORTS = [
     "spring_b200_version", "spring_b200_device_count", "spring_b200_create", "spring_b200_destroy",
     "spring_b200_last_error", "spring_b200_get_stats", "spring_b200_reorder_encode",
     "spring_b200_reorder_encode_device", "spring_b200_fetch_streams", "spring_b200_build_dictionary",
     "spring_b200_reorder", "spring_b200_reorder_encode_files", "spring_b200_write_streams",
-    "spring_b200_bucket_reads",
+    "spring_b200_bucket_reads", "spring_b200_set_schedule", "spring_b200_fetch_reorder",
 ]
 
 
@@ -159,6 +159,11 @@ class Context:
         if rc != 0:
             raise SpringB200Error(rc, self._lib.spring_b200_last_error(self._h).decode())
 
+    def set_schedule(self, deterministic: bool) -> None:
+        """True: round-synchronous chains (reproducible output); False (default): free-running chains."""
+        self._lib.spring_b200_set_schedule.argtypes = [C.c_void_p, C.c_int]
+        self._check(self._lib.spring_b200_set_schedule(self._h, 1 if deterministic else 0))
+
     def stats(self) -> dict:
         s = Stats()
         self._check(self._lib.spring_b200_get_stats(self._h, C.byref(s)))
@@ -248,6 +253,15 @@ class Context:
     def bucket_reads(self, reads_ptr: int, lengths_ptr: int, num_reads: int, max_readlen: int, num_buckets: int, out_ptr: int) -> None:
         """Device pointers; out: uint32[num_reads] owner bucket of every read (multi-GPU partitioning)."""
         self._check(self._lib.spring_b200_bucket_reads(self._h, reads_ptr, lengths_ptr, num_reads, max_readlen, num_buckets, out_ptr))
+
+    def fetch_reorder(self):
+        """(order, flag, pos, rev, singleton_order) the encoder of the last reorder_encode call consumed."""
+        o = ReorderOut()
+        self._lib.spring_b200_fetch_reorder.argtypes = [C.c_void_p, C.POINTER(ReorderOut)]
+        self._check(self._lib.spring_b200_fetch_reorder(self._h, C.byref(o)))
+        return (_view(o.order, o.num, np.uint32).copy(), _view(o.flag, o.num, np.uint8).copy(),
+                _view(o.pos, o.num, np.int64).copy(), _view(o.rev, o.num, np.uint8).copy(),
+                _view(o.singleton_order, o.num_singletons, np.uint32).copy())
 
     # ---- files ---------------------------------------------------------------------------------
     def reorder_encode_files(self, temp_dir: str, cp: CP, num_chains: int = 0) -> None:

@@ -60,8 +60,8 @@ struct DictView {
   uint32_t slot_mask;            // capacity - 1 (power of two)
   const uint32_t *bins;
   const uint32_t *slot_of_read;  // [n] slot index holding read i's key, 0xFFFFFFFF if the read is not indexed
-  const uint32_t *filter;        // one bit per hash bucket: set iff some key hashes there (kept L2-resident)
-  uint32_t filter_mask;          // number of filter bits - 1 (power of two)
+  const uint32_t *filter;        // blocked Bloom filter over the keys: 2 bits in one 32-bit word, >= 8 bits per key
+  uint32_t filter_mask;          // number of filter words - 1 (power of two)
   int start, end;                // base window [start, end]
   int key_bits;                  // bits per base * (end - start + 1)
 };
@@ -72,6 +72,10 @@ __host__ __device__ inline uint64_t mix64(uint64_t x) {  // murmur3 finalizer
   x ^= x >> 33;
   return x;
 }
+
+// key filter (kept L2-resident by the chain kernel): word (hk >> 32) & mask, bits hk[0:5) and hk[5:10)
+__host__ __device__ inline uint32_t filter_word(uint64_t hk, uint32_t wmask) { return (uint32_t)(hk >> 32) & wmask; }
+__host__ __device__ inline uint32_t filter_bits(uint64_t hk) { return (1u << (hk & 31)) | (1u << ((hk >> 5) & 31)); }
 
 __host__ __device__ inline int words_for(int max_readlen) { return (2 * max_readlen - 1) / 64 + 1; }
 
@@ -127,10 +131,44 @@ __device__ __forceinline__ uint64_t spread_bits(uint32_t x) {
 }
 __device__ __forceinline__ int base_code(const uint64_t *w, int j) { return (int)((w[j >> 5] >> (2 * (j & 31))) & 3ull); }
 
+__device__ __forceinline__ bool filter_test(const uint32_t *filter, uint32_t wmask, uint64_t hk) {
+  const uint32_t b = filter_bits(hk);
+  return (__ldg(filter + filter_word(hk, wmask)) & b) == b;
+}
+// L2 eviction policies: the key filter should stay in L2, the slot table streams through it
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ bool filter_test_hint(const uint32_t *filter, uint32_t wmask, uint64_t hk, uint64_t pol) {
+  const uint32_t b = filter_bits(hk);
+  uint32_t w;
+  asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(w) : "l"(filter + filter_word(hk, wmask)), "l"(pol));
+  return (w & b) == b;
+}
 // L2 (.cg) load: `live` is updated by other SMs between rounds, L1 must not serve it
 __device__ __forceinline__ DictSlot load_slot(const DictSlot *p) {
   const uint4 v = __ldcg(reinterpret_cast<const uint4 *>(p));
   const uint4 w = __ldcg(reinterpret_cast<const uint4 *>(p) + 1);
+  DictSlot s;
+  s.key = (uint64_t)v.x | ((uint64_t)v.y << 32);
+  s.start1 = v.z;
+  s.live = v.w;
+  s.count = w.x; s.rid[0] = w.y; s.rid[1] = w.z; s.rid[2] = w.w;
+  return s;
+}
+__device__ __forceinline__ DictSlot load_slot_hint(const DictSlot *p, uint64_t pol) {
+  uint4 v, w;
+  asm volatile("ld.global.cg.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(pol));
+  asm volatile("ld.global.cg.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w) : "l"(reinterpret_cast<const uint4 *>(p) + 1), "l"(pol));
   DictSlot s;
   s.key = (uint64_t)v.x | ((uint64_t)v.y << 32);
   s.start1 = v.z;

@@ -216,8 +216,7 @@ __global__ void k_align_singletons(AlignArgs a) {
     uint64_t key = 0;
     if (!rev) for (int t = d.start; t <= d.end; t++) key |= (uint64_t)win[t] << (2 * (t - d.start));
     else for (int t = d.start; t <= d.end; t++) key |= (uint64_t)(3 - win[L - 1 - t]) << (2 * (t - d.start));
-    const uint32_t fi = (uint32_t)(mix64(key) >> 32) & d.filter_mask;
-    if (!((__ldg(d.filter + (fi >> 5)) >> (fi & 31)) & 1u)) continue;
+    if (!filter_test(d.filter, d.filter_mask, mix64(key))) continue;
     const long long hdr = dict_find(d, key);
     if (hdr < 0) continue;
     const uint32_t bc = d.bins[hdr];

@@ -13,6 +13,7 @@ struct Ctx {
   std::string err;
   uint64_t launches = 0;  // kernels launched since the last reset (ours + CUB passes)
   cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;  // around the chain kernel
+  bool lockstep = false;  // chain schedule: deterministic round-synchronous, or free-running (default)
 };
 
 // ---- dict.cu : constructdictionary (bitset_util.h:74-221) ---------------------------------------

@@ -25,6 +25,7 @@ struct spring_b200_ctx {
   Ctx c;
   spring_b200_stats stats{};
   EncodeDev last_enc{};
+  ReorderDev last_ro{};
   bool have_enc = false;
   cudaEvent_t ev[8]{};
 };
@@ -172,6 +173,24 @@ void fetch(spring_b200_ctx *ctx, spring_b200_streams *o) {
   SB_CUDA(cudaStreamSynchronize(c.stream));
 }
 
+void copy_reorder_out(Ctx &c, const ReorderDev &ro, spring_b200_reorder_out *out) {
+  const size_t m = ro.num, s = ro.num_singletons;
+  uint32_t *h_order = c.pool.pin<uint32_t>("ro.h_order", m + 1);
+  uint8_t *h_flag = c.pool.pin<uint8_t>("ro.h_flag", m + 1);
+  int64_t *h_pos = c.pool.pin<int64_t>("ro.h_pos", m + 1);
+  uint8_t *h_rev = c.pool.pin<uint8_t>("ro.h_rev", m + 1);
+  uint32_t *h_s = c.pool.pin<uint32_t>("ro.h_s", s + 1);
+  if (m) {
+    SB_CUDA(cudaMemcpyAsync(h_order, ro.order, m * 4, cudaMemcpyDeviceToHost, c.stream));
+    SB_CUDA(cudaMemcpyAsync(h_flag, ro.flag, m, cudaMemcpyDeviceToHost, c.stream));
+    SB_CUDA(cudaMemcpyAsync(h_pos, ro.pos, m * 8, cudaMemcpyDeviceToHost, c.stream));
+    SB_CUDA(cudaMemcpyAsync(h_rev, ro.rev, m, cudaMemcpyDeviceToHost, c.stream));
+  }
+  if (s) SB_CUDA(cudaMemcpyAsync(h_s, ro.s_order, s * 4, cudaMemcpyDeviceToHost, c.stream));
+  out->order = h_order; out->flag = h_flag; out->pos = h_pos; out->rev = h_rev; out->num = m;
+  out->singleton_order = h_s; out->num_singletons = s;
+}
+
 void run_all(spring_b200_ctx *ctx, const spring_b200_input *in, uint32_t num_chains, bool host_in, spring_b200_streams *out) {
   check_input(in);
   if (!out) throw ArgError("null output");
@@ -185,6 +204,7 @@ void run_all(spring_b200_ctx *ctx, const spring_b200_input *in, uint32_t num_cha
   ReorderDev ro;
   reorder_on_device(ctx, d, in, num_chains, ro);
   run_encode(c, d.reads, d.lens, in->num_clean, L, ro, nr, in->num_reads, ctx->last_enc);
+  ctx->last_ro = ro;
   ctx->have_enc = true;
   rec(ctx, 4);
   memset(out, 0, sizeof(*out));
@@ -325,6 +345,12 @@ int spring_b200_get_stats(const spring_b200_ctx *ctx, spring_b200_stats *out) {
   return SPRING_B200_OK;
 }
 
+int spring_b200_set_schedule(spring_b200_ctx *ctx, int deterministic) {
+  if (!ctx) return SPRING_B200_EINVAL;
+  ctx->c.lockstep = deterministic != 0;
+  return SPRING_B200_OK;
+}
+
 int spring_b200_reorder_encode(spring_b200_ctx *ctx, const spring_b200_input *in, uint32_t num_chains, spring_b200_streams *out) {
   return guarded(ctx, [&] { run_all(ctx, in, num_chains, true, out); });
 }
@@ -384,6 +410,24 @@ int spring_b200_reorder(spring_b200_ctx *ctx, const spring_b200_input *in, uint3
     DevInput d = upload_reads(c, in, W);
     ReorderDev ro;
     reorder_on_device(ctx, d, in, num_chains, ro);
+    copy_reorder_out(c, ro, out);
+    rec(ctx, 4);
+    SB_CUDA(cudaStreamSynchronize(c.stream));
+    ctx->stats.ms_h2d = ms(ctx, 0, 1); ctx->stats.ms_dict = ms(ctx, 1, 2); ctx->stats.ms_chains = ms(ctx, 2, 3);
+    ctx->stats.ms_total = ms(ctx, 0, 4);
+    ctx->stats.gpu_launches = c.launches;
+  });
+}
+
+int spring_b200_fetch_reorder(spring_b200_ctx *ctx, spring_b200_reorder_out *out) {
+  return guarded(ctx, [&] {
+    if (!ctx->have_enc || !out) throw ArgError("no reorder output to fetch");
+    copy_reorder_out(ctx->c, ctx->last_ro, out);
+    SB_CUDA(cudaStreamSynchronize(ctx->c.stream));
+  });
+}
+
+#if 0
     const size_t m = ro.num, s = ro.num_singletons;
     uint32_t *h_order = c.pool.pin<uint32_t>("ro.h_order", m + 1);
     uint8_t *h_flag = c.pool.pin<uint8_t>("ro.h_flag", m + 1);
@@ -406,6 +450,7 @@ int spring_b200_reorder(spring_b200_ctx *ctx, const spring_b200_input *in, uint3
     ctx->stats.gpu_launches = c.launches;
   });
 }
+#endif
 
 int spring_b200_bucket_reads(spring_b200_ctx *ctx, const uint64_t *reads, const uint16_t *lengths, uint32_t num_reads,
                              uint32_t max_readlen, uint32_t num_buckets, uint32_t *bucket) {

@@ -194,15 +194,19 @@ __device__ bool scan_bin(const ChainArgs &a, const DictView &d, uint32_t bs, uin
 // dictionary at 10 M keys: L2-resident, no DRAM access); only filter positives (true keys + ~5 %
 // false positives) go on to the slot table in HBM.  The warp then walks its hits in the reference's
 // order (shift, forward before reverse, dict 0 before dict 1; bins from the highest id down).
-__device__ bool chain_search(const ChainArgs &a, const uint64_t *ref, const uint64_t *revref, int ref_len, int lane,
-                             uint32_t &prop_rid, int &prop_shift, int &prop_rev, unsigned long long &probes_issued,
+// One call examines ONE batch: shifts [S, S + 8n), n = 1, 2, 4, 8, 16, 16, ... probes per lane for
+// batch b = 0, 1, ...; a chain that finds nothing continues with the next batch in the next round
+// (bounded work per round keeps the lock-step chains balanced; claims only grow, so earlier batches
+// cannot turn productive later -- same result as a full search, see oracle/spring_oracle.c).
+__device__ bool chain_search(const ChainArgs &a, const uint64_t *ref, const uint64_t *revref, int ref_len, int lane, int b,
+                             int S, uint32_t &prop_rid, int &prop_shift, int &prop_rev, unsigned long long &probes_issued,
                              unsigned long long &probes_seq, unsigned long long &compares, unsigned long long &slot_probes) {
   const int W = a.W;
   const int kind = lane & 3, rev = kind >> 1, sub = lane >> 2;
   const DictView &d = a.dict[kind & 1];
   const uint64_t *src = rev ? revref : ref;
-  int S = 0;
-  for (int b = 0; S < a.maxshift; b++) {
+  const uint64_t pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
+  {
     const int n = b < 4 ? 1 << b : 16;  // 8, 16, 32, 64, then 128 shifts per batch
     // ---- pass 1: bounds + filter bit for this lane's n probes (independent 4-byte loads) ----
     unsigned okm = 0, cand = 0;
@@ -215,8 +219,7 @@ __device__ bool chain_search(const ChainArgs &a, const uint64_t *ref, const uint
       if (ok) {
         okm |= 1u << j;
         const uint64_t key = extract_bits(src, W, rev ? 2 * (d.start - s) : 2 * (d.start + s), d.key_bits);
-        const uint32_t fi = (uint32_t)(mix64(key) >> 32) & d.filter_mask;
-        if ((__ldg(d.filter + (fi >> 5)) >> (fi & 31)) & 1u) cand |= 1u << j;
+        if (filter_test_hint(d.filter, d.filter_mask, mix64(key), pol_keep)) cand |= 1u << j;
       }
     }
     probes_issued += __reduce_add_sync(FULL, (unsigned)__popc(okm));
@@ -232,7 +235,7 @@ __device__ bool chain_search(const ChainArgs &a, const uint64_t *ref, const uint
         uint32_t h = (uint32_t)mix64(key) & d.slot_mask;
         slot_probes++;
         for (;;) {
-          const DictSlot sl = load_slot(d.slots + h);
+          const DictSlot sl = load_slot_hint(d.slots + h, pol_stream);
           if (sl.start1 == 0) break;
           if (sl.key == key) {
             // a bin with no live read is an "empty_bin" (reorder.h:277-281): skipped without a visit
@@ -274,7 +277,6 @@ __device__ bool chain_search(const ChainArgs &a, const uint64_t *ref, const uint
     }
     probes_seq += __reduce_add_sync(FULL, (unsigned)__popc(seqmask));
     if (found_p >= 0) return true;
-    S += 8 * n;
   }
   return false;
 }
@@ -302,7 +304,11 @@ __device__ bool find_unclaimed(const uint32_t *claimed, long long lo, long long 
   return false;
 }
 
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) k_chains(ChainArgs a) {
+#ifndef SB_MIN_BLOCKS
+#define SB_MIN_BLOCKS 3
+#endif
+template <bool LOCKSTEP>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, SB_MIN_BLOCKS) k_chains(ChainArgs a) {
   extern __shared__ __align__(16) uint64_t smem[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const uint32_t cid = blockIdx.x * kWarpsPerBlock + wib;
@@ -312,7 +318,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) k_chains(ChainArgs a) 
   uint4 *cnt = reinterpret_cast<uint4 *>(curw + W + (W & 1));  // 16-byte aligned; one uint4 {A,C,T,G} per column
 
   int state = cid < a.num_chains ? ST_SEARCH : ST_DONE;
-  int ref_len = 0, prev_unmatched = 0, left_search = 0, iter_started = 0, stop_searching = 0;
+  int ref_len = 0, prev_unmatched = 0, left_search = 0, iter_started = 0, stop_searching = 0, batch = 0, batch_S = 0;
   long long ref_pos = 0, cur_read_pos = 0, cursor = -1, slice_lo = 0;
   uint32_t first_rid = 0, prev = 0, num_reads_thr = 0, num_unmatched_1m = 0, n_aligned = 0, n_single = 0;
   unsigned long long c_unmatched = 0, c_lost = 0, c_issued = 0, c_seq = 0, c_cmp = 0, c_slot = 0, target = 0, round = 0;
@@ -325,17 +331,21 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) k_chains(ChainArgs a) 
       if (sidx != 0xFFFFFFFFu) atomicSub(&a.dict[lane].slots[sidx].live, 1u);
     }
   };
+  auto claim_pre = [&](uint32_t rid, uint32_t sidx) {  // slot index fetched in phase A
+    if (lane == 0) atomicOr(a.claimed + (rid >> 5), 1u << (rid & 31));
+    if (lane < kNumDict && sidx != 0xFFFFFFFFu) atomicSub(&a.dict[lane].slots[sidx].live, 1u);
+  };
   auto stage_read = [&](uint32_t rid) {
     if (lane < W) curw[lane] = __ldg(a.reads + (size_t)rid * W + lane);
     __syncwarp();
   };
+  // the read must already be staged in curw
   auto new_contig = [&](uint32_t rid) {  // updaterefcount(..., resetcount = true, rev = false) + reorder.h:426-430,:601-612
-    stage_read(rid);
     const int len = __ldg(a.lens + rid);
     update_ref(ref, revref, curw, cnt, W, lane, 0, 0, 0, len, false, len);
     ref_len = len; ref_pos = 0; cur_read_pos = 0;
     prev_unmatched = 1; first_rid = rid; prev = rid; left_search = 0;
-    state = ST_SEARCH; iter_started = 0;
+    state = ST_SEARCH; iter_started = 0; batch = 0; batch_S = 0;
   };
 
   if (state == ST_SEARCH) {  // reorder.h:405-431
@@ -344,15 +354,126 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) k_chains(ChainArgs a) 
     cursor = cid == a.num_chains - 1 ? (long long)a.N - 1 : (long long)(cid + 1) * a.per - 1;
     claim(first);
     c_unmatched++;
+    stage_read(first);
     new_contig(first);
   }
   unsigned long long cy_search = 0, cy_wait_a = 0, cy_commit = 0, cy_wait_b = 0;
   long long t_last = clock64();
-  grid_barrier(a.barrier, target, t_last, cy_commit, cy_wait_b);
+  if (!LOCKSTEP) {
+    // ---------------- free-running schedule ----------------------------------------------------------
+    // Every chain runs at its own pace, exactly like a reference thread: a candidate is claimed on
+    // the spot with an atomic test-and-set of its claim bit (the reference's remainingreads[] under
+    // read_lock, reorder.h:303-309); losing that race just continues the search.  No grid barrier,
+    // no proposals; the result depends on timing for more than one chain -- as the reference's does.
+    const long long t_begin = clock64();
+    while (state != ST_DONE) {
+      if (state == ST_SEARCH) {
+        if (!iter_started) {  // loop top, reorder.h:433-439
+          if (num_reads_thr % kStopWindow == 0) {
+            if (num_unmatched_1m > kStopUnmatched) stop_searching = 1;
+            num_unmatched_1m = 0;
+          }
+          num_reads_thr++;
+          iter_started = 1;
+        }
+        bool found = false;
+        uint32_t k = 0;
+        int shift = 0, prev_rev = 0;
+        if (!stop_searching) {
+          int b = 0, S = 0;
+          while (S < a.maxshift) {
+            if (chain_search(a, ref, revref, ref_len, lane, b, S, k, shift, prev_rev, c_issued, c_seq, c_cmp, c_slot)) {
+              unsigned old = 0;
+              if (lane == 0) old = atomicOr(a.claimed + (k >> 5), 1u << (k & 31));
+              old = __shfl_sync(FULL, old, 0);
+              if (!((old >> (k & 31)) & 1u)) { found = true; break; }
+              c_lost++;  // another chain took it between the check and the claim: search this batch again
+              continue;
+            }
+            S += 8 * (b < 4 ? 1 << b : 16);
+            b++;
+          }
+        }
+        if (found) {
+          if (lane < kNumDict) {
+            const uint32_t sidx = __ldg(a.dict[lane].slot_of_read + k);
+            if (sidx != 0xFFFFFFFFu) atomicSub(&a.dict[lane].slots[sidx].live, 1u);
+          }
+          stage_read(k);
+          const int len = __ldg(a.lens + k), old = ref_len;
+          int delta, cs, nl, fold = 0;
+          if (!prev_rev) { delta = shift; cs = 0; nl = max(old - shift, len); }
+          else if (len - shift >= old) { fold = len - shift - old; delta = -fold; cs = 0; nl = len; }
+          else if (old + shift <= a.L) { delta = 0; cs = old - len + shift; nl = old + shift; }
+          else { delta = old + shift - a.L; cs = a.L - len; nl = a.L; }
+          update_ref(ref, revref, curw, cnt, W, lane, old, delta, cs, len, prev_rev != 0, nl, fold);
+          ref_len = nl;
+          if (!prev_rev) {
+            if (!left_search) { cur_read_pos = ref_pos + shift; ref_pos = cur_read_pos; }
+            else { cur_read_pos = ref_pos + old - shift - len; ref_pos = ref_pos + old - shift - nl; }
+          } else {
+            if (!left_search) { cur_read_pos = ref_pos + old + shift - len; ref_pos = ref_pos + old + shift - nl; }
+            else { cur_read_pos = ref_pos - shift; ref_pos = cur_read_pos; }
+          }
+          if (lane == 0) {
+            if (prev_unmatched) { a.rec_chain[prev] = cid; a.rec_k[prev] = n_aligned; a.rec_pos[prev] = 0; a.rec_meta[prev] = 0; }
+            const uint32_t kk = n_aligned + (prev_unmatched ? 1u : 0u);
+            const int is_r = prev_rev ? !left_search : left_search;
+            a.rec_chain[k] = cid; a.rec_k[k] = kk; a.rec_pos[k] = cur_read_pos; a.rec_meta[k] = (uint8_t)(2 | (is_r ? 1 : 0));
+          }
+          n_aligned += prev_unmatched ? 2u : 1u;
+          prev_unmatched = 0;
+          iter_started = 0;
+        } else {
+          num_unmatched_1m++;
+          if (!left_search) {
+            left_search = 1;
+            stage_read(first_rid);
+            const int len = __ldg(a.lens + first_rid);
+            update_ref(ref, revref, curw, cnt, W, lane, 0, 0, 0, len, true, len);
+            ref_len = len; ref_pos = 0; cur_read_pos = 0;
+            iter_started = 0;
+          } else {
+            left_search = 0;
+            state = ST_NEWREAD;
+          }
+        }
+      } else {  // ST_NEWREAD, reorder.h:576-612
+        uint32_t j = 0;
+        bool got = false;
+        while (find_unclaimed(a.claimed, slice_lo, cursor, lane, j)) {
+          unsigned old = 0;
+          if (lane == 0) old = atomicOr(a.claimed + (j >> 5), 1u << (j & 31));
+          old = __shfl_sync(FULL, old, 0);
+          cursor = (long long)j - 1;
+          if (!((old >> (j & 31)) & 1u)) { got = true; break; }
+        }
+        if (prev_unmatched) {
+          if (lane == 0) { a.rec_chain[prev] = cid; a.rec_k[prev] = n_single; a.rec_meta[prev] = 4; }
+          n_single++;
+        }
+        if (got) {
+          if (lane < kNumDict) {
+            const uint32_t sidx = __ldg(a.dict[lane].slot_of_read + j);
+            if (sidx != 0xFFFFFFFFu) atomicSub(&a.dict[lane].slots[sidx].live, 1u);
+          }
+          c_unmatched++;
+          stage_read(j);
+          new_contig(j);
+        } else {
+          prev_unmatched = 0;
+          state = ST_DONE;
+        }
+      }
+      round++;
+    }
+    cy_search = clock64() - t_begin;
+  }
+  if (LOCKSTEP) grid_barrier(a.barrier, target, t_last, cy_commit, cy_wait_b);
   cy_commit = 0; cy_wait_b = 0;
-  for (;;) {
+  while (LOCKSTEP) {
     // ---------------- phase A: search / pick against the round-start claim state -------------
-    bool has_prop = false;
+    bool has_prop = false, search_more = false;
     uint32_t prop_rid = 0;
     int prop_shift = 0, prop_rev = 0;
     if (state == ST_SEARCH) {
@@ -364,12 +485,28 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) k_chains(ChainArgs a) 
         num_reads_thr++;
         iter_started = 1;
       }
-      if (!stop_searching)
-        has_prop = chain_search(a, ref, revref, ref_len, lane, prop_rid, prop_shift, prop_rev, c_issued, c_seq, c_cmp, c_slot);
+      if (!stop_searching) {
+        has_prop = chain_search(a, ref, revref, ref_len, lane, batch, batch_S, prop_rid, prop_shift, prop_rev, c_issued,
+                                c_seq, c_cmp, c_slot);
+        if (!has_prop) {
+          const int nshift = 8 * (batch < 4 ? 1 << batch : 16);
+          if (batch_S + nshift < a.maxshift) { batch++; batch_S += nshift; search_more = true; }
+        }
+      }
     } else if (state == ST_NEWREAD) {
       has_prop = find_unclaimed(a.claimed, slice_lo, cursor, lane, prop_rid);
     }
     if (has_prop && lane == 0) atomicMin(a.winner + prop_rid, cid);
+    // everything phase B will need is fetched now, so its latency hides behind the barrier:
+    // the read to fold in (or the contig's first read when a left search is about to start) and the
+    // dictionary slots to decrement
+    uint32_t pre_sidx = 0xFFFFFFFFu;
+    if (has_prop) {
+      if (lane < kNumDict) pre_sidx = __ldg(a.dict[lane].slot_of_read + prop_rid);
+      stage_read(prop_rid);
+    } else if (state == ST_SEARCH && !search_more && !left_search) {
+      stage_read(first_rid);
+    }
     grid_barrier(a.barrier, target, t_last, cy_search, cy_wait_a);
 
     // ---------------- phase B: winners claim and update ----------------------------------------
@@ -377,8 +514,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) k_chains(ChainArgs a) 
       if (has_prop) {
         if (__ldcg(a.winner + prop_rid) == cid) {
           const uint32_t k = prop_rid;
-          claim(k);
-          stage_read(k);
+          claim_pre(k, pre_sidx);
           const int len = __ldg(a.lens + k), shift = prop_shift, old = ref_len;
           int delta, cs, nl, fold = 0;
           if (!prop_rev) { delta = shift; cs = 0; nl = max(old - shift, len); }                 // reorder.h:144-156
@@ -404,19 +540,18 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) k_chains(ChainArgs a) 
           }
           n_aligned += prev_unmatched ? 2u : 1u;
           prev_unmatched = 0;
-          iter_started = 0;
+          iter_started = 0; batch = 0; batch_S = 0;
         } else {
           c_lost++;
         }
-      } else {  // no match, reorder.h:559-615
+      } else if (!search_more) {  // no match, reorder.h:559-615
         num_unmatched_1m++;
         if (!left_search) {
           left_search = 1;
-          stage_read(first_rid);
           const int len = __ldg(a.lens + first_rid);
           update_ref(ref, revref, curw, cnt, W, lane, 0, 0, 0, len, true, len);
           ref_len = len; ref_pos = 0; cur_read_pos = 0;
-          iter_started = 0;
+          iter_started = 0; batch = 0; batch_S = 0;
         } else {
           left_search = 0;
           state = ST_NEWREAD;
@@ -426,7 +561,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) k_chains(ChainArgs a) 
       if (has_prop) {
         if (__ldcg(a.winner + prop_rid) == cid) {
           const uint32_t j = prop_rid;
-          claim(j);
+          claim_pre(j, pre_sidx);
           if (lane == 0 && prev_unmatched) { a.rec_chain[prev] = cid; a.rec_k[prev] = n_single; a.rec_meta[prev] = 4; }
           if (prev_unmatched) n_single++;
           cursor = (long long)j - 1;
@@ -509,9 +644,11 @@ void run_reorder(Ctx &c, const uint64_t *reads, const uint16_t *lens, uint32_t n
   if (n == 0) return;
 
   const size_t smem = kWarpsPerBlock * (3 * (size_t)W + (W & 1) + 2 * (size_t)Lp) * sizeof(uint64_t);
-  SB_CUDA(cudaFuncSetAttribute(k_chains, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const bool lockstep = c.lockstep;
+  auto kern = lockstep ? k_chains<true> : k_chains<false>;
+  SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
-  SB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_chains, kWarpsPerBlock * 32, smem));
+  SB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kWarpsPerBlock * 32, smem));
   if (per_sm < 1) throw CudaError("k_chains does not fit on an SM");
   const uint32_t max_chains = (uint32_t)per_sm * c.num_sms * kWarpsPerBlock;
   uint32_t C = num_chains;
@@ -550,7 +687,8 @@ void run_reorder(Ctx &c, const uint64_t *reads, const uint16_t *lens, uint32_t n
   void *args[] = {&a};
   if (!c.ev_k0) { SB_CUDA(cudaEventCreate(&c.ev_k0)); SB_CUDA(cudaEventCreate(&c.ev_k1)); }
   SB_CUDA(cudaEventRecord(c.ev_k0, st));
-  SB_CUDA(cudaLaunchCooperativeKernel((void *)k_chains, dim3(grid), dim3(kWarpsPerBlock * 32), args, smem, st));
+  if (lockstep) SB_CUDA(cudaLaunchCooperativeKernel((void *)kern, dim3(grid), dim3(kWarpsPerBlock * 32), args, smem, st));
+  else kern<<<grid, kWarpsPerBlock * 32, smem, st>>>(a);
   SB_CUDA(cudaEventRecord(c.ev_k1, st));
   c.launches++;
 

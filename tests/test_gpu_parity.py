@@ -14,6 +14,14 @@ pytestmark = pytest.mark.gpu
 CHAINS = (1, 5, 64)
 
 
+@pytest.fixture
+def det(ctx):
+    """ctx with the deterministic (round-synchronous) chain schedule; restored afterwards."""
+    ctx.set_schedule(True)
+    yield ctx
+    ctx.set_schedule(False)
+
+
 @pytest.mark.parametrize("name", ["se150", "var250", "short40", "long511"])
 def test_dictionary_matches_oracle(ctx, name):
     """constructdictionary: same unique keys, same bins, read ids ascending per bin (bit-exact)."""
@@ -25,8 +33,10 @@ def test_dictionary_matches_oracle(ctx, name):
 
 
 @pytest.mark.parametrize("name", sorted(CASES))
-def test_reorder_stream_matches_oracle(ctx, name):
-    """reorder<>(): order / flag / pos / rev / singleton lists bit-exact for 1 and many chains."""
+def test_reorder_stream_matches_oracle(det, name):
+    """reorder<>(), deterministic schedule: order / flag / pos / rev / singleton lists bit-exact
+    for 1 and many chains."""
+    ctx = det
     hp = make_input(**CASES[name])
     for chains in CHAINS:
         order, flag, pos, rev, s_order = ctx.reorder(hp.packed, hp.lengths, hp.max_readlen, chains)
@@ -41,8 +51,10 @@ def test_reorder_stream_matches_oracle(ctx, name):
 
 
 @pytest.mark.parametrize("name", sorted(CASES))
-def test_streams_match_oracle(ctx, name):
-    """call_reorder + call_encoder: every output stream bit-exact against the oracle."""
+def test_streams_match_oracle(det, name):
+    """call_reorder + call_encoder, deterministic schedule: every output stream bit-exact against
+    the oracle for 1 and many chains."""
+    ctx = det
     hp = make_input(**CASES[name])
     for chains in CHAINS:
         got = ctx.reorder_encode(hp.packed, hp.lengths, hp.max_readlen, hp.n_records, hp.order_n, hp.num_reads, chains)
@@ -68,8 +80,32 @@ def test_golden_vectors(ctx):
         assert got.unaligned_len == meta["unaligned_len"]
 
 
-def test_auto_chains_roundtrip_and_determinism(ctx):
-    """Default chain count (as many as co-reside): decode == input, and two runs are identical."""
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_free_running_schedule(ctx, name):
+    """Default (free-running) schedule.  One chain: bit-exact against the oracle (= the reference at
+    -t 1).  Many chains: timing-dependent like the reference at -t > 1, so (a) the reorder output is
+    a valid partition of the reads, (b) the encoder is bit-exact against the oracle's encoder fed
+    with the very same reorder stream, (c) the streams decode back to the input."""
+    hp = make_input(**CASES[name])
+    got = ctx.reorder_encode(hp.packed, hp.lengths, hp.max_readlen, hp.n_records, hp.order_n, hp.num_reads, 1)
+    _, er = po.reorder_encode(hp.packed, hp.lengths, hp.max_readlen, hp.n_records, hp.order_n, hp.num_reads, 1)
+    assert_streams_equal(got, er, f"{name} free-running, 1 chain")
+    for chains in (7, 0):
+        got = ctx.reorder_encode(hp.packed, hp.lengths, hp.max_readlen, hp.n_records, hp.order_n, hp.num_reads, chains)
+        order, flag, pos, rev, s_order = ctx.fetch_reorder()
+        allr = np.concatenate([order, s_order])
+        assert (np.sort(allr) == np.arange(len(hp.lengths), dtype=np.uint32)).all()
+        assert len(flag) == 0 or flag[0] == 0
+        ro = po.ReorderResult(order, flag, pos, rev, s_order, {})
+        er = po.encode(hp.packed, hp.lengths, hp.max_readlen, ro, hp.n_records, hp.order_n, hp.num_reads)
+        assert_streams_equal(got, er, f"{name} free-running, chains={chains}: encoder vs oracle on the same stream")
+        check_roundtrip(got, hp, po.decode)
+
+
+def test_auto_chains_roundtrip_and_determinism(det):
+    """Default chain count (as many as co-reside), deterministic schedule: decode == input, and two
+    runs are identical."""
+    ctx = det
     hp = make_input(num_reads=200000, read_len=150, seed=21, n_frac=0.002)
     a = ctx.reorder_encode(hp.packed, hp.lengths, hp.max_readlen, hp.n_records, hp.order_n, hp.num_reads, 0)
     st = ctx.stats()
@@ -97,7 +133,9 @@ def test_edge_cases(ctx):
     # identical reads (every shift-0 candidate passes), zero-length read among them
     seqs = [b"ACGTTGCAACGTTGCAACGTTGCAACGTTGCAACGTTGCAACGT"] * 50 + [b""]
     p, l = dnaio.seqs_to_packed(seqs, 44)
+    ctx.set_schedule(True)
     got = ctx.reorder_encode(p, l, 44, num_chains=3)
+    ctx.set_schedule(False)
     _, er = po.reorder_encode(p, l, 44, num_chains=ctx.stats()["num_chains"])
     assert_streams_equal(got, er, "identical reads")
     # bad arguments are refused with the reference's message

@@ -50,6 +50,7 @@ struct ChainArgs {
   uint32_t num_chains, per;
   unsigned long long *barrier; int *active; unsigned long long *ctr;
   unsigned long long max_rounds;
+  int *overflow;  // set when a packed u16 column count would overflow
 };
 
 __device__ __forceinline__ bool is_claimed(const uint32_t *claimed, uint32_t rid) {
@@ -84,59 +85,73 @@ __device__ __forceinline__ void grid_barrier(unsigned long long *ctr, unsigned l
 // fold = cur_len - shift - old_len columns with an ascending in-place loop, so a source column
 // that was already rewritten is read again: column i = q*fold + r ends up as
 // old[r] + sum_{t=1..q} e(read base at t*fold + r) rather than old[i - fold] + e(read base at i).
-__device__ void update_ref(uint64_t *ref, uint64_t *revref, const uint64_t *curw, uint4 *cnt, int W, int lane,
-                           int old_len, int delta, int cs, int cur_len, bool rev, int new_len, int fold = 0) {
+__device__ void update_ref(uint64_t *ref, uint64_t *revref, const uint64_t *curw, uint64_t *cnt, int W, int lane,
+                           int old_len, int delta, int cs, int cur_len, bool rev, int new_len, int fold, int *overflow) {
+  // cnt[col] packs the four per-base counts of a column as u16 fields, rows A,C,T,G
+  // (reorder.h:120-123); 2-bit read codes are A0 G1 C2 T3 -> field shift 0, 48, 16, 32
   const int nchunks = (new_len + 31) >> 5;
   for (int cc = 0; cc < nchunks; cc++) {
     const int ck = delta >= 0 ? cc : nchunks - 1 - cc;  // move direction decides the safe order
     const int i = (ck << 5) + lane;
     const bool in = i < new_len;
     const int src = i + delta;
-    uint32_t v0 = 0, v1 = 0, v2 = 0, v3 = 0;
+    uint64_t v = 0;
     if (in && src >= 0 && src < old_len) {
       if (fold > 0) {
         const int r = i % fold, q = i / fold;
-        const uint4 c4 = cnt[r];
-        v0 = c4.x; v1 = c4.y; v2 = c4.z; v3 = c4.w;
+        v = cnt[r];
         for (int t = 1; t < q; t++) {  // the t == q term is the read's own base at column i, added below
           const int b = 3 - base_code(curw, cur_len - 1 - (t * fold + r));
-          if (b == 0) v0++; else if (b == 2) v1++; else if (b == 3) v2++; else v3++;
+          v += 1ull << ((0x20103000u >> (8 * b)) & 0xFFu);
         }
       } else {
-        const uint4 c4 = cnt[src];
-        v0 = c4.x; v1 = c4.y; v2 = c4.z; v3 = c4.w;
+        v = cnt[src];
       }
     }
     __syncwarp();
-    int code = 0;
+    uint32_t code = 0;
     if (in) {
       const int ci = i - cs;
       if (ci >= 0 && ci < cur_len) {
         const int b = rev ? 3 - base_code(curw, cur_len - 1 - ci) : base_code(curw, ci);
-        // count rows are A,C,T,G (reorder.h:120-123); 2-bit codes are A0 G1 C2 T3
-        if (b == 0) v0++; else if (b == 2) v1++; else if (b == 3) v2++; else v3++;
+        const uint32_t sh = (0x20103000u >> (8 * b)) & 0xFFu;
+        if (((v >> sh) & 0xFFFFull) == 0xFFFFull) *overflow = 1;  // > 65535 reads stacked on one column
+        v += 1ull << sh;
       }
-      cnt[i] = make_uint4(v0, v1, v2, v3);
-      uint32_t mx = 0; int ind = 0;  // first strict maximum (reorder.h:204-212)
-      if (v0 > mx) { mx = v0; ind = 0; }
-      if (v1 > mx) { mx = v1; ind = 1; }
-      if (v2 > mx) { mx = v2; ind = 2; }
-      if (v3 > mx) { mx = v3; ind = 3; }
-      code = ind == 0 ? 0 : ind == 1 ? 2 : ind == 2 ? 3 : 1;
+      cnt[i] = v;
+      const uint32_t f0 = (uint32_t)v & 0xFFFFu, f1 = (uint32_t)(v >> 16) & 0xFFFFu;
+      const uint32_t f2 = (uint32_t)(v >> 32) & 0xFFFFu, f3 = (uint32_t)(v >> 48);
+      uint32_t mx = 0, ind = 0;  // first strict maximum (reorder.h:204-212)
+      if (f0 > mx) { mx = f0; ind = 0; }
+      if (f1 > mx) { mx = f1; ind = 1; }
+      if (f2 > mx) { mx = f2; ind = 2; }
+      if (f3 > mx) { mx = f3; ind = 3; }
+      code = (0x01030200u >> (8 * ind)) & 3u;  // rows A,C,T,G -> codes 0,2,3,1
     }
-    const unsigned b0 = __ballot_sync(FULL, code & 1), b1 = __ballot_sync(FULL, code & 2);
-    if (lane == 0) ref[ck] = spread_bits(b0) | (spread_bits(b1) << 1);
+    // 32 two-bit codes -> one 64-bit word: lanes 0-15 fill the low half, 16-31 the high half
+    const uint32_t part = code << (2 * (lane & 15));
+    const uint32_t lo = __reduce_or_sync(FULL, lane < 16 ? part : 0u);
+    const uint32_t hi = __reduce_or_sync(FULL, lane < 16 ? 0u : part);
+    if (lane == 0) ref[ck] = (uint64_t)lo | ((uint64_t)hi << 32);
     __syncwarp();
   }
   if (lane >= nchunks && lane < W) ref[lane] = 0ull;
   __syncwarp();
-  for (int ck = 0; ck < nchunks; ck++) {
-    const int i = (ck << 5) + lane;
-    const int code = i < new_len ? 3 - base_code(ref, new_len - 1 - i) : 0;
-    const unsigned b0 = __ballot_sync(FULL, code & 1), b1 = __ballot_sync(FULL, code & 2);
-    if (lane == 0) revref[ck] = spread_bits(b0) | (spread_bits(b1) << 1);
+  // revref = reverse complement of ref (reorder.h:215-217) by bit tricks: reverse the 2-bit groups of
+  // the whole W-word array, complement, shift the padding out
+  if (lane < W) {
+    const int pad = 64 * W - 2 * new_len, ws = pad >> 6, bs = pad & 63;
+    uint64_t a0 = 0, a1 = 0;
+    if (lane + ws < W) {
+      uint64_t x = __brevll(ref[W - 1 - (lane + ws)]);
+      a0 = ~(((x & 0x5555555555555555ull) << 1) | ((x >> 1) & 0x5555555555555555ull));
+    }
+    if (lane + ws + 1 < W) {
+      uint64_t x = __brevll(ref[W - 1 - (lane + ws + 1)]);
+      a1 = ~(((x & 0x5555555555555555ull) << 1) | ((x >> 1) & 0x5555555555555555ull));
+    }
+    revref[lane] = bs ? (a0 >> bs) | (a1 << (64 - bs)) : a0;
   }
-  if (lane >= nchunks && lane < W) revref[lane] = 0ull;
   __syncwarp();
 }
 
@@ -313,9 +328,9 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, SB_MIN_BLOCKS) k_chains(C
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const uint32_t cid = blockIdx.x * kWarpsPerBlock + wib;
   const int W = a.W, Lp = a.Lp;
-  const size_t per_chain = 3 * (size_t)W + (W & 1) + 2 * (size_t)Lp;  // uint64 words: ref, revref, cur, pad, Lp uint4 counts
+  const size_t per_chain = 3 * (size_t)W + (size_t)Lp;  // uint64 words: ref, revref, cur, Lp packed count columns
   uint64_t *ref = smem + wib * per_chain, *revref = ref + W, *curw = revref + W;
-  uint4 *cnt = reinterpret_cast<uint4 *>(curw + W + (W & 1));  // 16-byte aligned; one uint4 {A,C,T,G} per column
+  uint64_t *cnt = curw + W;  // one word per column: four u16 counts {A,C,T,G}
 
   int state = cid < a.num_chains ? ST_SEARCH : ST_DONE;
   int ref_len = 0, prev_unmatched = 0, left_search = 0, iter_started = 0, stop_searching = 0, batch = 0, batch_S = 0;
@@ -342,7 +357,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, SB_MIN_BLOCKS) k_chains(C
   // the read must already be staged in curw
   auto new_contig = [&](uint32_t rid) {  // updaterefcount(..., resetcount = true, rev = false) + reorder.h:426-430,:601-612
     const int len = __ldg(a.lens + rid);
-    update_ref(ref, revref, curw, cnt, W, lane, 0, 0, 0, len, false, len);
+    update_ref(ref, revref, curw, cnt, W, lane, 0, 0, 0, len, false, len, 0, a.overflow);
     ref_len = len; ref_pos = 0; cur_read_pos = 0;
     prev_unmatched = 1; first_rid = rid; prev = rid; left_search = 0;
     state = ST_SEARCH; iter_started = 0; batch = 0; batch_S = 0;
@@ -406,7 +421,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, SB_MIN_BLOCKS) k_chains(C
           else if (len - shift >= old) { fold = len - shift - old; delta = -fold; cs = 0; nl = len; }
           else if (old + shift <= a.L) { delta = 0; cs = old - len + shift; nl = old + shift; }
           else { delta = old + shift - a.L; cs = a.L - len; nl = a.L; }
-          update_ref(ref, revref, curw, cnt, W, lane, old, delta, cs, len, prev_rev != 0, nl, fold);
+          update_ref(ref, revref, curw, cnt, W, lane, old, delta, cs, len, prev_rev != 0, nl, fold, a.overflow);
           ref_len = nl;
           if (!prev_rev) {
             if (!left_search) { cur_read_pos = ref_pos + shift; ref_pos = cur_read_pos; }
@@ -430,7 +445,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, SB_MIN_BLOCKS) k_chains(C
             left_search = 1;
             stage_read(first_rid);
             const int len = __ldg(a.lens + first_rid);
-            update_ref(ref, revref, curw, cnt, W, lane, 0, 0, 0, len, true, len);
+            update_ref(ref, revref, curw, cnt, W, lane, 0, 0, 0, len, true, len, 0, a.overflow);
             ref_len = len; ref_pos = 0; cur_read_pos = 0;
             iter_started = 0;
           } else {
@@ -521,7 +536,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, SB_MIN_BLOCKS) k_chains(C
           else if (len - shift >= old) { fold = len - shift - old; delta = -fold; cs = 0; nl = len; }  // :159-174
           else if (old + shift <= a.L) { delta = 0; cs = old - len + shift; nl = old + shift; } // :175-184
           else { delta = old + shift - a.L; cs = a.L - len; nl = a.L; }                         // :185-199
-          update_ref(ref, revref, curw, cnt, W, lane, old, delta, cs, len, prop_rev != 0, nl, fold);
+          update_ref(ref, revref, curw, cnt, W, lane, old, delta, cs, len, prop_rev != 0, nl, fold, a.overflow);
           ref_len = nl;
           if (!prop_rev) {  // reorder.h:490-497
             if (!left_search) { cur_read_pos = ref_pos + shift; ref_pos = cur_read_pos; }
@@ -549,7 +564,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, SB_MIN_BLOCKS) k_chains(C
         if (!left_search) {
           left_search = 1;
           const int len = __ldg(a.lens + first_rid);
-          update_ref(ref, revref, curw, cnt, W, lane, 0, 0, 0, len, true, len);
+          update_ref(ref, revref, curw, cnt, W, lane, 0, 0, 0, len, true, len, 0, a.overflow);
           ref_len = len; ref_pos = 0; cur_read_pos = 0;
           iter_started = 0; batch = 0; batch_S = 0;
         } else {
@@ -643,7 +658,7 @@ void run_reorder(Ctx &c, const uint64_t *reads, const uint16_t *lens, uint32_t n
   out.s_order = c.pool.dev<uint32_t>("ro.s_order", nn);
   if (n == 0) return;
 
-  const size_t smem = kWarpsPerBlock * (3 * (size_t)W + (W & 1) + 2 * (size_t)Lp) * sizeof(uint64_t);
+  const size_t smem = kWarpsPerBlock * (3 * (size_t)W + (size_t)Lp) * sizeof(uint64_t);
   const bool lockstep = c.lockstep;
   auto kern = lockstep ? k_chains<true> : k_chains<false>;
   SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -675,6 +690,7 @@ void run_reorder(Ctx &c, const uint64_t *reads, const uint16_t *lens, uint32_t n
   uint32_t *off_single = c.pool.dev<uint32_t>("ro.off_single", nslots + 1);
   unsigned long long *sync = c.pool.dev<unsigned long long>("ro.sync", 2 + CTR_N);
   a.barrier = sync; a.active = reinterpret_cast<int *>(sync + 1); a.ctr = sync + 2;
+  a.overflow = reinterpret_cast<int *>(sync + 1) + 1;
   a.num_chains = C; a.per = n / C;
   a.max_rounds = 8ull * n + 4096ull;
   SB_CUDA(cudaMemsetAsync(a.claimed, 0, bm_words * sizeof(uint32_t), st));
@@ -701,14 +717,16 @@ void run_reorder(Ctx &c, const uint64_t *reads, const uint16_t *lens, uint32_t n
   k_scatter_records<<<(n + 255) / 256, 256, 0, st>>>(a.rec_chain, a.rec_k, a.rec_pos, a.rec_meta, n, off_aligned, off_single,
                                                      out.order, out.flag, out.pos, out.rev, out.s_order);
   c.launches++;
-  unsigned long long *h = c.pool.pin<unsigned long long>("ro.hsync", CTR_N + 2);
+  unsigned long long *h = c.pool.pin<unsigned long long>("ro.hsync", CTR_N + 4);
   SB_CUDA(cudaMemcpyAsync(h, a.ctr, CTR_N * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
   uint32_t *htot = reinterpret_cast<uint32_t *>(h + CTR_N);
   SB_CUDA(cudaMemcpyAsync(htot, off_aligned + nslots, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
   SB_CUDA(cudaMemcpyAsync(htot + 1, off_single + nslots, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  SB_CUDA(cudaMemcpyAsync(htot + 2, a.overflow, sizeof(int), cudaMemcpyDeviceToHost, st));
   SB_CUDA(cudaStreamSynchronize(st));
   SB_CUDA(cudaGetLastError());
   if (h[CTR_ABORT]) throw LimitError("reorder: watchdog hit (round limit) -- chain kernel did not converge");
+  if (htot[2]) throw LimitError("reorder: more than 65535 reads stacked on one consensus column (u16 column counts)");
   out.num = htot[0];
   out.num_singletons = htot[1];
   if (out.num + out.num_singletons != n) throw LimitError("reorder: records do not cover all reads");

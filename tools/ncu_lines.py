@@ -14,6 +14,8 @@ hdr_i = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
 hdr, rows = rows[hdr_i], rows[hdr_i + 1:]
 si = hdr.index("# Samples")
 samples = [int(r[si]) for r in rows if len(r) > si]
+ii = hdr.index("Instructions Executed")
+insts = [int(r[ii]) for r in rows if len(r) > si]
 sass = [r[1].strip() for r in rows if len(r) > si]
 
 d = tempfile.mkdtemp()
@@ -43,9 +45,13 @@ if lines is None:
 print(f"sass rows {len(sass)}  disasm instrs {len(lines)}  total samples {sum(samples)}")
 n = min(len(sass), len(lines))
 agg = {}
+iagg = {}
 for i in range(n):
     agg[lines[i]] = agg.get(lines[i], 0) + samples[i]
+    iagg[lines[i]] = iagg.get(lines[i], 0) + insts[i]
 tot = sum(samples)
+itot = sum(insts)
+print(f"warp instructions executed: {itot}")
 src_cache = {}
 for (k, v) in sorted(agg.items(), key=lambda kv: -kv[1])[:top]:
     text = ""
@@ -55,4 +61,4 @@ for (k, v) in sorted(agg.items(), key=lambda kv: -kv[1])[:top]:
             src_cache[p] = open(p).read().splitlines()
         if p in src_cache and k[1] - 1 < len(src_cache[p]):
             text = src_cache[p][k[1] - 1].strip()[:110]
-    print(f"{100*v/tot:5.1f}%  {v:8d}  {k}  {text}")
+    print(f"{100*v/tot:5.1f}%  inst {100*iagg[k]/itot:5.1f}%  {k}  {text}")

@@ -60,6 +60,30 @@ __device__ __forceinline__ uint32_t upper_bound_u64(const uint64_t *__restrict__
   return lo;
 }
 
+// reverse the 2-bit groups of a word (base j <-> base 31-j)
+__device__ __forceinline__ uint64_t rev_groups(uint64_t x) {
+  x = __brevll(x);
+  return ((x & 0x5555555555555555ull) << 1) | ((x >> 1) & 0x5555555555555555ull);
+}
+// word i of the read as the encoder sees it (writetofile applies RC to 'r' reads, reorder.h:674-677):
+// forward: r[i]; reverse: word i of the reverse complement.  comp = false reverses without
+// complementing (for the N bit-plane).
+__device__ __forceinline__ uint64_t oriented_word(const uint64_t *__restrict__ r, int W, int len, bool rev, int i, bool comp = true) {
+  if (!rev) return r[i];
+  const int pad = 64 * W - 2 * len, k = i + (pad >> 6), bs = pad & 63;
+  uint64_t a0 = 0, a1 = 0;
+  if (k < W) { a0 = rev_groups(r[W - 1 - k]); if (comp) a0 = ~a0; }
+  if (k + 1 < W) { a1 = rev_groups(r[W - 2 - k]); if (comp) a1 = ~a1; }
+  return bs ? (a0 >> bs) | (a1 << (64 - bs)) : a0;
+}
+// 64 bits of the packed consensus starting at base x (cons2 is zero padded by >= 2 words)
+__device__ __forceinline__ uint64_t cons_bits(const uint64_t *__restrict__ cons2, uint64_t x) {
+  const uint64_t w = x >> 5;
+  const int bs = 2 * (int)(x & 31);
+  const uint64_t lo = cons2[w], hi = cons2[w + 1];
+  return bs ? (lo >> bs) | (hi << (64 - bs)) : lo;
+}
+
 // ---- pool of singleton + N reads (readsingletons, encoder.h:541-570) -------------------------
 __global__ void k_gather_pool(const uint64_t *__restrict__ reads, const uint16_t *__restrict__ lens,
                               const uint32_t *__restrict__ s_order, uint32_t S, NReads nr, int W,
@@ -135,7 +159,7 @@ constexpr int kTile = 256, kStage = 64;
 __global__ void __launch_bounds__(kTile) k_consensus(const uint64_t *__restrict__ reads, const uint16_t *__restrict__ lens,
                                                      const uint32_t *__restrict__ order, const uint8_t *__restrict__ rev,
                                                      const uint64_t *__restrict__ sorted_ap, const uint32_t *__restrict__ perm,
-                                                     uint32_t m, int W, int L, uint64_t seq_len, uint8_t *cons) {
+                                                     uint32_t m, int W, int L, uint64_t seq_len, uint64_t *cons2) {
   __shared__ uint64_t s_words[kStage * kMaxWords];
   __shared__ uint64_t s_ap[kStage];
   __shared__ uint32_t s_rid[kStage];
@@ -181,19 +205,24 @@ __global__ void __launch_bounds__(kTile) k_consensus(const uint64_t *__restrict_
     }
     __syncthreads();
   }
+  uint32_t code = 0;
   if (x < seq_len) {  // first strict maximum in A,C,G,T order (encoder.cpp:62-71); uncovered -> 'A'
-    uint32_t mx = 0; int code = 0;
+    uint32_t mx = 0;
     if (cA > mx) { mx = cA; code = 0; }
     if (cC > mx) { mx = cC; code = 2; }
     if (cG > mx) { mx = cG; code = 1; }
     if (cT > mx) { mx = cT; code = 3; }
-    cons[x] = (uint8_t)code;
   }
+  // consensus kept 2 bits/base in the reads' own coding (A0 G1 C2 T3): each warp owns one word
+  const int lane = threadIdx.x & 31;
+  const uint32_t part = code << (2 * (lane & 15));
+  const uint32_t lo = __reduce_or_sync(FULL, lane < 16 ? part : 0u), hi = __reduce_or_sync(FULL, lane < 16 ? 0u : part);
+  if (lane == 0 && x0 + (threadIdx.x & ~31u) < seq_len) cons2[(x0 >> 5) + (threadIdx.x >> 5)] = (uint64_t)lo | ((uint64_t)hi << 32);
 }
 
 // ---- singleton re-alignment (encoder.h:231-352) ---------------------------------------------------
 struct AlignArgs {
-  const uint8_t *cons; uint64_t seq_len;
+  const uint64_t *cons2; uint64_t seq_len;
   const unsigned long long *cstart; uint32_t num_contigs;  // cstart[num_contigs] == seq_len
   DictView dict[2];
   const uint64_t *pool_codes; const uint16_t *pool_len; const uint32_t *pool_ncount;
@@ -207,15 +236,17 @@ __global__ void k_align_singletons(AlignArgs a) {
   uint32_t lo = 0, hi = a.num_contigs;
   while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (a.cstart[mid] <= j) lo = mid; else hi = mid; }
   if (j + (uint64_t)a.L > a.cstart[lo + 1]) return;  // window leaves the contig (or contig shorter than max_readlen)
-  const uint8_t *win = a.cons + j;
   const int L = a.L, W = a.W;
 #pragma unroll 1
   for (int kind = 0; kind < 4; kind++) {
     const int rev = kind >> 1, l = kind & 1;
     const DictView &d = a.dict[l];
-    uint64_t key = 0;
-    if (!rev) for (int t = d.start; t <= d.end; t++) key |= (uint64_t)win[t] << (2 * (t - d.start));
-    else for (int t = d.start; t <= d.end; t++) key |= (uint64_t)(3 - win[L - 1 - t]) << (2 * (t - d.start));
+    // window bases [start, end] of the consensus window at j, or of its reverse complement
+    const int nb = d.end - d.start + 1;
+    const uint64_t kmask = nb < 32 ? (1ull << (2 * nb)) - 1ull : ~0ull;
+    uint64_t key;
+    if (!rev) key = cons_bits(a.cons2, j + d.start) & kmask;
+    else key = ~(rev_groups(cons_bits(a.cons2, j + L - 1 - d.end) & kmask) >> (64 - 2 * nb)) & kmask;
     if (!filter_test(d.filter, d.filter_mask, mix64(key))) continue;
     const long long hdr = dict_find(d, key);
     if (hdr < 0) continue;
@@ -228,8 +259,9 @@ __global__ void k_align_singletons(AlignArgs a) {
       const uint64_t *r = a.pool_codes + (size_t)rid * W;
       int h = (int)a.pool_ncount[rid];
       for (int b = 0; b < len && h <= kThreshEncoder; b++) {
-        const int wc = rev ? 3 - win[L - 1 - b] : win[b];
-        h += __popc((unsigned)(wc ^ base_code(r, b)));
+        const uint64_t x = rev ? j + L - 1 - b : j + b;
+        const int cc = (int)((a.cons2[x >> 5] >> (2 * (x & 31))) & 3ull);
+        h += __popc((unsigned)((rev ? 3 - cc : cc) ^ base_code(r, b)));
       }
       if (h <= kThreshEncoder) atomicMin(a.best + rid, prio);
     }
@@ -303,53 +335,52 @@ __constant__ char kEncNoise[4][4] = {
 
 struct NoiseArgs {
   const uint64_t *reads; const uint64_t *pool_codes; const uint64_t *pool_nflag; int W;
-  const uint8_t *cons; FinalArrays f; uint32_t m;
+  const uint64_t *cons2; FinalArrays f; uint32_t m;
   uint32_t *nmis;                  // pass 1 out / pass 2 in (exclusive scan)
   const uint64_t *noise_off;       // exclusive scan of nmis
   uint8_t *noise; uint16_t *noisepos;
 };
+// One thread per aligned read: the read (as oriented in the contig) XOR the consensus window, 32
+// bases per word; set bit pairs are the mismatches.
 template <bool WRITE>
 __global__ void k_noise(NoiseArgs a) {
-  const uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
+  const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= a.m) return;
-  const int len = a.f.len[q];
+  const int len = a.f.len[q], W = a.W;
   const bool rev = a.f.rev[q] == 'r';
   const bool pool = a.f.kind[q] != 0;
-  const uint64_t *r = (pool ? a.pool_codes : a.reads) + (size_t)a.f.src[q] * a.W;
-  const uint64_t *nf = pool ? a.pool_nflag + (size_t)a.f.src[q] * a.W : nullptr;
-  const uint8_t *ref = a.cons + a.f.pos[q];
+  const uint64_t *r = (pool ? a.pool_codes : a.reads) + (size_t)a.f.src[q] * W;
+  const uint64_t *nf = pool ? a.pool_nflag + (size_t)a.f.src[q] * W : nullptr;
+  const uint64_t pos = a.f.pos[q];
   uint32_t total = 0;
   int prevj = 0;
   uint64_t off = 0;
-  if (WRITE) off = a.noise_off[q];
-  for (int base = 0; base < len; base += 32) {
-    const int t = base + lane;
-    bool mis = false; char sym = 0;
-    if (t < len) {
-      const int src = rev ? len - 1 - t : t;
-      int code = base_code(r, src);
-      if (rev) code = 3 - code;
-      const bool isn = nf && ((nf[src >> 5] >> (2 * (src & 31))) & 1ull);
-      const int rc = ref[t];
-      if (isn) { mis = true; sym = '3'; }
-      else if (code != rc) { mis = true; sym = kEncNoise[rc][code]; }
+  if (WRITE) off = a.noise_off[q] + q;  // + q: one newline per earlier read
+  const int nw = (len + 31) >> 5;
+  for (int i = 0; i < nw; i++) {
+    const uint64_t o = oriented_word(r, W, len, rev, i);
+    const uint64_t c = cons_bits(a.cons2, pos + 32ull * i);
+    const int rem = len - 32 * i;
+    const uint64_t lm = rem >= 32 ? ~0ull : (1ull << (2 * rem)) - 1ull;
+    uint64_t x = (o ^ c) & lm;
+    uint64_t nfw = 0;
+    if (nf) nfw = oriented_word(nf, W, len, rev, i, false) & lm & 0x5555555555555555ull;
+    uint64_t mm = ((x | (x >> 1)) & 0x5555555555555555ull) | nfw;  // bit 2t set: base 32i+t differs (or is N)
+    if (!WRITE) { total += __popcll(mm); continue; }
+    while (mm) {
+      const int bp = __ffsll((long long)mm) - 1;
+      mm &= mm - 1;
+      const int t = 32 * i + (bp >> 1);
+      const int rc = (int)((c >> bp) & 3ull), code = (int)((o >> bp) & 3ull);
+      const char sym = ((nfw >> bp) & 1ull) ? '3' : kEncNoise[rc][code];
+      a.noise[off + total] = (uint8_t)sym;
+      a.noisepos[off - q + total] = (uint16_t)(t - prevj);
+      prevj = t;
+      total++;
     }
-    const unsigned mm = __ballot_sync(FULL, mis);
-    if (WRITE && mis) {
-      const unsigned below = mm & ((1u << lane) - 1u);
-      const uint32_t rank = total + __popc(below);
-      const int pj = below ? base + (31 - __clz(below)) : prevj;
-      a.noise[off + q + rank] = (uint8_t)sym;       // + q: one '\n' per earlier read
-      a.noisepos[off + rank] = (uint16_t)(t - pj);
-    }
-    if (mm) prevj = base + (31 - __clz(mm));
-    total += __popc(mm);
   }
-  if (lane == 0) {
-    if (WRITE) a.noise[off + q + total] = '\n';
-    else a.nmis[q] = total;
-  }
+  if (WRITE) a.noise[off + total] = '\n';
+  else a.nmis[q] = total;
 }
 
 // ---- unaligned tail (encoder.h:426-453) --------------------------------------------------------------
@@ -387,16 +418,13 @@ __global__ void k_unaligned_write(const uint32_t *__restrict__ u_idx, uint32_t u
   len_out[i] = (uint16_t)len;
 }
 
-// consensus bytes (reorder codes A0 G1 C2 T3) -> 2 bits/base A0 C1 G2 T3, LSB first (encoder.cpp:126-141)
-__global__ void k_pack_seq(const uint8_t *__restrict__ cons, uint64_t seq_len, uint8_t *packed) {
+// packed consensus (reads' coding A0 G1 C2 T3) -> the file's coding A0 C1 G2 T3 (encoder.cpp:126-141):
+// swap the two bits of every base, 32 bases per thread
+__global__ void k_pack_seq(const uint64_t *__restrict__ cons2, uint64_t nwords, uint64_t *packed) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i * 4 >= seq_len) return;
-  uint8_t v = 0;
-  for (int j = 0; j < 4; j++) {
-    const uint64_t x = i * 4 + j;
-    if (x < seq_len) { const int c = cons[x]; v |= (uint8_t)((((c & 1) << 1) | (c >> 1)) << (2 * j)); }
-  }
-  packed[i] = v;
+  if (i >= nwords) return;
+  const uint64_t w = cons2[i];
+  packed[i] = ((w & 0x5555555555555555ull) << 1) | ((w >> 1) & 0x5555555555555555ull);
 }
 
 __global__ void k_fill_u64(unsigned long long *p, uint64_t n, unsigned long long v) {
@@ -479,9 +507,11 @@ void run_encode(Ctx &c, const uint64_t *reads, const uint16_t *lens, uint32_t n,
   out.seq_len = seq_len;
 
   // ---- consensus ------------------------------------------------------------------------------------
-  uint8_t *cons = c.pool.dev<uint8_t>("en.cons", seq_len + 8);
+  const uint64_t cons_words = (seq_len + 31) / 32;
+  uint64_t *cons2 = c.pool.dev<uint64_t>("en.cons2", cons_words + 4);
+  SB_CUDA(cudaMemsetAsync(cons2 + cons_words, 0, 4 * sizeof(uint64_t), st));  // zero pad: windows may read 2 words past the end
   if (seq_len) {
-    k_consensus<<<grid_for(seq_len, kTile), kTile, 0, st>>>(reads, lens, ro.order, ro.rev, sorted_ap, perm, M, W, L, seq_len, cons);
+    k_consensus<<<grid_for(seq_len, kTile), kTile, 0, st>>>(reads, lens, ro.order, ro.rev, sorted_ap, perm, M, W, L, seq_len, cons2);
     c.launches++;
   }
 
@@ -503,7 +533,7 @@ void run_encode(Ctx &c, const uint64_t *reads, const uint16_t *lens, uint32_t n,
       build_dictionary(c, pool_codes, pool_len, pool_nflag, P, W, es[0], ee[0], "en.dict0", ed[0]);
       build_dictionary(c, pool_codes, pool_len, pool_nflag, P, W, es[1], ee[1], "en.dict1", ed[1]);
       AlignArgs aa{};
-      aa.cons = cons; aa.seq_len = seq_len; aa.cstart = cstart; aa.num_contigs = NC;
+      aa.cons2 = cons2; aa.seq_len = seq_len; aa.cstart = cstart; aa.num_contigs = NC;
       aa.dict[0] = ed[0].view; aa.dict[1] = ed[1].view;
       aa.pool_codes = pool_codes; aa.pool_len = pool_len; aa.pool_ncount = pool_ncount; aa.W = W; aa.L = L; aa.best = best;
       k_align_singletons<<<grid_for(seq_len, 256), 256, 0, st>>>(aa);
@@ -558,11 +588,11 @@ void run_encode(Ctx &c, const uint64_t *reads, const uint16_t *lens, uint32_t n,
   uint64_t *noise_off = c.pool.dev<uint64_t>("en.noise_off", MAn + 1);
   uint64_t total_noise = 0;
   NoiseArgs na{};
-  na.reads = reads; na.pool_codes = pool_codes; na.pool_nflag = pool_nflag; na.W = W; na.cons = cons; na.f = f; na.m = MA;
+  na.reads = reads; na.pool_codes = pool_codes; na.pool_nflag = pool_nflag; na.W = W; na.cons2 = cons2; na.f = f; na.m = MA;
   na.nmis = nmis; na.noise_off = noise_off;
   if (MA) {
     SB_CUDA(cudaMemsetAsync(nmis + MA, 0, sizeof(uint32_t), st));
-    k_noise<false><<<grid_for((uint64_t)MA * 32, 256), 256, 0, st>>>(na);
+    k_noise<false><<<grid_for(MA, 256), 256, 0, st>>>(na);
     size_t need = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, need, nmis, noise_off, (int)MA + 1, st); cub_need(need);
     need = cub_bytes; cub::DeviceScan::ExclusiveSum(cub_tmp, need, nmis, noise_off, (int)MA + 1, st);
@@ -575,7 +605,7 @@ void run_encode(Ctx &c, const uint64_t *reads, const uint16_t *lens, uint32_t n,
   out.noisepos = c.pool.dev<uint16_t>("en.out_noisepos", total_noise + 1);
   if (MA) {
     na.noise = out.noise; na.noisepos = out.noisepos;
-    k_noise<true><<<grid_for((uint64_t)MA * 32, 256), 256, 0, st>>>(na);
+    k_noise<true><<<grid_for(MA, 256), 256, 0, st>>>(na);
     c.launches++;
   }
 
@@ -602,8 +632,8 @@ void run_encode(Ctx &c, const uint64_t *reads, const uint16_t *lens, uint32_t n,
   }
 
   // ---- consensus packing --------------------------------------------------------------------------------
-  out.seq_packed = c.pool.dev<uint8_t>("en.out_seq", seq_len / 4 + 2);
-  if (seq_len) { k_pack_seq<<<grid_for((seq_len + 3) / 4, 256), 256, 0, st>>>(cons, seq_len, out.seq_packed); c.launches++; }
+  out.seq_packed = reinterpret_cast<uint8_t *>(c.pool.dev<uint64_t>("en.out_seq", cons_words + 1));
+  if (seq_len) { k_pack_seq<<<grid_for(cons_words, 256), 256, 0, st>>>(cons2, cons_words, reinterpret_cast<uint64_t *>(out.seq_packed)); c.launches++; }
   SB_CUDA(cudaGetLastError());
 }
 

@@ -174,6 +174,12 @@ def reorder_encode(packed, lengths, max_readlen, n_records=b"", order_n=None, nu
 
 def decode(er, stride: int | None = None) -> list[bytes]:
     """Rebuild every read of the stream (aligned then unaligned), decompress.cpp:263-283."""
+    out = decode_matrix(er, stride)
+    return [out[i, : er.lengths[i]].tobytes() for i in range(len(er.lengths))]
+
+
+def decode_matrix(er, stride: int | None = None) -> np.ndarray:
+    """Same, as one uint8[num_reads, stride] ASCII matrix (rows zero-padded): for full-size checks."""
     n = len(er.lengths)
     stride = stride or (int(er.lengths.max()) if n else 1) or 1
     out = np.zeros((max(n, 1), stride), dtype=np.uint8)
@@ -185,7 +191,7 @@ def decode(er, stride: int | None = None) -> list[bytes]:
                           _p(a[6], C.c_uint8), C.c_uint64(len(er.unaligned)), _p(out, C.c_uint8), C.c_int(stride))
     if rc != 0:
         raise RuntimeError(f"orc_decode failed: {rc}")
-    return [out[i, : er.lengths[i]].tobytes() for i in range(n)]
+    return out[:n]
 
 
 def reorder_dict(packed, lengths, max_readlen, which):

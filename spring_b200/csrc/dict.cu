@@ -170,7 +170,8 @@ void build_dictionary(Ctx &c, const uint64_t *reads, const uint16_t *lens, const
   DictSlot *slots = c.pool.dev<DictSlot>(nm(".slots").c_str(), cap);
   SB_CUDA(cudaMemsetAsync(slots, 0, sizeof(DictSlot) * (size_t)cap, st));
   uint64_t fbits = 65536;
-  while (fbits < 8ull * out.numkeys && fbits < (1ull << 36)) fbits <<= 1;
+  static const unsigned long long kFilterBitsPerKey = getenv("SPRING_B200_FILTER_BITS") ? strtoull(getenv("SPRING_B200_FILTER_BITS"), nullptr, 10) : 8ull;
+  while (fbits < kFilterBitsPerKey * out.numkeys && fbits < (1ull << 36)) fbits <<= 1;
   uint32_t *filter = c.pool.dev<uint32_t>(nm(".filter").c_str(), fbits / 32);
   SB_CUDA(cudaMemsetAsync(filter, 0, fbits / 8, st));
   out.view.filter = filter;

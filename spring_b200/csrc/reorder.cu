@@ -26,6 +26,7 @@
 // Memory traffic per claimed read (L = 150): ~128 slot probes x 32 B sectors per round, one
 // read_id sector + one or two 40 B candidate rows per hit, 17 B of records; all other state stays
 // in shared memory / registers for the life of the kernel.
+#include <algorithm>
 #include <cooperative_groups.h>
 #include <cub/cub.cuh>
 #include "kernels.cuh"
@@ -51,6 +52,7 @@ struct ChainArgs {
   unsigned long long *barrier; int *active; unsigned long long *ctr;
   unsigned long long max_rounds;
   int *overflow;  // set when a packed u16 column count would overflow
+  unsigned long long *chain_dbg;  // [2 * chains]: steps, globaltimer ns at finish (profiling aid)
 };
 
 __device__ __forceinline__ bool is_claimed(const uint32_t *claimed, uint32_t rid) {
@@ -483,6 +485,11 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, SB_MIN_BLOCKS) k_chains(C
       round++;
     }
     cy_search = clock64() - t_begin;
+    if (lane == 0 && a.chain_dbg) {
+      unsigned long long ns;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+      a.chain_dbg[2 * cid] = round; a.chain_dbg[2 * cid + 1] = ns;
+    }
   }
   if (LOCKSTEP) grid_barrier(a.barrier, target, t_last, cy_commit, cy_wait_b);
   cy_commit = 0; cy_wait_b = 0;
@@ -691,6 +698,8 @@ void run_reorder(Ctx &c, const uint64_t *reads, const uint16_t *lens, uint32_t n
   unsigned long long *sync = c.pool.dev<unsigned long long>("ro.sync", 2 + CTR_N);
   a.barrier = sync; a.active = reinterpret_cast<int *>(sync + 1); a.ctr = sync + 2;
   a.overflow = reinterpret_cast<int *>(sync + 1) + 1;
+  a.chain_dbg = getenv("SPRING_B200_CHAIN_DBG") ? c.pool.dev<unsigned long long>("ro.chain_dbg", 2 * (size_t)nslots + 2) : nullptr;
+  if (a.chain_dbg) SB_CUDA(cudaMemsetAsync(a.chain_dbg, 0, (2 * (size_t)nslots + 2) * sizeof(unsigned long long), st));
   a.num_chains = C; a.per = n / C;
   a.max_rounds = 8ull * n + 4096ull;
   SB_CUDA(cudaMemsetAsync(a.claimed, 0, bm_words * sizeof(uint32_t), st));
@@ -725,6 +734,18 @@ void run_reorder(Ctx &c, const uint64_t *reads, const uint16_t *lens, uint32_t n
   SB_CUDA(cudaMemcpyAsync(htot + 2, a.overflow, sizeof(int), cudaMemcpyDeviceToHost, st));
   SB_CUDA(cudaStreamSynchronize(st));
   SB_CUDA(cudaGetLastError());
+  if (a.chain_dbg) {
+    std::vector<unsigned long long> dbg(2 * (size_t)nslots);
+    SB_CUDA(cudaMemcpy(dbg.data(), a.chain_dbg, dbg.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    std::vector<unsigned long long> steps, ends;
+    unsigned long long t0 = ~0ull;
+    for (uint32_t i = 0; i < C; i++) { steps.push_back(dbg[2 * i]); ends.push_back(dbg[2 * i + 1]); if (dbg[2 * i + 1] && dbg[2 * i + 1] < t0) t0 = dbg[2 * i + 1]; }
+    std::sort(steps.begin(), steps.end()); std::sort(ends.begin(), ends.end());
+    auto pct = [&](std::vector<unsigned long long> &v, double q) { return v[(size_t)(q * (v.size() - 1))]; };
+    fprintf(stderr, "[chain_dbg] steps min %llu p50 %llu p90 %llu p99 %llu max %llu | finish (ms after first finisher) p10 %.2f p50 %.2f p90 %.2f p99 %.2f max %.2f\n",
+            steps.front(), pct(steps, .5), pct(steps, .9), pct(steps, .99), steps.back(), (pct(ends, .1) - t0) / 1e6,
+            (pct(ends, .5) - t0) / 1e6, (pct(ends, .9) - t0) / 1e6, (pct(ends, .99) - t0) / 1e6, (ends.back() - t0) / 1e6);
+  }
   if (h[CTR_ABORT]) throw LimitError("reorder: watchdog hit (round limit) -- chain kernel did not converge");
   if (htot[2]) throw LimitError("reorder: more than 65535 reads stacked on one consensus column (u16 column counts)");
   out.num = htot[0];

@@ -209,3 +209,47 @@ def test_bucket_kernel_matches_numpy_mirror(ctx):
         ctx.bucket_reads(r.data_ptr(), l.data_ptr(), len(hp.lengths), hp.max_readlen, g, out.data_ptr())
         torch.cuda.synchronize()
         assert (out.cpu().numpy() == bucket_numpy(hp.packed, hp.lengths, g)).all()
+
+
+def _full_size_roundtrip(ctx, rs, chains=0):
+    """Size-independent property at BASELINE sizes: decode(streams)[i] == original read order[i],
+    order is a permutation, aligned reads first.  Vectorised (no Python loop over reads)."""
+    import torch
+    from spring_b200 import synth
+    hp = synth.to_hotpath_input(rs)
+    got = ctx.reorder_encode(hp.packed, hp.lengths, hp.max_readlen, hp.n_records, hp.order_n, hp.num_reads, chains)
+    order = np.asarray(got.order).astype(np.int64)
+    assert (np.sort(order) == np.arange(hp.num_reads)).all()
+    L = rs.max_readlen
+    dec = po.decode_matrix(got, L)
+    ascii_of = np.frombuffer(b"AGCTN", dtype=np.uint8)
+    codes = rs.codes.cpu().numpy()
+    lens = rs.lengths.cpu().numpy()
+    orig = ascii_of[codes[order]]
+    valid = np.arange(L)[None, :] < lens[order][:, None]
+    assert (np.asarray(got.lengths) == lens[order]).all()
+    assert (np.where(valid, orig, 0) == np.where(valid, dec, 0)).all()
+    return got, ctx.stats()
+
+
+def test_config2_scale_roundtrip(ctx):
+    """BASELINE config 2 at 1/5 scale (2 M SE 150 bp, 30x, --no-quality) through the default path."""
+    from spring_b200 import synth
+    rs = synth.generate(2_000_000, 150, genome_len=10_000_000, seed=3, sub_rate=0.005, device="cuda")
+    got, st = _full_size_roundtrip(ctx, rs)
+    assert got.num_aligned > 0.95 * 2_000_000 and st["num_chains"] > 1000
+
+
+def test_config3_like_roundtrip(ctx):
+    """Config 3 shape (paired-end, Illumina error model, 0.2 % reads with N) at 2 M reads."""
+    from spring_b200 import synth
+    rs = synth.generate(2_000_000, 150, genome_len=10_000_000, seed=4, paired=True, n_frac=0.002, error_model="illumina", device="cuda")
+    got, st = _full_size_roundtrip(ctx, rs)
+    assert got.matched_N > 0
+
+
+def test_config5_like_roundtrip(ctx):
+    """Config 5 shape (variable length 35-250 bp: 512-bit reorder rows) at 1 M reads."""
+    from spring_b200 import synth
+    rs = synth.generate(1_000_000, 250, genome_len=5_000_000, seed=6, var_len=(35, 250), sub_rate=0.005, device="cuda")
+    _full_size_roundtrip(ctx, rs)

@@ -66,10 +66,11 @@ struct DictView {
   int key_bits;                  // bits per base * (end - start + 1)
 };
 
-__host__ __device__ inline uint64_t mix64(uint64_t x) {  // murmur3 finalizer
-  x ^= x >> 33; x *= 0xff51afd7ed558ccdULL;
-  x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL;
-  x ^= x >> 33;
+// multiply-fold hash of a window key (internal: slot placement and filter bits only)
+__host__ __device__ inline uint64_t mix64(uint64_t x) {
+  x ^= x >> 31;
+  x *= 0x9E3779B97F4A7C15ULL;
+  x ^= x >> 29;
   return x;
 }
 

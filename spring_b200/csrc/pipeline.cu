@@ -427,30 +427,6 @@ int spring_b200_fetch_reorder(spring_b200_ctx *ctx, spring_b200_reorder_out *out
   });
 }
 
-#if 0
-    const size_t m = ro.num, s = ro.num_singletons;
-    uint32_t *h_order = c.pool.pin<uint32_t>("ro.h_order", m + 1);
-    uint8_t *h_flag = c.pool.pin<uint8_t>("ro.h_flag", m + 1);
-    int64_t *h_pos = c.pool.pin<int64_t>("ro.h_pos", m + 1);
-    uint8_t *h_rev = c.pool.pin<uint8_t>("ro.h_rev", m + 1);
-    uint32_t *h_s = c.pool.pin<uint32_t>("ro.h_s", s + 1);
-    if (m) {
-      SB_CUDA(cudaMemcpyAsync(h_order, ro.order, m * 4, cudaMemcpyDeviceToHost, c.stream));
-      SB_CUDA(cudaMemcpyAsync(h_flag, ro.flag, m, cudaMemcpyDeviceToHost, c.stream));
-      SB_CUDA(cudaMemcpyAsync(h_pos, ro.pos, m * 8, cudaMemcpyDeviceToHost, c.stream));
-      SB_CUDA(cudaMemcpyAsync(h_rev, ro.rev, m, cudaMemcpyDeviceToHost, c.stream));
-    }
-    if (s) SB_CUDA(cudaMemcpyAsync(h_s, ro.s_order, s * 4, cudaMemcpyDeviceToHost, c.stream));
-    rec(ctx, 4);
-    SB_CUDA(cudaStreamSynchronize(c.stream));
-    out->order = h_order; out->flag = h_flag; out->pos = h_pos; out->rev = h_rev; out->num = m;
-    out->singleton_order = h_s; out->num_singletons = s;
-    ctx->stats.ms_h2d = ms(ctx, 0, 1); ctx->stats.ms_dict = ms(ctx, 1, 2); ctx->stats.ms_chains = ms(ctx, 2, 3);
-    ctx->stats.ms_total = ms(ctx, 0, 4);
-    ctx->stats.gpu_launches = c.launches;
-  });
-}
-#endif
 
 int spring_b200_bucket_reads(spring_b200_ctx *ctx, const uint64_t *reads, const uint16_t *lengths, uint32_t num_reads,
                              uint32_t max_readlen, uint32_t num_buckets, uint32_t *bucket) {

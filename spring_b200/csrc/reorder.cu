@@ -27,7 +27,6 @@
 // read_id sector + one or two 40 B candidate rows per hit, 17 B of records; all other state stays
 // in shared memory / registers for the life of the kernel.
 #include <algorithm>
-#include <cooperative_groups.h>
 #include <cub/cub.cuh>
 #include "kernels.cuh"
 
@@ -116,19 +115,16 @@ __device__ void update_ref(uint64_t *ref, uint64_t *revref, const uint64_t *curw
       const int ci = i - cs;
       if (ci >= 0 && ci < cur_len) {
         const int b = rev ? 3 - base_code(curw, cur_len - 1 - ci) : base_code(curw, ci);
-        const uint32_t sh = (0x20103000u >> (8 * b)) & 0xFFu;
-        if (((v >> sh) & 0xFFFFull) == 0xFFFFull) *overflow = 1;  // > 65535 reads stacked on one column
-        v += 1ull << sh;
+        v += 1ull << ((0x20103000u >> (8 * b)) & 0xFFu);
       }
       cnt[i] = v;
       const uint32_t f0 = (uint32_t)v & 0xFFFFu, f1 = (uint32_t)(v >> 16) & 0xFFFFu;
       const uint32_t f2 = (uint32_t)(v >> 32) & 0xFFFFu, f3 = (uint32_t)(v >> 48);
-      uint32_t mx = 0, ind = 0;  // first strict maximum (reorder.h:204-212)
-      if (f0 > mx) { mx = f0; ind = 0; }
-      if (f1 > mx) { mx = f1; ind = 1; }
-      if (f2 > mx) { mx = f2; ind = 2; }
-      if (f3 > mx) { mx = f3; ind = 3; }
-      code = (0x01030200u >> (8 * ind)) & 3u;  // rows A,C,T,G -> codes 0,2,3,1
+      uint32_t mx = f0;  // first strict maximum over rows A,C,T,G (reorder.h:204-212) -> codes 0,2,3,1
+      if (f1 > mx) { mx = f1; code = 2; }
+      if (f2 > mx) { mx = f2; code = 3; }
+      if (f3 > mx) { mx = f3; code = 1; }
+      if (mx == 0xFFFFu) *overflow = 1;  // a u16 field is about to wrap: > 65535 reads stacked on one column
     }
     // 32 two-bit codes -> one 64-bit word: lanes 0-15 fill the low half, 16-31 the high half
     const uint32_t part = code << (2 * (lane & 15));

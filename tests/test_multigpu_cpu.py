@@ -21,10 +21,9 @@ M64 = (1 << 64) - 1
 
 
 def mix64(x: np.ndarray) -> np.ndarray:
-    x = x.astype(np.uint64)
-    x ^= x >> np.uint64(33); x *= np.uint64(0xff51afd7ed558ccd)
-    x ^= x >> np.uint64(33); x *= np.uint64(0xc4ceb9fe1a85ec53)
-    x ^= x >> np.uint64(33)
+    x = x.astype(np.uint64)          # mirror of sb::mix64 (spring_b200/csrc/common.cuh)
+    x ^= x >> np.uint64(31); x *= np.uint64(0x9E3779B97F4A7C15)
+    x ^= x >> np.uint64(29)
     return x
 
 

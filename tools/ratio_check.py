@@ -1,0 +1,26 @@
+"""GPU box: compressed size + stage times of the reference vs the reference host with libspring_b200
+spliced in (oracle/_ref/spring_b200_ref), same FASTQ, `-c -r --no-quality`."""
+import os, re, subprocess, sys, tempfile, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle import pyoracle as po
+from spring_b200 import synth
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 2_000_000
+threads = os.cpu_count() or 8
+rs = synth.generate(n, 150, genome_len=n * 150 // 30, seed=3, sub_rate=0.005, device="cuda")
+d = tempfile.mkdtemp(dir="/dev/shm")
+fq = os.path.join(d, "in.fastq")
+t0 = time.time(); synth.write_fastq(rs, fq); print(f"wrote {n} reads in {time.time()-t0:.1f}s")
+for name, binary, env in (("reference", po.REF_BIN, {}), ("b200 auto chains", po.SPLICE_BIN, {}), ("b200 1 chain", po.SPLICE_BIN, {"SPRING_B200_CHAINS": "1"})):
+    out = os.path.join(d, name.replace(" ", "_") + ".spring")
+    t0 = time.time()
+    r = subprocess.run([binary, "-c", "-r", "--no-quality", "-i", fq, "-o", out, "-t", str(threads), "-w", d], capture_output=True, text=True, env={**os.environ, **env})
+    wall = time.time() - t0
+    if r.returncode != 0:
+        print(name, "FAILED", r.stdout[-500:], r.stderr[-500:]); continue
+    steps = re.findall(r"^(\w[\w /]+?) (?:done!|\.\.\.)\nTime for this step: (\d+) s", r.stdout, re.M)
+    reads = re.search(r"Reads:\s+(\d+) bytes", r.stdout).group(1)
+    unm = re.search(r"(\d+) were unmatched", r.stdout)
+    al = re.findall(r"(\d+) (?:singleton reads|reads with N) were aligned", r.stdout)
+    print(f"{name:18s} wall {wall:6.1f}s  Reads: {int(reads):>10d} bytes  ({8*int(reads)/n/150:.4f} bits/base)  unmatched {unm.group(1) if unm else '?'}  archive {os.path.getsize(out)}")
+    print("    stage seconds:", [(a.strip(), int(b)) for a, b in steps])

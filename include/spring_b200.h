@@ -124,6 +124,9 @@ int spring_b200_device_count(void);
 /* device: CUDA ordinal.  stream: a cudaStream_t to run on (e.g. torch's current stream) or NULL
  * for a stream owned by the context. */
 int spring_b200_create(int device, void *stream, spring_b200_ctx **out);
+/* Run all later calls on this cudaStream_t.  Unlike create(), a NULL handle here means the legacy
+ * default stream (what e.g. torch.cuda.current_stream().cuda_stream is unless a side stream is set). */
+int spring_b200_set_stream(spring_b200_ctx *ctx, void *stream);
 void spring_b200_destroy(spring_b200_ctx *ctx);
 const char *spring_b200_last_error(const spring_b200_ctx *ctx); /* ctx may be NULL: last create() error */
 int spring_b200_get_stats(const spring_b200_ctx *ctx, spring_b200_stats *out);

@@ -19,7 +19,7 @@ EXPORTS = [
     "spring_b200_last_error", "spring_b200_get_stats", "spring_b200_reorder_encode",
     "spring_b200_reorder_encode_device", "spring_b200_fetch_streams", "spring_b200_build_dictionary",
     "spring_b200_reorder", "spring_b200_reorder_encode_files", "spring_b200_write_streams",
-    "spring_b200_bucket_reads", "spring_b200_set_schedule", "spring_b200_fetch_reorder",
+    "spring_b200_bucket_reads", "spring_b200_set_schedule", "spring_b200_fetch_reorder", "spring_b200_set_stream",
 ]
 
 
@@ -139,9 +139,12 @@ class Context:
     def __init__(self, device: int = 0, stream: int | None = None):
         self._lib = load()
         self._h = C.c_void_p()
-        rc = self._lib.spring_b200_create(device, C.c_void_p(stream) if stream else None, C.byref(self._h))
+        rc = self._lib.spring_b200_create(device, None, C.byref(self._h))
         if rc != 0:
             raise SpringB200Error(rc, self._lib.spring_b200_last_error(None).decode())
+        if stream is not None:  # 0 is a valid handle: the legacy default stream
+            self._lib.spring_b200_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+            self._check(self._lib.spring_b200_set_stream(self._h, C.c_void_p(stream)))
         self._keep = []
 
     def close(self):

@@ -345,6 +345,16 @@ int spring_b200_get_stats(const spring_b200_ctx *ctx, spring_b200_stats *out) {
   return SPRING_B200_OK;
 }
 
+int spring_b200_set_stream(spring_b200_ctx *ctx, void *stream) {
+  if (!ctx) return SPRING_B200_EINVAL;
+  cudaSetDevice(ctx->c.device);
+  cudaStreamSynchronize(ctx->c.stream);
+  if (ctx->c.own_stream) cudaStreamDestroy(ctx->c.stream);
+  ctx->c.stream = (cudaStream_t)stream;
+  ctx->c.own_stream = false;
+  return SPRING_B200_OK;
+}
+
 int spring_b200_set_schedule(spring_b200_ctx *ctx, int deterministic) {
   if (!ctx) return SPRING_B200_EINVAL;
   ctx->c.lockstep = deterministic != 0;

@@ -75,8 +75,9 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
-def test_two_rank_exchange_and_merge():
-    world, port = 2, _free_port()
+@pytest.mark.parametrize("world", [2, 4])
+def test_multi_rank_exchange_and_merge(world):
+    port = _free_port()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]

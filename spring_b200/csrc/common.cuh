@@ -60,6 +60,8 @@ struct DictView {
   uint32_t slot_mask;            // capacity - 1 (power of two)
   const uint32_t *bins;
   const uint32_t *slot_of_read;  // [n] slot index holding read i's key, 0xFFFFFFFF if the read is not indexed
+  uint32_t *skip;                // [like bins] at a bin's header index: entries before this offset are all claimed
+                                 // (monotone hint: a scan of a big bin starts there; plays bbhashdict::remove's compaction)
   const uint32_t *filter;        // blocked Bloom filter over the keys: 2 bits in one 32-bit word, >= 8 bits per key
   uint32_t filter_mask;          // number of filter words - 1 (power of two)
   int start, end;                // base window [start, end]

@@ -109,6 +109,9 @@ void build_dictionary(Ctx &c, const uint64_t *reads, const uint16_t *lens, const
   uint32_t *slot_of_bin = c.pool.dev<uint32_t>(nm(".slot_of_bin").c_str(), nn);
   uint32_t *slot_of_read = c.pool.dev<uint32_t>(nm(".slot_of_read").c_str(), nn);
   uint32_t *bins = c.pool.dev<uint32_t>(nm(".bins").c_str(), 2 * (size_t)nn);
+  uint32_t *skip = c.pool.dev<uint32_t>(nm(".skip").c_str(), 2 * (size_t)nn);
+  SB_CUDA(cudaMemsetAsync(skip, 0, 2 * (size_t)nn * sizeof(uint32_t), st));
+  out.view.skip = skip;
   uint32_t *d_count = c.pool.dev<uint32_t>(nm(".count").c_str(), 4);
   uint32_t *h_count = c.pool.pin<uint32_t>(nm(".hcount").c_str(), 4);
   if (n == 0) {

@@ -159,12 +159,25 @@ __device__ bool scan_bin(const ChainArgs &a, const DictView &d, uint32_t bs, uin
                          bool rev, int s, int ref_len, int lane, uint32_t &rid_out, unsigned long long &compares) {
   const int W = a.W;
   int live_before = 0;
-  for (uint32_t off = 0; off < bc; off += 32) {
+  // big bins (repeats): skip the prefix of entries already known to be claimed, and extend that
+  // hint when this scan meets more of them -- claims only grow, so the hint never hides a live read
+  uint32_t t0 = 0, dead_to = 0;
+  bool prefix_dead = bc > 3;
+  if (bc > 3) { t0 = __ldcg(d.skip + (bs - 1)); dead_to = t0; }
+  for (uint32_t off = t0; off < bc; off += 32) {
     const uint32_t t = off + lane;
     uint32_t rid = 0;
     bool live = false;
     if (t < bc) { rid = bc <= 3 ? in3 : __ldg(d.bins + bs + t); live = !is_claimed(a.claimed, rid); }
     const unsigned lm = __ballot_sync(FULL, live);
+    if (prefix_dead) {
+      if (lm == 0) dead_to = min(bc, off + 32);
+      else {
+        dead_to = off + (__ffs(lm) - 1);
+        prefix_dead = false;
+        if (lane == 0 && dead_to > t0) atomicMax(d.skip + (bs - 1), dead_to);
+      }
+    }
     const int rank = live_before + __popc(lm & ((1u << lane) - 1u));
     const bool ev = live && rank < kMaxSearch;
     bool pass = false;
@@ -195,6 +208,7 @@ __device__ bool scan_bin(const ChainArgs &a, const DictView &d, uint32_t bs, uin
     live_before += __popc(lm);
     if (live_before >= kMaxSearch) break;
   }
+  if (prefix_dead && lane == 0 && dead_to > t0) atomicMax(d.skip + (bs - 1), dead_to);
   return false;
 }
 

@@ -5,8 +5,9 @@ import torch
 from spring_b200 import capi, synth
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 10_000_000
 chains = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+genome = int(sys.argv[3]) if len(sys.argv) > 3 else n * 150 // 30
 dev = torch.device("cuda", 0)
-rs = synth.generate(n, 150, genome_len=n * 150 // 30, seed=3, sub_rate=0.005, device=dev)
+rs = synth.generate(n, 150, genome_len=genome, seed=3, sub_rate=0.005, device=dev)
 d_reads = synth.pack_reads(rs.codes, rs.lengths, 150).contiguous(); d_lens = rs.lengths.to(torch.int16).contiguous(); del rs
 ctx = capi.Context(0, torch.cuda.current_stream().cuda_stream)
 inp = ctx.make_input(d_reads.data_ptr(), d_lens.data_ptr(), n, 150)

@@ -192,10 +192,14 @@ __global__ void __launch_bounds__(kTile) k_consensus(const uint64_t *__restrict_
     }
     __syncthreads();
     if (x < seq_len) {
-      for (uint32_t q = 0; q < cnt; q++) {
+      // staged reads are sorted by position: only those with ap in (x - L, x] can cover column x
+      uint32_t q = 0, qh = cnt;
+      const uint64_t first = x >= (uint64_t)(L - 1) ? x - (uint64_t)(L - 1) : 0;
+      while (q < qh) { const uint32_t mid = (q + qh) >> 1; if (s_ap[mid] < first) q = mid + 1; else qh = mid; }
+      for (; q < cnt && s_ap[q] <= x; q++) {
         const uint64_t a = s_ap[q];
         const int len = s_len[q];
-        if (x >= a && x < a + (uint64_t)len) {
+        if (x < a + (uint64_t)len) {
           const int off = (int)(x - a);
           const uint64_t *w = s_words + q * kMaxWords;
           const int code = s_rev[q] ? 3 - base_code(w, len - 1 - off) : base_code(w, off);
@@ -230,11 +234,19 @@ struct AlignArgs {
   unsigned long long *best;
 };
 __global__ void k_align_singletons(AlignArgs a) {
-  const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t j0 = (uint64_t)blockIdx.x * blockDim.x, j = j0 + threadIdx.x;
+  // contig of the block's first column by binary search (last c with cstart[c] <= j0); each thread
+  // then walks forward the few contigs a 256-column block can span
+  __shared__ uint32_t s_c0;
+  if (threadIdx.x == 0) {
+    uint32_t l0 = 0, h0 = a.num_contigs;
+    while (h0 - l0 > 1) { const uint32_t mid = (l0 + h0) >> 1; if (a.cstart[mid] <= j0) l0 = mid; else h0 = mid; }
+    s_c0 = l0;
+  }
+  __syncthreads();
   if (j + (uint64_t)a.L > a.seq_len) return;
-  // contig of column j: last c with cstart[c] <= j
-  uint32_t lo = 0, hi = a.num_contigs;
-  while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (a.cstart[mid] <= j) lo = mid; else hi = mid; }
+  uint32_t lo = s_c0;
+  while (lo + 1 < a.num_contigs && a.cstart[lo + 1] <= j) lo++;
   if (j + (uint64_t)a.L > a.cstart[lo + 1]) return;  // window leaves the contig (or contig shorter than max_readlen)
   const int L = a.L, W = a.W;
 #pragma unroll 1

@@ -18,6 +18,16 @@ CASES = {
     "long511": dict(num_reads=1500, read_len=511, seed=7, var_len=(300, 511), genome_len=20000),
     "heavy_bins": dict(num_reads=30000, read_len=40, seed=8, genome_len=60, sub_rate=0.01),
     "lowcov": dict(num_reads=4000, read_len=100, seed=9, genome_len=4000000),
+    # window-formula boundaries: reorder.h:752-759 switches at L = 100, encoder.h:610-620 at L = 50
+    "len50": dict(num_reads=2500, read_len=50, seed=10, n_frac=0.02),
+    "len51": dict(num_reads=2500, read_len=51, seed=11, n_frac=0.02),
+    "len100": dict(num_reads=3000, read_len=100, seed=12, sub_rate=0.01),
+    "len101": dict(num_reads=3000, read_len=101, seed=13, sub_rate=0.01),
+    "fixed12": dict(num_reads=1500, read_len=12, seed=14, genome_len=400),
+    "tiny16": dict(num_reads=1500, read_len=16, seed=14, genome_len=4000, var_len=(3, 16)),
+    "dups": dict(num_reads=4000, read_len=80, seed=15, genome_len=500, sub_rate=0.0),
+    "mostly_n": dict(num_reads=1500, read_len=90, seed=16, n_frac=0.9),
+    "pe_var": dict(num_reads=4000, read_len=140, seed=17, paired=True, var_len=(50, 140), n_frac=0.02, error_model="illumina"),
 }
 
 

@@ -15,6 +15,7 @@ hdr, rows = rows[hdr_i], rows[hdr_i + 1:]
 si = hdr.index("# Samples")
 samples = [int(r[si]) for r in rows if len(r) > si]
 ii = hdr.index("Instructions Executed")
+rows = [r for r in rows if len(r) > si and r[si].isdigit()]
 insts = [int(r[ii]) for r in rows if len(r) > si]
 sass = [r[1].strip() for r in rows if len(r) > si]
 

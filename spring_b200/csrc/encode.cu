@@ -160,14 +160,15 @@ __global__ void __launch_bounds__(kTile) k_consensus(const uint64_t *__restrict_
                                                      const uint32_t *__restrict__ order, const uint8_t *__restrict__ rev,
                                                      const uint64_t *__restrict__ sorted_ap, const uint32_t *__restrict__ perm,
                                                      uint32_t m, int W, int L, uint64_t seq_len, uint64_t *cons2) {
-  __shared__ uint64_t s_words[kStage * kMaxWords];
-  __shared__ uint64_t s_ap[kStage];
+  __shared__ uint64_t s_words[kStage * kMaxWords];  // staged reads, already oriented as in the contig
+  __shared__ int s_rel[kStage];                     // read start relative to the tile's first column
   __shared__ uint32_t s_rid[kStage];
   __shared__ uint16_t s_len[kStage];
   __shared__ uint8_t s_rev[kStage];
   __shared__ uint32_t s_range[2];
   const uint64_t x0 = (uint64_t)blockIdx.x * kTile;
   const uint64_t x = x0 + threadIdx.x;
+  const int xr = (int)threadIdx.x;
   if (threadIdx.x == 0) {
     const uint64_t lo_ap = x0 >= (uint64_t)(L - 1) ? x0 - (uint64_t)(L - 1) : 0;  // reads with ap + L > x0
     s_range[0] = lower_bound_u64(sorted_ap, m, lo_ap);
@@ -180,7 +181,7 @@ __global__ void __launch_bounds__(kTile) k_consensus(const uint64_t *__restrict_
     const uint32_t cnt = min((uint32_t)kStage, r_hi - base);
     if (threadIdx.x < cnt) {
       const uint32_t r = base + threadIdx.x, p = perm[r], rid = order[p];
-      s_ap[threadIdx.x] = sorted_ap[r];
+      s_rel[threadIdx.x] = (int)((long long)sorted_ap[r] - (long long)x0);
       s_rid[threadIdx.x] = rid;
       s_len[threadIdx.x] = lens[rid];
       s_rev[threadIdx.x] = rev[p] == 'r';
@@ -188,24 +189,20 @@ __global__ void __launch_bounds__(kTile) k_consensus(const uint64_t *__restrict_
     __syncthreads();
     for (uint32_t t = threadIdx.x; t < cnt * (uint32_t)W; t += kTile) {
       const uint32_t q = t / W, w = t - q * W;
-      s_words[q * kMaxWords + w] = reads[(size_t)s_rid[q] * W + w];
+      s_words[q * kMaxWords + w] = oriented_word(reads + (size_t)s_rid[q] * W, W, s_len[q], s_rev[q] != 0, (int)w);
     }
     __syncthreads();
     if (x < seq_len) {
-      // staged reads are sorted by position: only those with ap in (x - L, x] can cover column x
+      // staged reads are sorted by position: only those starting in (x - L, x] can cover column x
       uint32_t q = 0, qh = cnt;
-      const uint64_t first = x >= (uint64_t)(L - 1) ? x - (uint64_t)(L - 1) : 0;
-      while (q < qh) { const uint32_t mid = (q + qh) >> 1; if (s_ap[mid] < first) q = mid + 1; else qh = mid; }
-      for (; q < cnt && s_ap[q] <= x; q++) {
-        const uint64_t a = s_ap[q];
-        const int len = s_len[q];
-        if (x < a + (uint64_t)len) {
-          const int off = (int)(x - a);
-          const uint64_t *w = s_words + q * kMaxWords;
-          const int code = s_rev[q] ? 3 - base_code(w, len - 1 - off) : base_code(w, off);
-          cA += code == 0; cG += code == 1; cC += code == 2; cT += code == 3;
-        }
+      const int first = xr - (L - 1);
+      while (q < qh) { const uint32_t mid = (q + qh) >> 1; if (s_rel[mid] < first) q = mid + 1; else qh = mid; }
+      uint32_t acc = 0;  // four u8 counters {A,G,C,T}; at most kStage (< 256) additions per stage
+      for (; q < cnt && s_rel[q] <= xr; q++) {
+        const unsigned off = (unsigned)(xr - s_rel[q]);
+        if (off < (unsigned)s_len[q]) acc += 1u << (8 * base_code(s_words + q * kMaxWords, (int)off));
       }
+      cA += acc & 0xFFu; cG += (acc >> 8) & 0xFFu; cC += (acc >> 16) & 0xFFu; cT += acc >> 24;
     }
     __syncthreads();
   }

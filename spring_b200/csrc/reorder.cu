@@ -51,6 +51,9 @@ struct ChainArgs {
   unsigned long long *barrier; int *active; unsigned long long *ctr;
   unsigned long long max_rounds;
   int *overflow;  // set when a packed u16 column count would overflow
+  uint32_t G;            // scan_bin: candidates verified per pass = 32 / W
+  unsigned leader_mask;  // scan_bin: lanes g * W, g < G
+  int generic_update;    // debugging aid: always use the per-column update_ref
   unsigned long long *chain_dbg;  // [2 * chains]: steps, globaltimer ns at finish (profiling aid)
 };
 
@@ -86,7 +89,7 @@ __device__ __forceinline__ void grid_barrier(unsigned long long *ctr, unsigned l
 // fold = cur_len - shift - old_len columns with an ascending in-place loop, so a source column
 // that was already rewritten is read again: column i = q*fold + r ends up as
 // old[r] + sum_{t=1..q} e(read base at t*fold + r) rather than old[i - fold] + e(read base at i).
-__device__ void update_ref(uint64_t *ref, uint64_t *revref, const uint64_t *curw, uint64_t *cnt, int W, int lane,
+__device__ __noinline__ void update_ref(uint64_t *ref, uint64_t *revref, const uint64_t *curw, uint64_t *cnt, int W, int lane,
                            int old_len, int delta, int cs, int cur_len, bool rev, int new_len, int fold, int *overflow) {
   // cnt[col] packs the four per-base counts of a column as u16 fields, rows A,C,T,G
   // (reorder.h:120-123); 2-bit read codes are A0 G1 C2 T3 -> field shift 0, 48, 16, 32
@@ -153,51 +156,146 @@ __device__ void update_ref(uint64_t *ref, uint64_t *revref, const uint64_t *curw
   __syncwarp();
 }
 
+// word w of the reverse complement of the len-base sequence a[] (W words, zero beyond len): reverse the
+// 2-bit groups of the whole array, complement, shift the padding out (reorder.h:215-217 by bit tricks)
+__device__ __forceinline__ uint64_t revcomp_word(const uint64_t *a, int W, int len, int w) {
+  const int pad = 64 * W - 2 * len, ws = pad >> 6, bs = pad & 63;
+  uint64_t a0 = 0, a1 = 0;
+  if (w + ws < W) {
+    const uint64_t x = __brevll(a[W - 1 - (w + ws)]);
+    a0 = ~(((x & 0x5555555555555555ull) << 1) | ((x >> 1) & 0x5555555555555555ull));
+  }
+  if (w + ws + 1 < W) {
+    const uint64_t x = __brevll(a[W - 2 - (w + ws)]);
+    a1 = ~(((x & 0x5555555555555555ull) << 1) | ((x >> 1) & 0x5555555555555555ull));
+  }
+  return bs ? (a0 >> bs) | (a1 << (64 - bs)) : a0;
+}
+
+// update_ref for every case but the fold quirk (delta >= 0): same result as the generic version above,
+// with the consensus rebuilt by word operations instead of a majority vote per column.
+//   * counts: one pass over the columns, 32 per step: cnt[i] = cnt[i + delta] (+ the read's base);
+//   * consensus: ref[] always equals the column-wise majority of cnt[] (true after a reset, kept by
+//     every update).  A column the read does not cover keeps its counts, hence its base; a column where
+//     the read agrees with the old consensus keeps it too (the winner's count grows); a column with no
+//     source is new and takes the read's base.  So new ref = (old ref >> delta columns) merged with the
+//     read's words, and only the columns where read and old consensus DIFFER -- at most THRESH_REORDER
+//     of them, the match passed the Hamming test on exactly these bits -- need the vote.
+// curw is overwritten with the read as oriented in the contig.
+__device__ void update_ref_fast(uint64_t *ref, uint64_t *revref, uint64_t *curw, uint64_t *cnt, int W, int lane, int old_len,
+                                int delta, int cs, int cur_len, bool rev, int new_len, int *overflow) {
+  if (rev) {
+    uint64_t o = 0;
+    if (lane < W) o = revcomp_word(curw, W, cur_len, lane);
+    __syncwarp();
+    if (lane < W) curw[lane] = o;
+    __syncwarp();
+  }
+  const int nchunks = (new_len + 31) >> 5;
+  for (int cc = 0; cc < nchunks; cc++) {  // ascending is safe: delta >= 0, sources lie at or above the column
+    const int i = (cc << 5) + lane;
+    const bool in = i < new_len;
+    uint64_t v = 0;
+    if (in && i + delta < old_len) v = cnt[i + delta];
+    __syncwarp();
+    if (in) {
+      const unsigned ci = (unsigned)(i - cs);
+      if (ci < (unsigned)cur_len) {
+        // cnt[col] packs the four per-base counts as u16 fields, rows A,C,T,G (reorder.h:120-123);
+        // 2-bit read codes are A0 G1 C2 T3 -> field shift 0, 48, 16, 32
+        const int sh = (int)((0x20103000u >> (8 * base_code(curw, (int)ci))) & 0xFFu);
+        v += 1ull << sh;
+        if (((v >> sh) & 0xFFFFull) == 0xFFFFull) *overflow = 1;  // > 65535 reads stacked on one column
+      }
+      cnt[i] = v;
+    }
+  }
+  uint64_t nw = 0, mm = 0;
+  if (lane < W) {
+    const uint64_t MA = range_mask(lane, 0, 2 * (old_len - delta));        // columns that have a source column
+    const uint64_t MB = range_mask(lane, 2 * cs, 2 * (cs + cur_len));      // columns the read covers
+    const uint64_t A = shr_word(ref, W, lane, 2 * delta) & MA;
+    const uint64_t B = shl_word(curw, W, lane, 2 * cs) & MB;
+    nw = A | (B & ~MA);
+    const uint64_t X = (A ^ B) & MA & MB;
+    mm = (X | (X >> 1)) & 0x5555555555555555ull;  // bit 2t: column 32*lane + t needs the vote
+  }
+  __syncwarp();  // counts written, old ref read
+  while (mm) {
+    const int bp = __ffsll((long long)mm) - 1;
+    mm &= mm - 1;
+    const uint64_t v = cnt[(lane << 5) + (bp >> 1)];
+    const uint32_t f0 = (uint32_t)v & 0xFFFFu, f1 = (uint32_t)(v >> 16) & 0xFFFFu;
+    const uint32_t f2 = (uint32_t)(v >> 32) & 0xFFFFu, f3 = (uint32_t)(v >> 48);
+    uint32_t mx = f0, code = 0;  // first strict maximum over rows A,C,T,G (reorder.h:204-212) -> codes 0,2,3,1
+    if (f1 > mx) { mx = f1; code = 2; }
+    if (f2 > mx) { mx = f2; code = 3; }
+    if (f3 > mx) { mx = f3; code = 1; }
+    nw = (nw & ~(3ull << bp)) | ((uint64_t)code << bp);
+  }
+  if (lane < W) ref[lane] = nw;
+  __syncwarp();
+  if (lane < W) revref[lane] = revcomp_word(ref, W, new_len, lane);
+  __syncwarp();
+}
+
 // Verify the live reads of one bin, highest id first, at most MAX_SEARCH of them (reorder.h:287-311).
-// in3: the bin's first three entries (from the slot); bins[] is only read for bins of > 3 reads.
-__device__ bool scan_bin(const ChainArgs &a, const DictView &d, uint32_t bs, uint32_t bc, uint32_t in3, const uint64_t *refsm,
-                         bool rev, int s, int ref_len, int lane, uint32_t &rid_out, unsigned long long &compares) {
+// r0..r2: the bin's first three entries (from the slot); bins[] is only read for bins of > 3 reads.
+//
+// Lane layout: the warp is cut into G = 32 / W groups of W lanes; group g verifies candidate off + g and
+// lane wig of the group handles word wig of the bitsets: one coalesced 8W-byte row load per candidate, one
+// XOR / mask / popcount per lane, a W-lane segmented sum.  (A lane per candidate would spend W times the
+// instructions on the one or two candidates a typical bin holds.)  The shifted reference word is the
+// same for every candidate of the scan and is computed once.
+__device__ bool scan_bin(const ChainArgs &a, const DictView &d, uint32_t bs, uint32_t bc, uint32_t r0, uint32_t r1, uint32_t r2,
+                         const uint64_t *refsm, bool rev, int s, int ref_len, int lane, int grp, int wig, uint32_t &rid_out,
+                         uint32_t &compares) {
   const int W = a.W;
+  const uint32_t G = a.G;
+  const bool act = (uint32_t)grp < G;
+  const unsigned leaders = a.leader_mask;                  // lanes with wig == 0 of the G groups
+  const unsigned below = leaders & ((1u << (lane - wig)) - 1u);  // leaders of the groups before mine
+  const uint64_t rw = rev ? shl_word(refsm, W, wig, 2 * s) : shr_word(refsm, W, wig, 2 * s);
   int live_before = 0;
   // big bins (repeats): skip the prefix of entries already known to be claimed, and extend that
   // hint when this scan meets more of them -- claims only grow, so the hint never hides a live read
   uint32_t t0 = 0, dead_to = 0;
   bool prefix_dead = bc > 3;
   if (bc > 3) { t0 = __ldcg(d.skip + (bs - 1)); dead_to = t0; }
-  for (uint32_t off = t0; off < bc; off += 32) {
-    const uint32_t t = off + lane;
+  for (uint32_t off = t0; off < bc; off += G) {
+    const uint32_t t = off + (uint32_t)grp;
     uint32_t rid = 0;
     bool live = false;
-    if (t < bc) { rid = bc <= 3 ? in3 : __ldg(d.bins + bs + t); live = !is_claimed(a.claimed, rid); }
-    const unsigned lm = __ballot_sync(FULL, live);
+    if (act && t < bc) {
+      rid = bc <= 3 ? (t == 0 ? r0 : t == 1 ? r1 : r2) : __ldg(d.bins + bs + t);
+      live = !is_claimed(a.claimed, rid);
+    }
+    const unsigned lm = __ballot_sync(FULL, live) & leaders;  // one bit per live candidate, in scan order
     if (prefix_dead) {
-      if (lm == 0) dead_to = min(bc, off + 32);
+      if (lm == 0) dead_to = min(bc, off + G);
       else {
-        dead_to = off + (__ffs(lm) - 1);
+        dead_to = off + (uint32_t)__popc(leaders & ((1u << (__ffs(lm) - 1)) - 1u));
         prefix_dead = false;
         if (lane == 0 && dead_to > t0) atomicMax(d.skip + (bs - 1), dead_to);
       }
     }
-    const int rank = live_before + __popc(lm & ((1u << lane) - 1u));
+    const int rank = live_before + __popc(lm & below);
     const bool ev = live && rank < kMaxSearch;
-    bool pass = false;
+    int h = 0;
     if (ev) {
       const int len = __ldg(a.lens + rid);
       int lo, hi;
       if (!rev) { lo = 0; hi = 2 * min(ref_len - s, len); }
       else { lo = 2 * s; hi = 2 * min(ref_len + s, len); }
-      const uint64_t *cand = a.reads + (size_t)rid * W;
-      int h = 0;
-      for (int i = 0; i < W; i++) {
-        const uint64_t m = range_mask(i, lo, hi);
-        if (m) {
-          const uint64_t r = rev ? shl_word(refsm, W, i, 2 * s) : shr_word(refsm, W, i, 2 * s);
-          h += __popcll((r ^ __ldg(cand + i)) & m);
-        }
-      }
-      pass = h <= kThreshReorder;
+      const uint64_t m = range_mask(wig, lo, hi);
+      if (m) h = __popcll((rw ^ __ldg(a.reads + (size_t)rid * W + wig)) & m);
     }
-    const unsigned em = __ballot_sync(FULL, ev), pm = __ballot_sync(FULL, pass);
+    for (int o = 1; o < W; o <<= 1) {  // sum over the group's W lanes, into its leader
+      const int t2 = __shfl_down_sync(FULL, h, o);
+      if (wig + o < W) h += t2;
+    }
+    const unsigned em = __ballot_sync(FULL, ev) & leaders;
+    const unsigned pm = __ballot_sync(FULL, ev && h <= kThreshReorder) & leaders;
     if (pm) {
       const int wl = __ffs(pm) - 1;
       rid_out = __shfl_sync(FULL, rid, wl);
@@ -225,9 +323,9 @@ __device__ bool scan_bin(const ChainArgs &a, const DictView &d, uint32_t bs, uin
 // batch b = 0, 1, ...; a chain that finds nothing continues with the next batch in the next round
 // (bounded work per round keeps the lock-step chains balanced; claims only grow, so earlier batches
 // cannot turn productive later -- same result as a full search, see oracle/spring_oracle.c).
-__device__ bool chain_search(const ChainArgs &a, const uint64_t *ref, const uint64_t *revref, int ref_len, int lane, int b,
-                             int S, uint32_t &prop_rid, int &prop_shift, int &prop_rev, unsigned long long &probes_issued,
-                             unsigned long long &probes_seq, unsigned long long &compares, unsigned long long &slot_probes) {
+__device__ bool chain_search(const ChainArgs &a, const uint64_t *ref, const uint64_t *revref, int ref_len, int lane, int grp,
+                             int wig, int b, int S, uint32_t &prop_rid, int &prop_shift, int &prop_rev, uint32_t &probes_issued,
+                             uint32_t &probes_seq, uint32_t &compares, uint32_t &slot_probes) {
   const int W = a.W;
   const int kind = lane & 3, rev = kind >> 1, sub = lane >> 2;
   const DictView &d = a.dict[kind & 1];
@@ -249,7 +347,7 @@ __device__ bool chain_search(const ChainArgs &a, const uint64_t *ref, const uint
         if (filter_test_hint(d.filter, d.filter_mask, mix64(key), pol_keep)) cand |= 1u << j;
       }
     }
-    probes_issued += __reduce_add_sync(FULL, (unsigned)__popc(okm));
+    probes_issued += (unsigned)__popc(okm);  // per-lane partial sum, reduced when the chain ends
     // ---- pass 2: resolve hits in priority order ----------------------------------------------------
     int cur_j = -1, found_p = -1;
     uint32_t cur_start1 = 0, cur_count = 0, cur_r0 = 0, cur_r1 = 0, cur_r2 = 0;
@@ -279,12 +377,10 @@ __device__ bool chain_search(const ChainArgs &a, const uint64_t *ref, const uint
       const int owner = (((ps - S) & 7) << 2) | pk;
       const uint32_t mb = __shfl_sync(FULL, cur_start1, owner);  // entries follow the header at bins[mb - 1]
       const uint32_t mc = __shfl_sync(FULL, cur_count, owner);
-      // lane t < 3 receives the owner's t-th inline id
       const uint32_t r0 = __shfl_sync(FULL, cur_r0, owner), r1 = __shfl_sync(FULL, cur_r1, owner), r2 = __shfl_sync(FULL, cur_r2, owner);
-      const uint32_t in3 = lane == 0 ? r0 : lane == 1 ? r1 : r2;
       const DictView &pd = a.dict[pk & 1];
       uint32_t rid;
-      if (scan_bin(a, pd, mb, mc, in3, (pk >> 1) ? revref : ref, pk >> 1, ps, ref_len, lane, rid, compares)) {
+      if (scan_bin(a, pd, mb, mc, r0, r1, r2, (pk >> 1) ? revref : ref, pk >> 1, ps, ref_len, lane, grp, wig, rid, compares)) {
         prop_rid = rid; prop_shift = ps; prop_rev = pk >> 1; found_p = p;
         break;
       }
@@ -302,7 +398,7 @@ __device__ bool chain_search(const ChainArgs &a, const uint64_t *ref, const uint
         seqmask = jm < 0 ? 0u : (jm >= 31 ? seqmask : seqmask & ((2u << jm) - 1u));
       }
     }
-    probes_seq += __reduce_add_sync(FULL, (unsigned)__popc(seqmask));
+    probes_seq += (unsigned)__popc(seqmask);
     if (found_p >= 0) return true;
   }
   return false;
@@ -340,15 +436,35 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, SB_MIN_BLOCKS) k_chains(C
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const uint32_t cid = blockIdx.x * kWarpsPerBlock + wib;
   const int W = a.W, Lp = a.Lp;
+  const int grp = lane / W, wig = lane - grp * W;  // scan_bin's lane layout
   const size_t per_chain = 3 * (size_t)W + (size_t)Lp;  // uint64 words: ref, revref, cur, Lp packed count columns
   uint64_t *ref = smem + wib * per_chain, *revref = ref + W, *curw = revref + W;
   uint64_t *cnt = curw + W;  // one word per column: four u16 counts {A,C,T,G}
 
   int state = cid < a.num_chains ? ST_SEARCH : ST_DONE;
   int ref_len = 0, prev_unmatched = 0, left_search = 0, iter_started = 0, stop_searching = 0, batch = 0, batch_S = 0;
-  long long ref_pos = 0, cur_read_pos = 0, cursor = -1, slice_lo = 0;
+  long long ref_pos = 0, cur_read_pos = 0;
+  int cursor = -1, slice_lo = 0;  // read ids fit 31 bits (check_input)
   uint32_t first_rid = 0, prev = 0, num_reads_thr = 0, num_unmatched_1m = 0, n_aligned = 0, n_single = 0;
-  unsigned long long c_unmatched = 0, c_lost = 0, c_issued = 0, c_seq = 0, c_cmp = 0, c_slot = 0, target = 0, round = 0;
+  // statistics: c_issued / c_seq / c_slot are per-lane partial sums, c_cmp / c_unmatched / c_lost are
+  // warp-uniform; 32-bit in registers, flushed to the 64-bit totals before they can wrap
+  uint32_t c_unmatched = 0, c_lost = 0, c_issued = 0, c_seq = 0, c_cmp = 0, c_slot = 0;
+  unsigned long long target = 0, round = 0;
+  auto flush_counters = [&](bool force) {
+    if (!force && !__any_sync(FULL, (c_issued | c_seq | c_slot | c_cmp | c_lost) >> 30)) return;
+    auto wsum = [&](uint32_t v) {  // exact 64-bit warp sum of 32-bit lane values
+      return (unsigned long long)__reduce_add_sync(FULL, v & 0xFFFFu) + ((unsigned long long)__reduce_add_sync(FULL, v >> 16) << 16);
+    };
+    const unsigned long long s_issued = wsum(c_issued), s_seq = wsum(c_seq), s_slot = wsum(c_slot);
+    if (lane == 0) {
+      atomicAdd(a.ctr + CTR_PROBES_ISSUED, s_issued);
+      atomicAdd(a.ctr + CTR_PROBES_SEQ, s_seq);
+      atomicAdd(a.ctr + CTR_SLOT_PROBES, s_slot);
+      atomicAdd(a.ctr + CTR_COMPARES, (unsigned long long)c_cmp);
+      atomicAdd(a.ctr + CTR_LOST, (unsigned long long)c_lost);
+    }
+    c_issued = c_seq = c_slot = c_cmp = c_lost = 0;
+  };
 
   // claim bit + "remove from both dictionaries" (reorder.h:458-472): one decrement per bin
   auto claim = [&](uint32_t rid) {
@@ -366,19 +482,26 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, SB_MIN_BLOCKS) k_chains(C
     if (lane < W) curw[lane] = __ldg(a.reads + (size_t)rid * W + lane);
     __syncwarp();
   };
+  // fold the read staged in curw into the window: word-parallel fast path, or the per-column generic
+  // version for the reference's in-place "fold" quirk (and on request, as a cross-check)
+  auto upd = [&](int old_len, int delta, int cs, int cur_len, bool rev, int new_len, int fold) {
+    if (fold > 0 || a.generic_update) update_ref(ref, revref, curw, cnt, W, lane, old_len, delta, cs, cur_len, rev, new_len, fold, a.overflow);
+    else update_ref_fast(ref, revref, curw, cnt, W, lane, old_len, delta, cs, cur_len, rev, new_len, a.overflow);
+  };
   // the read must already be staged in curw
   auto new_contig = [&](uint32_t rid) {  // updaterefcount(..., resetcount = true, rev = false) + reorder.h:426-430,:601-612
     const int len = __ldg(a.lens + rid);
-    update_ref(ref, revref, curw, cnt, W, lane, 0, 0, 0, len, false, len, 0, a.overflow);
+    upd(0, 0, 0, len, false, len, 0);
     ref_len = len; ref_pos = 0; cur_read_pos = 0;
     prev_unmatched = 1; first_rid = rid; prev = rid; left_search = 0;
     state = ST_SEARCH; iter_started = 0; batch = 0; batch_S = 0;
+    flush_counters(false);
   };
 
   if (state == ST_SEARCH) {  // reorder.h:405-431
     const uint32_t first = cid * a.per;
-    slice_lo = first;
-    cursor = cid == a.num_chains - 1 ? (long long)a.N - 1 : (long long)(cid + 1) * a.per - 1;
+    slice_lo = (int)first;
+    cursor = cid == a.num_chains - 1 ? (int)a.N - 1 : (int)((cid + 1) * a.per) - 1;
     claim(first);
     c_unmatched++;
     stage_read(first);
@@ -409,7 +532,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, SB_MIN_BLOCKS) k_chains(C
         if (!stop_searching) {
           int b = 0, S = 0;
           while (S < a.maxshift) {
-            if (chain_search(a, ref, revref, ref_len, lane, b, S, k, shift, prev_rev, c_issued, c_seq, c_cmp, c_slot)) {
+            if (chain_search(a, ref, revref, ref_len, lane, grp, wig, b, S, k, shift, prev_rev, c_issued, c_seq, c_cmp, c_slot)) {
               unsigned old = 0;
               if (lane == 0) old = atomicOr(a.claimed + (k >> 5), 1u << (k & 31));
               old = __shfl_sync(FULL, old, 0);
@@ -433,7 +556,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, SB_MIN_BLOCKS) k_chains(C
           else if (len - shift >= old) { fold = len - shift - old; delta = -fold; cs = 0; nl = len; }
           else if (old + shift <= a.L) { delta = 0; cs = old - len + shift; nl = old + shift; }
           else { delta = old + shift - a.L; cs = a.L - len; nl = a.L; }
-          update_ref(ref, revref, curw, cnt, W, lane, old, delta, cs, len, prev_rev != 0, nl, fold, a.overflow);
+          upd(old, delta, cs, len, prev_rev != 0, nl, fold);
           ref_len = nl;
           if (!prev_rev) {
             if (!left_search) { cur_read_pos = ref_pos + shift; ref_pos = cur_read_pos; }
@@ -457,7 +580,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, SB_MIN_BLOCKS) k_chains(C
             left_search = 1;
             stage_read(first_rid);
             const int len = __ldg(a.lens + first_rid);
-            update_ref(ref, revref, curw, cnt, W, lane, 0, 0, 0, len, true, len, 0, a.overflow);
+            upd(0, 0, 0, len, true, len, 0);
             ref_len = len; ref_pos = 0; cur_read_pos = 0;
             iter_started = 0;
           } else {
@@ -472,7 +595,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, SB_MIN_BLOCKS) k_chains(C
           unsigned old = 0;
           if (lane == 0) old = atomicOr(a.claimed + (j >> 5), 1u << (j & 31));
           old = __shfl_sync(FULL, old, 0);
-          cursor = (long long)j - 1;
+          cursor = (int)j - 1;
           if (!((old >> (j & 31)) & 1u)) { got = true; break; }
         }
         if (prev_unmatched) {
@@ -518,7 +641,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, SB_MIN_BLOCKS) k_chains(C
         iter_started = 1;
       }
       if (!stop_searching) {
-        has_prop = chain_search(a, ref, revref, ref_len, lane, batch, batch_S, prop_rid, prop_shift, prop_rev, c_issued,
+        has_prop = chain_search(a, ref, revref, ref_len, lane, grp, wig, batch, batch_S, prop_rid, prop_shift, prop_rev, c_issued,
                                 c_seq, c_cmp, c_slot);
         if (!has_prop) {
           const int nshift = 8 * (batch < 4 ? 1 << batch : 16);
@@ -553,7 +676,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, SB_MIN_BLOCKS) k_chains(C
           else if (len - shift >= old) { fold = len - shift - old; delta = -fold; cs = 0; nl = len; }  // :159-174
           else if (old + shift <= a.L) { delta = 0; cs = old - len + shift; nl = old + shift; } // :175-184
           else { delta = old + shift - a.L; cs = a.L - len; nl = a.L; }                         // :185-199
-          update_ref(ref, revref, curw, cnt, W, lane, old, delta, cs, len, prop_rev != 0, nl, fold, a.overflow);
+          upd(old, delta, cs, len, prop_rev != 0, nl, fold);
           ref_len = nl;
           if (!prop_rev) {  // reorder.h:490-497
             if (!left_search) { cur_read_pos = ref_pos + shift; ref_pos = cur_read_pos; }
@@ -581,7 +704,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, SB_MIN_BLOCKS) k_chains(C
         if (!left_search) {
           left_search = 1;
           const int len = __ldg(a.lens + first_rid);
-          update_ref(ref, revref, curw, cnt, W, lane, 0, 0, 0, len, true, len, 0, a.overflow);
+          upd(0, 0, 0, len, true, len, 0);
           ref_len = len; ref_pos = 0; cur_read_pos = 0;
           iter_started = 0; batch = 0; batch_S = 0;
         } else {
@@ -596,7 +719,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, SB_MIN_BLOCKS) k_chains(C
           claim_pre(j, pre_sidx);
           if (lane == 0 && prev_unmatched) { a.rec_chain[prev] = cid; a.rec_k[prev] = n_single; a.rec_meta[prev] = 4; }
           if (prev_unmatched) n_single++;
-          cursor = (long long)j - 1;
+          cursor = (int)j - 1;
           c_unmatched++;
           new_contig(j);
         } else {
@@ -619,16 +742,11 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, SB_MIN_BLOCKS) k_chains(C
       break;
     }
   }
-  for (int o = 16; o; o >>= 1) c_slot += __shfl_xor_sync(FULL, c_slot, o);
+  flush_counters(true);
   if (lane == 0) {
-    atomicAdd(a.ctr + CTR_SLOT_PROBES, c_slot);
     a.chain_aligned[cid] = n_aligned;
     a.chain_single[cid] = n_single;
-    atomicAdd(a.ctr + CTR_UNMATCHED, c_unmatched);
-    atomicAdd(a.ctr + CTR_LOST, c_lost);
-    atomicAdd(a.ctr + CTR_PROBES_ISSUED, c_issued);
-    atomicAdd(a.ctr + CTR_PROBES_SEQ, c_seq);
-    atomicAdd(a.ctr + CTR_COMPARES, c_cmp);
+    atomicAdd(a.ctr + CTR_UNMATCHED, (unsigned long long)c_unmatched);
     if (threadIdx.x == 0) {  // per-block numbers (thread 0 runs the barrier)
       atomicAdd(a.ctr + CTR_CYC_SEARCH, cy_search);
       atomicAdd(a.ctr + CTR_CYC_WAIT_A, cy_wait_a);
@@ -711,6 +829,10 @@ void run_reorder(Ctx &c, const uint64_t *reads, const uint16_t *lens, uint32_t n
   a.chain_dbg = getenv("SPRING_B200_CHAIN_DBG") ? c.pool.dev<unsigned long long>("ro.chain_dbg", 2 * (size_t)nslots + 2) : nullptr;
   if (a.chain_dbg) SB_CUDA(cudaMemsetAsync(a.chain_dbg, 0, (2 * (size_t)nslots + 2) * sizeof(unsigned long long), st));
   a.num_chains = C; a.per = n / C;
+  a.G = 32u / (uint32_t)W;
+  a.leader_mask = 0;
+  for (uint32_t g = 0; g < a.G; g++) a.leader_mask |= 1u << (g * W);
+  a.generic_update = getenv("SPRING_B200_GENERIC_UPDATE") ? 1 : 0;
   a.max_rounds = 8ull * n + 4096ull;
   SB_CUDA(cudaMemsetAsync(a.claimed, 0, bm_words * sizeof(uint32_t), st));
   SB_CUDA(cudaMemsetAsync(a.winner, 0xFF, (size_t)n * sizeof(uint32_t), st));

@@ -156,26 +156,38 @@ __global__ void k_abs_pos(const uint32_t *__restrict__ cidx1, const int64_t *__r
 
 // ---- consensus (buildcontig, encoder.cpp:32-74) ---------------------------------------------------
 constexpr int kTile = 256, kStage = 64;
+
+// Which sorted reads can touch which 256-column tile, without a binary search per tile (46 dependent
+// HBM loads per block used to be most of the consensus kernel's time): sorted_ap is ascending, so
+// tile_hi[t] = first r with ap[r] / kTile >= t and tile_lo[t] = first r with (ap[r] + L - 1) / kTile >= t
+// are written by the reads at which these quotients step up.  Tile t then stages reads
+// [tile_lo[t], tile_hi[t + 1]): those with ap + L - 1 >= t * kTile and ap < (t + 1) * kTile.
+__global__ void k_tile_ranges(const uint64_t *__restrict__ sorted_ap, uint32_t m, int L, uint32_t num_tiles,
+                              uint32_t *tile_lo, uint32_t *tile_hi) {
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r > m) return;
+  // r == m: a virtual read beyond every tile closes the arrays (entries up to num_tiles inclusive)
+  const uint64_t hi_now = r < m ? sorted_ap[r] / kTile : (uint64_t)num_tiles + 1;
+  const uint64_t lo_now = r < m ? (sorted_ap[r] + (uint64_t)(L - 1)) / kTile : (uint64_t)num_tiles + 1;
+  const uint64_t hi_prev = r ? sorted_ap[r - 1] / kTile + 1 : 0;                          // first tile not yet assigned
+  const uint64_t lo_prev = r ? (sorted_ap[r - 1] + (uint64_t)(L - 1)) / kTile + 1 : 0;
+  for (uint64_t t = hi_prev; t <= hi_now && t <= num_tiles; t++) tile_hi[t] = r;
+  for (uint64_t t = lo_prev; t <= lo_now && t <= num_tiles; t++) tile_lo[t] = r;
+}
 __global__ void __launch_bounds__(kTile) k_consensus(const uint64_t *__restrict__ reads, const uint16_t *__restrict__ lens,
                                                      const uint32_t *__restrict__ order, const uint8_t *__restrict__ rev,
                                                      const uint64_t *__restrict__ sorted_ap, const uint32_t *__restrict__ perm,
+                                                     const uint32_t *__restrict__ tile_lo, const uint32_t *__restrict__ tile_hi,
                                                      uint32_t m, int W, int L, uint64_t seq_len, uint64_t *cons2) {
   __shared__ uint64_t s_words[kStage * kMaxWords];  // staged reads, already oriented as in the contig
   __shared__ int s_rel[kStage];                     // read start relative to the tile's first column
   __shared__ uint32_t s_rid[kStage];
   __shared__ uint16_t s_len[kStage];
   __shared__ uint8_t s_rev[kStage];
-  __shared__ uint32_t s_range[2];
   const uint64_t x0 = (uint64_t)blockIdx.x * kTile;
   const uint64_t x = x0 + threadIdx.x;
   const int xr = (int)threadIdx.x;
-  if (threadIdx.x == 0) {
-    const uint64_t lo_ap = x0 >= (uint64_t)(L - 1) ? x0 - (uint64_t)(L - 1) : 0;  // reads with ap + L > x0
-    s_range[0] = lower_bound_u64(sorted_ap, m, lo_ap);
-    s_range[1] = lower_bound_u64(sorted_ap, m, x0 + kTile);
-  }
-  __syncthreads();
-  const uint32_t r_lo = s_range[0], r_hi = s_range[1];
+  const uint32_t r_lo = tile_lo[blockIdx.x], r_hi = tile_hi[blockIdx.x + 1];  // reads with ap + L > x0 and ap < x0 + kTile
   uint32_t cA = 0, cC = 0, cG = 0, cT = 0;
   for (uint32_t base = r_lo; base < r_hi; base += kStage) {
     const uint32_t cnt = min((uint32_t)kStage, r_hi - base);
@@ -229,20 +241,22 @@ struct AlignArgs {
   const uint64_t *pool_codes; const uint16_t *pool_len; const uint32_t *pool_ncount;
   int W, L;
   unsigned long long *best;
+  const uint32_t *tile_contig;  // contig holding column 256 * t (k_tile_contigs)
 };
+// contig of the first column of every 256-column block: thread per contig, each writes the block starts
+// that fall inside it (contigs tile the consensus, so every block start has exactly one owner)
+__global__ void k_tile_contigs(const unsigned long long *__restrict__ cstart, uint32_t nc, uint32_t *tile_contig) {
+  const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nc) return;
+  const unsigned long long b = cstart[c], e = cstart[c + 1];
+  for (unsigned long long t = (b + 255) / 256; t * 256 < e; t++) tile_contig[t] = c;
+}
 __global__ void k_align_singletons(AlignArgs a) {
   const uint64_t j0 = (uint64_t)blockIdx.x * blockDim.x, j = j0 + threadIdx.x;
-  // contig of the block's first column by binary search (last c with cstart[c] <= j0); each thread
-  // then walks forward the few contigs a 256-column block can span
-  __shared__ uint32_t s_c0;
-  if (threadIdx.x == 0) {
-    uint32_t l0 = 0, h0 = a.num_contigs;
-    while (h0 - l0 > 1) { const uint32_t mid = (l0 + h0) >> 1; if (a.cstart[mid] <= j0) l0 = mid; else h0 = mid; }
-    s_c0 = l0;
-  }
-  __syncthreads();
+  // contig of the block's first column from the table; each thread then walks forward the few contigs
+  // a 256-column block can span
   if (j + (uint64_t)a.L > a.seq_len) return;
-  uint32_t lo = s_c0;
+  uint32_t lo = a.tile_contig[blockIdx.x];
   while (lo + 1 < a.num_contigs && a.cstart[lo + 1] <= j) lo++;
   if (j + (uint64_t)a.L > a.cstart[lo + 1]) return;  // window leaves the contig (or contig shorter than max_readlen)
   const int L = a.L, W = a.W;
@@ -519,9 +533,13 @@ void run_encode(Ctx &c, const uint64_t *reads, const uint16_t *lens, uint32_t n,
   const uint64_t cons_words = (seq_len + 31) / 32;
   uint64_t *cons2 = c.pool.dev<uint64_t>("en.cons2", cons_words + 4);
   SB_CUDA(cudaMemsetAsync(cons2 + cons_words, 0, 4 * sizeof(uint64_t), st));  // zero pad: windows may read 2 words past the end
+  const uint32_t num_tiles = grid_for(seq_len, kTile);
+  uint32_t *tile_lo = c.pool.dev<uint32_t>("en.tile_lo", (size_t)num_tiles + 2), *tile_hi = c.pool.dev<uint32_t>("en.tile_hi", (size_t)num_tiles + 2);
+  uint32_t *tile_contig = c.pool.dev<uint32_t>("en.tile_contig", (size_t)num_tiles + 2);
   if (seq_len) {
-    k_consensus<<<grid_for(seq_len, kTile), kTile, 0, st>>>(reads, lens, ro.order, ro.rev, sorted_ap, perm, M, W, L, seq_len, cons2);
-    c.launches++;
+    k_tile_ranges<<<grid_for((uint64_t)M + 1, 256), 256, 0, st>>>(sorted_ap, M, L, num_tiles, tile_lo, tile_hi);
+    k_consensus<<<num_tiles, kTile, 0, st>>>(reads, lens, ro.order, ro.rev, sorted_ap, perm, tile_lo, tile_hi, M, W, L, seq_len, cons2);
+    c.launches += 2;
   }
 
   // ---- singleton / N re-alignment ------------------------------------------------------------------
@@ -545,8 +563,10 @@ void run_encode(Ctx &c, const uint64_t *reads, const uint16_t *lens, uint32_t n,
       aa.cons2 = cons2; aa.seq_len = seq_len; aa.cstart = cstart; aa.num_contigs = NC;
       aa.dict[0] = ed[0].view; aa.dict[1] = ed[1].view;
       aa.pool_codes = pool_codes; aa.pool_len = pool_len; aa.pool_ncount = pool_ncount; aa.W = W; aa.L = L; aa.best = best;
+      aa.tile_contig = tile_contig;
+      k_tile_contigs<<<grid_for(NC, 256), 256, 0, st>>>(cstart, NC, tile_contig);
       k_align_singletons<<<grid_for(seq_len, 256), 256, 0, st>>>(aa);
-      c.launches++;
+      c.launches += 2;
     }
     uint8_t *fl_a = c.pool.dev<uint8_t>("en.fl_a", Pn), *fl_u = c.pool.dev<uint8_t>("en.fl_u", Pn);
     k_pool_flags<<<grid_for(P, 256), 256, 0, st>>>(best, P, fl_a, fl_u);

@@ -35,7 +35,7 @@ namespace sb {
 namespace {
 
 constexpr unsigned FULL = 0xFFFFFFFFu;
-constexpr int kWarpsPerBlock = 8;
+constexpr const char *kChainCfgDefault = "8x4";  // 32 chains per SM (64 registers, a few spills) beat 24 spill-free ones
 enum { ST_SEARCH = 0, ST_NEWREAD = 1, ST_DONE = 2 };
 enum { CTR_UNMATCHED = 0, CTR_ROUNDS, CTR_LOST, CTR_PROBES_ISSUED, CTR_PROBES_SEQ, CTR_COMPARES, CTR_ABORT,
        CTR_CYC_SEARCH, CTR_CYC_WAIT_A, CTR_CYC_COMMIT, CTR_CYC_WAIT_B, CTR_SLOT_PROBES, CTR_N };
@@ -195,19 +195,22 @@ __device__ void update_ref_fast(uint64_t *ref, uint64_t *revref, uint64_t *curw,
   for (int cc = 0; cc < nchunks; cc++) {  // ascending is safe: delta >= 0, sources lie at or above the column
     const int i = (cc << 5) + lane;
     const bool in = i < new_len;
-    uint64_t v = 0;
-    if (in && i + delta < old_len) v = cnt[i + delta];
+    uint2 v = make_uint2(0u, 0u);  // .x: rows A (bits 0-15), C (16-31); .y: rows T, G
+    if (in && i + delta < old_len) v = reinterpret_cast<const uint2 *>(cnt)[i + delta];
     __syncwarp();
     if (in) {
       const unsigned ci = (unsigned)(i - cs);
       if (ci < (unsigned)cur_len) {
         // cnt[col] packs the four per-base counts as u16 fields, rows A,C,T,G (reorder.h:120-123);
-        // 2-bit read codes are A0 G1 C2 T3 -> field shift 0, 48, 16, 32
-        const int sh = (int)((0x20103000u >> (8 * base_code(curw, (int)ci))) & 0xFFu);
-        v += 1ull << sh;
-        if (((v >> sh) & 0xFFFFull) == 0xFFFFull) *overflow = 1;  // > 65535 reads stacked on one column
+        // 2-bit read codes are A0 G1 C2 T3 -> field shift 0, 48, 16, 32: odd codes live in the high
+        // word, codes 1 and 2 in the upper half of their word
+        const int b = base_code(curw, (int)ci);
+        const int sh = ((b ^ (b >> 1)) & 1) << 4;
+        uint32_t f;
+        if (b & 1) { v.y += 1u << sh; f = v.y; } else { v.x += 1u << sh; f = v.x; }
+        if (((f >> sh) & 0xFFFFu) == 0xFFFFu) *overflow = 1;  // > 65535 reads stacked on one column
       }
-      cnt[i] = v;
+      reinterpret_cast<uint2 *>(cnt)[i] = v;
     }
   }
   uint64_t nw = 0, mm = 0;
@@ -323,6 +326,14 @@ __device__ bool scan_bin(const ChainArgs &a, const DictView &d, uint32_t bs, uin
 // batch b = 0, 1, ...; a chain that finds nothing continues with the next batch in the next round
 // (bounded work per round keeps the lock-step chains balanced; claims only grow, so earlier batches
 // cannot turn productive later -- same result as a full search, see oracle/spring_oracle.c).
+// bits [pos, pos + nbits) of a bitset that is followed by one zero word (ref / revref in shared memory):
+// no bounds checks, pos < 64 W
+__device__ __forceinline__ uint64_t window_key(const uint64_t *a, int pos, int nbits) {
+  const int k = pos >> 6, bs = pos & 63;
+  const uint64_t v = (a[k] >> bs) | ((a[k + 1] << 1) << (63 - bs));
+  return nbits < 64 ? v & ((1ull << nbits) - 1ull) : v;
+}
+
 __device__ bool chain_search(const ChainArgs &a, const uint64_t *ref, const uint64_t *revref, int ref_len, int lane, int grp,
                              int wig, int b, int S, uint32_t &prop_rid, int &prop_shift, int &prop_rev, uint32_t &probes_issued,
                              uint32_t &probes_seq, uint32_t &compares, uint32_t &slot_probes) {
@@ -331,6 +342,12 @@ __device__ bool chain_search(const ChainArgs &a, const uint64_t *ref, const uint
   const DictView &d = a.dict[kind & 1];
   const uint64_t *src = rev ? revref : ref;
   const uint64_t pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
+  // shifts this lane's probe kind may use: forward d.end + s < ref_len (reorder.h:264-265), reverse
+  // d.end < ref_len + s and s < d.start (:266-267), all below maxshift
+  const int s_lo = rev ? d.end - ref_len + 1 : 0;
+  const int s_hi = min(a.maxshift, rev ? d.start : ref_len - d.end);
+  // bit position of the window key in src at shift s: kbase + ksign * 2s
+  const int kbase = 2 * d.start, kstep = rev ? -2 : 2;
   {
     const int n = b < 4 ? 1 << b : 16;  // 8, 16, 32, 64, then 128 shifts per batch
     // ---- pass 1: bounds + filter bit for this lane's n probes (independent 4-byte loads) ----
@@ -338,12 +355,9 @@ __device__ bool chain_search(const ChainArgs &a, const uint64_t *ref, const uint
 #pragma unroll 4
     for (int j = 0; j < n; j++) {
       const int s = S + sub + 8 * j;
-      bool ok = s < a.maxshift;
-      if (!rev) ok = ok && !(d.end + s >= ref_len);                          // reorder.h:264-265
-      else ok = ok && !(d.end >= ref_len + s || d.start <= s);               // reorder.h:266-267
-      if (ok) {
+      if (s >= s_lo && s < s_hi) {
         okm |= 1u << j;
-        const uint64_t key = extract_bits(src, W, rev ? 2 * (d.start - s) : 2 * (d.start + s), d.key_bits);
+        const uint64_t key = window_key(src, kbase + kstep * s, d.key_bits);
         if (filter_test_hint(d.filter, d.filter_mask, mix64(key), pol_keep)) cand |= 1u << j;
       }
     }
@@ -356,7 +370,7 @@ __device__ bool chain_search(const ChainArgs &a, const uint64_t *ref, const uint
         const int j = __ffs(cand) - 1;
         cand &= cand - 1;
         const int s = S + sub + 8 * j;
-        const uint64_t key = extract_bits(src, W, rev ? 2 * (d.start - s) : 2 * (d.start + s), d.key_bits);
+        const uint64_t key = window_key(src, kbase + kstep * s, d.key_bits);
         uint32_t h = (uint32_t)mix64(key) & d.slot_mask;
         slot_probes++;
         for (;;) {
@@ -427,19 +441,25 @@ __device__ bool find_unclaimed(const uint32_t *claimed, long long lo, long long 
   return false;
 }
 
-#ifndef SB_MIN_BLOCKS
-#define SB_MIN_BLOCKS 3
-#endif
-template <bool LOCKSTEP>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, SB_MIN_BLOCKS) k_chains(ChainArgs a) {
+// shared memory of one chain, in uint64 words: ref and revref (W words + one zero word each, so that
+// window_key may read one word past the bitset), the staged read, Lp packed count columns
+__host__ __device__ inline size_t chain_smem_words(int W, int Lp) { return 3 * (size_t)W + 2 + (size_t)Lp; }
+
+// WPB warps (= chains) per block, at least MINB blocks per SM: the register budget is the knob that
+// decides how many chains co-reside (run_reorder picks the configuration)
+template <bool LOCKSTEP, int WPB, int MINB>
+__global__ void __launch_bounds__(WPB * 32, MINB) k_chains(ChainArgs a) {
+  constexpr int kWarpsPerBlock = WPB;
   extern __shared__ __align__(16) uint64_t smem[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const uint32_t cid = blockIdx.x * kWarpsPerBlock + wib;
   const int W = a.W, Lp = a.Lp;
   const int grp = lane / W, wig = lane - grp * W;  // scan_bin's lane layout
-  const size_t per_chain = 3 * (size_t)W + (size_t)Lp;  // uint64 words: ref, revref, cur, Lp packed count columns
-  uint64_t *ref = smem + wib * per_chain, *revref = ref + W, *curw = revref + W;
+  const size_t per_chain = chain_smem_words(W, Lp);
+  uint64_t *ref = smem + wib * per_chain, *revref = ref + W + 1, *curw = revref + W + 1;
   uint64_t *cnt = curw + W;  // one word per column: four u16 counts {A,C,T,G}
+  if (lane == 0) { ref[W] = 0ull; revref[W] = 0ull; }
+  __syncwarp();
 
   int state = cid < a.num_chains ? ST_SEARCH : ST_DONE;
   int ref_len = 0, prev_unmatched = 0, left_search = 0, iter_started = 0, stop_searching = 0, batch = 0, batch_S = 0;
@@ -793,9 +813,23 @@ void run_reorder(Ctx &c, const uint64_t *reads, const uint16_t *lens, uint32_t n
   out.s_order = c.pool.dev<uint32_t>("ro.s_order", nn);
   if (n == 0) return;
 
-  const size_t smem = kWarpsPerBlock * (3 * (size_t)W + (size_t)Lp) * sizeof(uint64_t);
   const bool lockstep = c.lockstep;
-  auto kern = lockstep ? k_chains<true> : k_chains<false>;
+  // launch configuration: warps per block x minimum blocks per SM.  The deterministic schedule is a
+  // cooperative launch and keeps 8 x 3; the free-running one defaults to kChainCfgDefault
+  // (SPRING_B200_KCFG=8x3|8x4|4x7 overrides it: occupancy experiments).
+  void (*kern)(ChainArgs) = k_chains<true, 8, 3>;
+  int kWarpsPerBlock = 8;
+  if (!lockstep) {
+    const char *cfg = getenv("SPRING_B200_KCFG");
+    const std::string want = cfg ? cfg : kChainCfgDefault;
+    if (want == "8x4") { kern = k_chains<false, 8, 4>; kWarpsPerBlock = 8; }
+    else if (want == "8x5") { kern = k_chains<false, 8, 5>; kWarpsPerBlock = 8; }
+    else if (want == "8x6") { kern = k_chains<false, 8, 6>; kWarpsPerBlock = 8; }
+    else if (want == "4x9") { kern = k_chains<false, 4, 9>; kWarpsPerBlock = 4; }
+    else if (want == "4x7") { kern = k_chains<false, 4, 7>; kWarpsPerBlock = 4; }
+    else { kern = k_chains<false, 8, 3>; kWarpsPerBlock = 8; }
+  }
+  const size_t smem = kWarpsPerBlock * chain_smem_words(W, Lp) * sizeof(uint64_t);
   SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
   SB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kWarpsPerBlock * 32, smem));

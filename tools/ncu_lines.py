@@ -1,65 +1,41 @@
-"""Aggregate ncu warp-stall samples of one kernel per CUDA source line.
+"""Aggregate an ncu report of one kernel per CUDA source line (needs -lineinfo and --import-source on).
 
-usage: ncu_lines.py <report.ncu-rep> <lib.so> <kernel-substring> [top]
-ncu's CLI prints per-SASS-instruction samples but no line numbers; nvdisasm -g prints the same
-instruction sequence with '//## File "...", line N' markers.  The two are aligned by index.
+usage: ncu_lines.py <report.ncu-rep> <kernel-regex> [top] [--by inst|samples]
+Uses `ncu --page source --print-source cuda,sass --csv`: the rows whose Address is "-" are ncu's own
+per-source-line aggregates (warp-stall samples, warp instructions executed), one section per file.
 """
-import csv, io, os, re, subprocess, sys, tempfile
+import csv, io, os, subprocess, sys
 
-rep, lib, kname = sys.argv[1:4]
-top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "-k", f"regex:{kname}"], capture_output=True, text=True).stdout
+args = [a for a in sys.argv[1:] if not a.startswith("--")]
+rep, kname = args[0], args[1]
+top = int(args[2]) if len(args) > 2 else 40
+by = "inst" if "--by" in sys.argv and sys.argv[sys.argv.index("--by") + 1] == "inst" else "samples"
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass", "-k", f"regex:{kname}"],
+                     capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
-hdr_i = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
-hdr, rows = rows[hdr_i], rows[hdr_i + 1:]
-si = hdr.index("# Samples")
-samples = [int(r[si]) for r in rows if len(r) > si]
-ii = hdr.index("Instructions Executed")
-rows = [r for r in rows if len(r) > si and r[si].isdigit()]
-insts = [int(r[ii]) for r in rows if len(r) > si]
-sass = [r[1].strip() for r in rows if len(r) > si]
-
-d = tempfile.mkdtemp()
-subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(lib)], cwd=d, capture_output=True)
-lines = None
-for f in sorted(os.listdir(d)):
-    txt = subprocess.run(["nvdisasm", "-g", os.path.join(d, f)], capture_output=True, text=True).stdout
-    if kname not in txt:
+cur_file, hdr, agg = None, None, {}
+for r in rows:
+    if not r:
         continue
-    # isolate the function
-    m = re.search(r"\.text\.[^\n]*" + re.escape(kname) + r"[^\n]*:\n", txt)
-    start = m.end() if m else txt.index(kname)
-    body = txt[start:]
-    end = re.search(r"\n\s*\.section|\n//-+ \.text\.", body)
-    body = body[: end.start()] if end else body
-    cur, lines = None, []
-    for ln in body.splitlines():
-        mm = re.search(r'//## File "([^"]+)", line (\d+)', ln)
-        if mm:
-            cur = (os.path.basename(mm.group(1)), int(mm.group(2)))
-            continue
-        if re.match(r"\s+/\*[0-9a-f]{4}\*/", ln):
-            lines.append(cur)
-    break
-if lines is None:
-    sys.exit("kernel not found in cubins")
-print(f"sass rows {len(sass)}  disasm instrs {len(lines)}  total samples {sum(samples)}")
-n = min(len(sass), len(lines))
-agg = {}
-iagg = {}
-for i in range(n):
-    agg[lines[i]] = agg.get(lines[i], 0) + samples[i]
-    iagg[lines[i]] = iagg.get(lines[i], 0) + insts[i]
-tot = sum(samples)
-itot = sum(insts)
-print(f"warp instructions executed: {itot}")
-src_cache = {}
-for (k, v) in sorted(agg.items(), key=lambda kv: -kv[1])[:top]:
-    text = ""
-    if k:
-        p = os.path.join(os.path.dirname(os.path.abspath(lib)), "csrc", k[0])
-        if p not in src_cache and os.path.exists(p):
-            src_cache[p] = open(p).read().splitlines()
-        if p in src_cache and k[1] - 1 < len(src_cache[p]):
-            text = src_cache[p][k[1] - 1].strip()[:110]
-    print(f"{100*v/tot:5.1f}%  inst {100*iagg[k]/itot:5.1f}%  {k}  {text}")
+    if r[0] == "File Path":
+        cur_file = os.path.basename(r[1]); continue
+    if r[0] == "Line No":
+        hdr = r; continue
+    if hdr is None or len(r) < len(hdr) or r[2] != "-":
+        continue
+    si, ii, ti = hdr.index("# Samples"), hdr.index("Instructions Executed"), hdr.index("Thread Instructions Executed")
+    try:
+        s, i, t = int(r[si]), int(r[ii]), int(r[ti])
+    except ValueError:
+        continue
+    k = (cur_file, int(r[0]))
+    a = agg.setdefault(k, [0, 0, 0, r[1].strip()])
+    a[0] += s; a[1] += i; a[2] += t
+tot_s = sum(a[0] for a in agg.values()) or 1
+tot_i = sum(a[1] for a in agg.values()) or 1
+tot_t = sum(a[2] for a in agg.values())
+print(f"kernel {kname}: {tot_s} stall samples, {tot_i} warp instructions, {tot_t / tot_i:.1f} active threads per instruction")
+key = (lambda kv: -kv[1][1]) if by == "inst" else (lambda kv: -kv[1][0])
+print("samples%  inst%   thr/inst  file:line  source")
+for k, a in sorted(agg.items(), key=key)[:top]:
+    print(f"{100 * a[0] / tot_s:6.1f}  {100 * a[1] / tot_i:6.1f}  {a[2] / max(a[1], 1):6.1f}  {k[0]}:{k[1]}  {a[3][:100]}")

@@ -280,11 +280,18 @@ __global__ void k_align_singletons(AlignArgs a) {
       const uint32_t rid = d.bins[hdr + 1 + t];
       const int len = a.pool_len[rid];
       const uint64_t *r = a.pool_codes + (size_t)rid * W;
+      // Hamming distance over the read's length, 32 bases per step.  Reverse strand: base b of the
+      // window's reverse complement against read base b is consensus base j + L - 1 - b against the
+      // complement of read base b, i.e. the consensus from j + L - len on against RC(read).  N bases are
+      // stored as 00 and counted once more through pool_ncount (3-bit codes of the reference, header).
+      const uint64_t x0 = rev ? j + (uint64_t)(L - len) : j;
       int h = (int)a.pool_ncount[rid];
-      for (int b = 0; b < len && h <= kThreshEncoder; b++) {
-        const uint64_t x = rev ? j + L - 1 - b : j + b;
-        const int cc = (int)((a.cons2[x >> 5] >> (2 * (x & 31))) & 3ull);
-        h += __popc((unsigned)((rev ? 3 - cc : cc) ^ base_code(r, b)));
+      const int nw = (len + 31) >> 5;
+      for (int i = 0; i < nw && h <= kThreshEncoder; i++) {
+        const uint64_t o = oriented_word(r, W, len, rev != 0, i);
+        const int rem = len - 32 * i;
+        const uint64_t lm = rem >= 32 ? ~0ull : (1ull << (2 * rem)) - 1ull;
+        h += __popcll((o ^ cons_bits(a.cons2, x0 + 32ull * i)) & lm);
       }
       if (h <= kThreshEncoder) atomicMin(a.best + rid, prio);
     }

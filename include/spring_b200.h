@@ -116,6 +116,7 @@ typedef struct spring_b200_stats {
   float ms_chain_kernel;     /* k_chains alone (CUDA events around the cooperative launch) */
   uint64_t cyc_search, cyc_wait_a, cyc_commit, cyc_wait_b; /* SM cycles summed over blocks, per phase of a round */
   uint64_t slot_probes;      /* lookups that passed the L2-resident key filter and read the slot table in HBM */
+  float ms_reblock;          /* device time of the last spring_b200_reblock_* call (pe_encode + re-blocking kernels) */
 } spring_b200_stats;
 
 /* ---- context ---------------------------------------------------------------------------- */
@@ -165,6 +166,42 @@ int spring_b200_reorder(spring_b200_ctx *ctx, const spring_b200_input *in, uint3
  * encoder consumed), copied to host memory owned by the context: lets a test feed the very same
  * stream to an independent encoder. */
 int spring_b200_fetch_reorder(spring_b200_ctx *ctx, spring_b200_reorder_out *out);
+
+/* ---- the stages after the encoder ----------------------------------------------- */
+/* pe_encode (src/pe_encode.cpp:24-84; called at src/spring.cpp:193 for -r paired input): order[i] =
+ * original index of stream read i (read_order.bin) -> order_out[i] = its position in the decompressed
+ * output (file-1 reads keep the stream order, mates follow at + num_reads/2).  HOST buffers. */
+int spring_b200_pe_encode(spring_b200_ctx *ctx, const uint32_t *order, uint32_t num_reads, uint32_t *order_out);
+
+/* The nine per-block streams reorder_compress_streams hands to BSC
+ * (src/reorder_compress_streams.cpp:201-361): read_flag.txt.<b>, read_pos.bin.<b>, read_noise.txt.<b>,
+ * read_noisepos.bin.<b>, read_rev.txt.<b>, read_unaligned.txt.<b>, read_lengths.bin.<b>,
+ * read_pos_pair.bin.<b>, read_rev_pair.txt.<b> (the last two only for paired-end input). */
+#define SPRING_B200_NUM_BLOCK_STREAMS 9
+enum spring_b200_block_stream {
+  SPRING_B200_BS_FLAG = 0, SPRING_B200_BS_POS, SPRING_B200_BS_NOISE, SPRING_B200_BS_NOISEPOS, SPRING_B200_BS_REV,
+  SPRING_B200_BS_UNALIGNED, SPRING_B200_BS_LENGTHS, SPRING_B200_BS_POS_PAIR, SPRING_B200_BS_REV_PAIR
+};
+typedef struct spring_b200_blocks {
+  uint32_t num_blocks;                                    /* ceil(units / cp.num_reads_per_block), units = reads or pairs */
+  const uint8_t *data[SPRING_B200_NUM_BLOCK_STREAMS];     /* stream s, blocks concatenated; HOST, owned by the context */
+  uint64_t size[SPRING_B200_NUM_BLOCK_STREAMS];           /* bytes */
+  const uint64_t *off[SPRING_B200_NUM_BLOCK_STREAMS];     /* [num_blocks + 1]: block b = data[s][off[s][b] .. off[s][b+1]) */
+  const uint32_t *order;   /* read_order.bin as the stage consumed it (after pe_encode), NULL when it is not used (SE -r) */
+  uint64_t num_reads;
+} spring_b200_blocks;
+/* The re-blocking of reorder_compress_streams (src/reorder_compress_streams.cpp:83-361), preceded by
+ * pe_encode when cp->paired_end && !cp->preserve_order (src/spring.cpp:193).  streams: the encoder's
+ * output as HOST arrays, or NULL to use the streams the last spring_b200_reorder_encode* call on this
+ * context left in HBM (no host round trip).  Uses cp->paired_end, preserve_order, num_reads_per_block. */
+int spring_b200_reblock_streams(spring_b200_ctx *ctx, const spring_b200_streams *streams, const spring_b200_cp *cp,
+                                spring_b200_blocks *out);
+/* File-level drop-in for pe_encode + reorder_compress_streams up to (not including) the BSC calls:
+ * reads read_pos.bin, read_noise.txt, read_noisepos.bin, read_rev.txt, read_order.bin, read_lengths.bin,
+ * read_unaligned.txt[.count] from temp_dir, deletes them (as :174-181 does) and writes the raw block
+ * files <name>.<b>; the host then runs bsc::BSC_compress(<name>.<b>, <name>.<b>.bsc) on each and removes
+ * the raw file (:363-428).  See INTEGRATION.md. */
+int spring_b200_reblock_files(spring_b200_ctx *ctx, const char *temp_dir, const spring_b200_cp *cp);
 
 /* ---- multi-GPU partitioning ------------------------------------------------------------------ */
 /* DEVICE pointers.  bucket[i] = hash(strand-canonical 16-mer minimizer of read i) mod num_buckets:

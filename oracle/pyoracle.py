@@ -240,3 +240,97 @@ def load_reference_streams(temp_dir: str, num_thr: int) -> EncodeResult:
     return EncodeResult(seq, rd("read_pos.bin", np.uint64), rd("read_noise.txt"), rd("read_noisepos.bin", np.uint16), rc,
                         rd("read_order.bin", np.uint32), rd("read_lengths.bin", np.uint16), rd("read_unaligned.txt"),
                         ul, len(rc), -1, -1)
+
+
+# ---------------------------------------------------------------------------------------------
+# pe_encode + the re-blocking of reorder_compress_streams (oracle/reblock_oracle.c), SURVEY 8(f)
+# ---------------------------------------------------------------------------------------------
+BLOCK_STREAMS = ("flag", "pos", "noise", "noisepos", "rc", "unaligned", "lengths", "pos_pair", "rc_pair")
+BLOCK_FILES = ("read_flag.txt", "read_pos.bin", "read_noise.txt", "read_noisepos.bin", "read_rev.txt",
+               "read_unaligned.txt", "read_lengths.bin", "read_pos_pair.bin", "read_rev_pair.txt")
+
+
+class _BlocksOut(C.Structure):
+    _fields_ = [("data", C.POINTER(C.c_uint8) * 9), ("size", C.c_uint64 * 9), ("cap", C.c_uint64 * 9),
+                ("off", C.POINTER(C.c_uint64) * 9), ("num_blocks", C.c_uint32)]
+
+
+@dataclass
+class BlockStreams:
+    """The nine per-block streams reorder_compress_streams hands to BSC, blocks concatenated.
+    data[s]: uint8 bytes; off[s]: uint64[num_blocks + 1] byte offsets of the blocks in data[s]."""
+    num_blocks: int
+    data: dict
+    off: dict
+
+    def block(self, stream: str, b: int) -> bytes:
+        o = self.off[stream]
+        return self.data[stream][int(o[b]): int(o[b + 1])].tobytes()
+
+
+def pe_encode(order: np.ndarray) -> np.ndarray:
+    """pe_encode.cpp:24-84 on read_order.bin's contents."""
+    o = np.ascontiguousarray(order, dtype=np.uint32).copy()
+    buf = o if len(o) else np.zeros(1, np.uint32)
+    if lib().orc_pe_encode(_p(buf, C.c_uint32), C.c_uint32(len(o))) != 0:
+        raise RuntimeError("orc_pe_encode failed")
+    return o
+
+
+def reblock(er, paired_end: bool, preserve_order: bool, num_reads_per_block: int = 256000, order=None) -> BlockStreams:
+    """reorder_compress_streams.cpp:83-361 on the encoder streams `er` (EncodeResult / StreamsResult);
+    `order` overrides er.order (the output of pe_encode for -r paired input)."""
+    assert lib().orc_sizeof_blocks_out() == C.sizeof(_BlocksOut)
+    order = er.order if order is None else order
+    nz = lambda a, dt: np.ascontiguousarray(a, dtype=dt) if len(a) else np.zeros(1, dt)
+    pos, noise, noisepos, rc = nz(er.pos, np.uint64), nz(er.noise, np.uint8), nz(er.noisepos, np.uint16), nz(er.rc, np.uint8)
+    ordr, lens, unal = nz(order, np.uint32), nz(er.lengths, np.uint16), nz(er.unaligned, np.uint8)
+    out = _BlocksOut()
+    rcode = lib().orc_reblock(_p(pos, C.c_uint64), _p(noise, C.c_uint8), C.c_uint64(len(er.noise)), _p(noisepos, C.c_uint16),
+                              _p(rc, C.c_uint8), C.c_uint64(int(er.num_aligned)), _p(ordr, C.c_uint32), _p(lens, C.c_uint16),
+                              C.c_uint64(len(er.lengths)), _p(unal, C.c_uint8), C.c_uint64(len(er.unaligned)),
+                              C.c_int(int(paired_end)), C.c_int(int(preserve_order)), C.c_uint32(num_reads_per_block), C.byref(out))
+    if rcode != 0:
+        raise RuntimeError(f"orc_reblock failed: {rcode}")
+    nb = out.num_blocks
+    data, off = {}, {}
+    for i, name in enumerate(BLOCK_STREAMS):
+        n = out.size[i]
+        data[name] = np.ctypeslib.as_array(out.data[i], shape=(n,)).copy() if n else np.zeros(0, np.uint8)
+        off[name] = np.ctypeslib.as_array(out.off[i], shape=(nb + 1,)).copy()
+    lib().orc_blocks_free(C.byref(out))
+    return BlockStreams(nb, data, off)
+
+
+def write_encoder_streams(temp_dir: str, er, cp_bytes: bytes) -> None:
+    """Lay the encoder's streams out as files, as encoder.h:386-487 leaves them for the later host stages
+    (read_seq.bin.* is not needed by them), plus cp_in.bin for spring_ref --reblock."""
+    os.makedirs(temp_dir, exist_ok=True)
+    w = lambda name, a, dt: np.ascontiguousarray(a, dtype=dt).tofile(os.path.join(temp_dir, name))
+    w("read_pos.bin", er.pos, np.uint64); w("read_noise.txt", er.noise, np.uint8); w("read_noisepos.bin", er.noisepos, np.uint16)
+    w("read_rev.txt", er.rc, np.uint8); w("read_order.bin", er.order, np.uint32); w("read_lengths.bin", er.lengths, np.uint16)
+    w("read_unaligned.txt", er.unaligned, np.uint8)
+    np.array([er.unaligned_len], np.uint64).tofile(os.path.join(temp_dir, "read_unaligned.txt.count"))
+    with open(os.path.join(temp_dir, "cp_in.bin"), "wb") as f:
+        f.write(cp_bytes)
+
+
+def run_reference_reblock(temp_dir: str, paired_end: bool, num_blocks: int, num_thr: int = 2) -> BlockStreams:
+    """pe_encode + reorder_compress_streams of the unmodified reference on a temp_dir laid out by
+    write_encoder_streams; returns the raw (BSC-decoded) per-block files."""
+    r = subprocess.run([REF_BIN, "--reblock", "--temp", temp_dir, "-t", str(num_thr)], capture_output=True, text=True, cwd=temp_dir)
+    if r.returncode != 0:
+        raise RuntimeError(f"spring_ref --reblock failed:\n{r.stdout}\n{r.stderr}")
+    data, off = {}, {}
+    for name, fn in zip(BLOCK_STREAMS, BLOCK_FILES):
+        parts, o = [], [0]
+        for b in range(num_blocks):
+            p = os.path.join(temp_dir, f"{fn}.{b}")
+            if not paired_end and name in ("pos_pair", "rc_pair"):
+                a = np.zeros(0, np.uint8)
+            else:
+                a = np.fromfile(p, dtype=np.uint8) if os.path.getsize(p) else np.zeros(0, np.uint8)
+            parts.append(a); o.append(o[-1] + len(a))
+        data[name] = np.concatenate(parts) if parts else np.zeros(0, np.uint8)
+        off[name] = np.array(o, np.uint64)
+    return BlockStreams(num_blocks, data, off)

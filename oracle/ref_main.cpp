@@ -14,6 +14,10 @@
 //        reads DIR/cp_in.bin, runs call_reorder + call_encoder
 //        (spring.cpp:153,166), prints "HOTPATH_SECONDS reorder encode";
 //        --unbsc also BSC-decodes read_seq.bin.<t>.bsc to read_seq.bin.<t>
+//   spring_ref --reblock --temp DIR [-t N]
+//        reads DIR/cp_in.bin, runs pe_encode (spring.cpp:193, only for -r paired input) and
+//        reorder_compress_streams (spring.cpp:206) on the encoder streams in DIR, then BSC-decodes
+//        every per-block file it wrote (X.<b>.bsc -> X.<b>) so the raw block streams can be compared
 //
 // When built with -DSPRING_B200_SPLICE the two call_* symbols come from
 // spring_b200/csrc/host/call_template_functions_b200.cpp (our CUDA library
@@ -33,7 +37,9 @@
 #include <boost/filesystem.hpp>
 #include "call_template_functions.h"
 #include "libbsc/bsc.h"
+#include "pe_encode.h"
 #include "preprocess.h"
+#include "reorder_compress_streams.h"
 #include "spring.h"
 #include "util.h"
 
@@ -46,7 +52,7 @@ static double now_s() {
 int main(int argc, char **argv) {
   bool compress_flag = false, decompress_flag = false, pairing_only = false,
        no_quality = false, no_ids = false, pre_flag = false, hot_flag = false,
-       unbsc = false;
+       unbsc = false, reblock_flag = false;
   std::vector<std::string> in_vec, out_vec, quality_opts;
   std::vector<uint64_t> range_vec;
   std::string working_dir = ".", temp_given;
@@ -62,6 +68,7 @@ int main(int argc, char **argv) {
     else if (a == "--preprocess") { pre_flag = true; cur = NULL; }
     else if (a == "--hotpath") { hot_flag = true; cur = NULL; }
     else if (a == "--unbsc") { unbsc = true; cur = NULL; }
+    else if (a == "--reblock") { reblock_flag = true; cur = NULL; }
     else if (a == "-i" || a == "--input-file") cur = &in_vec;
     else if (a == "-o" || a == "--output-file") cur = &out_vec;
     else if ((a == "-t" || a == "--num-threads") && i + 1 < argc) { num_thr = atoi(argv[++i]); cur = NULL; }
@@ -108,6 +115,28 @@ int main(int argc, char **argv) {
         for (int t = 0; t < cp.num_thr; t++) {
           std::string b = temp_given + "/read_seq.bin." + std::to_string(t);
           spring::bsc::BSC_decompress((b + ".bsc").c_str(), b.c_str());
+        }
+      return 0;
+    }
+    if (reblock_flag) {
+      spring::compression_params cp;
+      std::ifstream f(temp_given + "/cp_in.bin", std::ios::binary);
+      f.read((char *)&cp, sizeof(cp));
+      if (!f.good()) throw std::runtime_error("cannot read cp_in.bin");
+      f.close();
+      remove((temp_given + "/cp_in.bin").c_str());
+      cp.num_thr = num_thr;
+      omp_set_dynamic(0);
+      if (!cp.preserve_order && cp.paired_end) spring::pe_encode(temp_given, cp);
+      spring::reorder_compress_streams(temp_given, cp);
+      const uint64_t units = cp.paired_end ? cp.num_reads / 2 : cp.num_reads;
+      const uint64_t nb = (units + cp.num_reads_per_block - 1) / cp.num_reads_per_block;
+      const char *names[] = {"read_flag.txt", "read_pos.bin", "read_noise.txt", "read_noisepos.bin", "read_rev.txt",
+                             "read_unaligned.txt", "read_lengths.bin", "read_pos_pair.bin", "read_rev_pair.txt"};
+      for (uint64_t b = 0; b < nb; b++)
+        for (int s = 0; s < (cp.paired_end ? 9 : 7); s++) {
+          std::string x = temp_given + "/" + names[s] + "." + std::to_string(b);
+          spring::bsc::BSC_decompress((x + ".bsc").c_str(), x.c_str());
         }
       return 0;
     }

@@ -20,6 +20,7 @@ EXPORTS = [
     "spring_b200_reorder_encode_device", "spring_b200_fetch_streams", "spring_b200_build_dictionary",
     "spring_b200_reorder", "spring_b200_reorder_encode_files", "spring_b200_write_streams",
     "spring_b200_bucket_reads", "spring_b200_set_schedule", "spring_b200_fetch_reorder", "spring_b200_set_stream",
+    "spring_b200_pe_encode", "spring_b200_reblock_streams", "spring_b200_reblock_files",
 ]
 
 
@@ -59,6 +60,15 @@ class ReorderOut(C.Structure):
                 ("singleton_order", C.c_void_p), ("num_singletons", C.c_uint64)]
 
 
+NUM_BLOCK_STREAMS = 9
+BLOCK_STREAMS = ("flag", "pos", "noise", "noisepos", "rc", "unaligned", "lengths", "pos_pair", "rc_pair")
+
+
+class Blocks(C.Structure):
+    _fields_ = [("num_blocks", C.c_uint32), ("data", C.c_void_p * NUM_BLOCK_STREAMS), ("size", C.c_uint64 * NUM_BLOCK_STREAMS),
+                ("off", C.c_void_p * NUM_BLOCK_STREAMS), ("order", C.c_void_p), ("num_reads", C.c_uint64)]
+
+
 class Stats(C.Structure):
     _fields_ = [("num_chains", C.c_uint32), ("unmatched", C.c_uint32), ("rounds", C.c_uint64),
                 ("lost_proposals", C.c_uint64), ("probes_issued", C.c_uint64), ("probes_seq", C.c_uint64),
@@ -66,7 +76,7 @@ class Stats(C.Structure):
                 ("ms_chains", C.c_float), ("ms_scatter", C.c_float), ("ms_encode", C.c_float), ("ms_d2h", C.c_float),
                 ("ms_total", C.c_float), ("ms_chain_kernel", C.c_float), ("cyc_search", C.c_uint64),
                 ("cyc_wait_a", C.c_uint64), ("cyc_commit", C.c_uint64), ("cyc_wait_b", C.c_uint64),
-                ("slot_probes", C.c_uint64)]
+                ("slot_probes", C.c_uint64), ("ms_reblock", C.c_float)]
 
     def as_dict(self) -> dict:
         return {f: getattr(self, f) for f, _ in self._fields_}
@@ -97,6 +107,9 @@ def load():
         lib.spring_b200_reorder_encode_files.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(CP), C.c_uint32]
         lib.spring_b200_bucket_reads.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
         lib.spring_b200_write_streams.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(Streams), C.c_int]
+        lib.spring_b200_pe_encode.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
+        lib.spring_b200_reblock_streams.argtypes = [C.c_void_p, C.POINTER(Streams), C.POINTER(CP), C.POINTER(Blocks)]
+        lib.spring_b200_reblock_files.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(CP)]
         _lib = lib
     return _lib
 
@@ -131,6 +144,20 @@ class StreamsResult:
         b = self.seq_packed
         codes = np.stack([(b >> (2 * j)) & 3 for j in range(4)], axis=1).reshape(-1)[: self.seq_len]
         return np.frombuffer(b"ACGT", dtype=np.uint8)[codes]
+
+
+@dataclass
+class BlocksResult:
+    """Host copy of spring_b200_blocks: data[s] = stream s with its blocks concatenated, off[s] the
+    byte offsets of the blocks (same layout as the oracle's BlockStreams)."""
+    num_blocks: int
+    data: dict
+    off: dict
+    order: "np.ndarray | None"
+
+    def block(self, stream: str, b: int) -> bytes:
+        o = self.off[stream]
+        return self.data[stream][int(o[b]): int(o[b + 1])].tobytes()
 
 
 class Context:
@@ -265,6 +292,41 @@ class Context:
         return (_view(o.order, o.num, np.uint32).copy(), _view(o.flag, o.num, np.uint8).copy(),
                 _view(o.pos, o.num, np.int64).copy(), _view(o.rev, o.num, np.uint8).copy(),
                 _view(o.singleton_order, o.num_singletons, np.uint32).copy())
+
+    # ---- the stages after the encoder ----------------------------------------------
+    def pe_encode(self, order: np.ndarray) -> np.ndarray:
+        """pe_encode (src/pe_encode.cpp:24-84) on read_order.bin's contents."""
+        o = np.ascontiguousarray(order, dtype=np.uint32)
+        out = np.empty_like(o)
+        self._check(self._lib.spring_b200_pe_encode(self._h, o.ctypes.data if len(o) else None, len(o),
+                                                    out.ctypes.data if len(o) else None))
+        return out
+
+    def reblock_streams(self, cp: CP, streams: "StreamsResult | None" = None) -> "BlocksResult":
+        """The re-blocking of reorder_compress_streams (+ pe_encode for -r paired input).  streams=None:
+        use the encoder streams the last reorder_encode* call left in HBM."""
+        sp = None
+        if streams is not None:
+            arrs = [np.ascontiguousarray(a, dtype=dt) for a, dt in (
+                (streams.pos, np.uint64), (streams.noise, np.uint8), (streams.noisepos, np.uint16), (streams.rc, np.uint8),
+                (streams.order, np.uint32), (streams.lengths, np.uint16), (streams.unaligned, np.uint8))]
+            self._keep = arrs
+            s = Streams()
+            ptr = lambda a: a.ctypes.data if a.size else None
+            s.pos, s.noise, s.noisepos, s.rev, s.order, s.lengths, s.unaligned = (ptr(a) for a in arrs)
+            s.noise_bytes, s.num_noise, s.unaligned_bytes = len(arrs[1]), len(arrs[2]), len(arrs[6])
+            s.unaligned_len, s.num_aligned, s.num_reads = int(streams.unaligned_len), int(streams.num_aligned), len(arrs[5])
+            sp = C.byref(s)
+        b = Blocks()
+        self._check(self._lib.spring_b200_reblock_streams(self._h, sp, C.byref(cp), C.byref(b)))
+        nb = b.num_blocks
+        data = {n: _view(b.data[i], b.size[i], np.uint8).copy() for i, n in enumerate(BLOCK_STREAMS)}
+        off = {n: _view(b.off[i], nb + 1, np.uint64).copy() for i, n in enumerate(BLOCK_STREAMS)}
+        order = _view(b.order, b.num_reads, np.uint32).copy() if b.order else None
+        return BlocksResult(nb, data, off, order)
+
+    def reblock_files(self, temp_dir: str, cp: CP) -> None:
+        self._check(self._lib.spring_b200_reblock_files(self._h, temp_dir.encode(), C.byref(cp)))
 
     # ---- files ---------------------------------------------------------------------------------
     def reorder_encode_files(self, temp_dir: str, cp: CP, num_chains: int = 0) -> None:

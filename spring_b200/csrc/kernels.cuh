@@ -67,6 +67,20 @@ struct NReads {  // reads with N, parsed from input_N.dna on the host and upload
 void run_encode(Ctx &c, const uint64_t *reads, const uint16_t *lens, uint32_t n, int L, const ReorderDev &ro,
                 const NReads &nr, uint32_t num_total, EncodeDev &out);
 
+// ---- reblock.cu : pe_encode + the re-blocking of reorder_compress_streams ---------------
+enum { RB_FLAG = 0, RB_POS, RB_NOISE, RB_NOISEPOS, RB_RC, RB_UNALIGNED, RB_LENGTHS, RB_POS_PAIR, RB_RC_PAIR, RB_NSTREAMS };
+struct ReblockDev {
+  uint32_t num_blocks = 0;
+  uint8_t *data[RB_NSTREAMS] = {};           // blocks concatenated (device)
+  uint64_t size[RB_NSTREAMS] = {};           // bytes
+  unsigned long long *block_off = nullptr;   // [RB_NSTREAMS][num_blocks + 1] byte offsets (device)
+  uint32_t *order = nullptr;                 // output slot of every stream read, or nullptr (SE -r: identity)
+};
+// pe_encode.cpp:24-84 on device arrays: slot[i] = position of stream read i in the decompressed output
+void run_pe_encode(Ctx &c, const uint32_t *order, uint32_t n, uint32_t *slot);
+// reorder_compress_streams.cpp:83-361 on the device-resident encoder streams `e`
+void run_reblock(Ctx &c, const EncodeDev &e, bool paired, bool preserve, uint32_t block, ReblockDev &out);
+
 // ---- bucket.cu : multi-GPU partitioning key --------------------------------------------------
 void bucket_reads(Ctx &c, const uint64_t *reads, const uint16_t *lens, uint32_t n, int L, uint32_t num_buckets, uint32_t *bucket);
 

@@ -27,7 +27,7 @@ struct spring_b200_ctx {
   EncodeDev last_enc{};
   ReorderDev last_ro{};
   bool have_enc = false;
-  cudaEvent_t ev[8]{};
+  cudaEvent_t ev[8]{};  // 0-5: the hot path's stages, 6-7: around the re-blocking
 };
 
 static thread_local std::string g_create_err;
@@ -285,6 +285,73 @@ void write_streams(const std::string &dir, const spring_b200_streams *s, int num
   spill(dir + "/read_unaligned.txt.count", &s->unaligned_len, 8);
 }
 
+// ---- pe_encode / re-blocking -----------------------------------------------------------------
+// host copies of the encoder's streams -> device buffers laid out like run_encode's output
+EncodeDev upload_streams(Ctx &c, const spring_b200_streams *s) {
+  if (s->num_aligned > s->num_reads) throw ArgError("streams: num_aligned > num_reads");
+  if (s->num_reads >= 0x7FFFFFF0ull) throw ArgError("too many reads for one GPU shard (>= 2^31)");
+  if (s->noise_bytes != s->num_noise + s->num_aligned) throw ArgError("streams: noise_bytes != num_noise + num_aligned");
+  EncodeDev e{};
+  auto up = [&](const char *name, const void *h, size_t bytes) -> void * {
+    void *d = c.pool.device(name, bytes + 8);
+    if (bytes) {
+      if (!h) throw ArgError(std::string("streams: null pointer for ") + name);
+      SB_CUDA(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, c.stream));
+    }
+    return d;
+  };
+  e.pos = (uint64_t *)up("rbin.pos", s->pos, s->num_aligned * 8);
+  e.noise = (uint8_t *)up("rbin.noise", s->noise, s->noise_bytes);
+  e.noisepos = (uint16_t *)up("rbin.noisepos", s->noisepos, s->num_noise * 2);
+  e.rev = (uint8_t *)up("rbin.rev", s->rev, s->num_aligned);
+  e.order = (uint32_t *)up("rbin.order", s->order, s->num_reads * 4);
+  e.lengths = (uint16_t *)up("rbin.lengths", s->lengths, s->num_reads * 2);
+  e.unaligned = (uint8_t *)up("rbin.unaligned", s->unaligned, s->unaligned_bytes);
+  e.noise_bytes = s->noise_bytes; e.num_noise = s->num_noise; e.unaligned_bytes = s->unaligned_bytes;
+  e.unaligned_len = s->unaligned_len; e.num_aligned = s->num_aligned; e.num_reads = s->num_reads;
+  return e;
+}
+
+void reblock(spring_b200_ctx *ctx, const spring_b200_streams *streams, const spring_b200_cp *cp, spring_b200_blocks *out) {
+  if (!cp || !out) throw ArgError("null argument");
+  if (cp->long_flag) throw ArgError("long mode has no reorder_compress_streams stage (spring.cpp:150)");
+  if (cp->num_reads_per_block <= 0) throw ArgError("cp.num_reads_per_block <= 0");
+  Ctx &c = ctx->c;
+  c.launches = 0;
+  EncodeDev e;
+  if (streams) e = upload_streams(c, streams);
+  else {
+    if (!ctx->have_enc) throw ArgError("no streams resident on the device (run spring_b200_reorder_encode* first, or pass host streams)");
+    e = ctx->last_enc;
+  }
+  if (e.num_reads != cp->num_reads) throw ArgError("streams hold a different number of reads than cp.num_reads");
+  rec(ctx, 6);
+  ReblockDev rb;
+  run_reblock(c, e, cp->paired_end != 0, cp->preserve_order != 0, (uint32_t)cp->num_reads_per_block, rb);
+  rec(ctx, 7);
+  memset(out, 0, sizeof(*out));
+  out->num_blocks = rb.num_blocks;
+  out->num_reads = e.num_reads;
+  static const char *names[RB_NSTREAMS] = {"rbo.flag", "rbo.pos", "rbo.noise", "rbo.noisepos", "rbo.rc", "rbo.unal", "rbo.len", "rbo.pos_pair", "rbo.rc_pair"};
+  for (int s = 0; s < RB_NSTREAMS; s++) {
+    uint8_t *h = c.pool.pin<uint8_t>(names[s], rb.size[s] + 1);
+    if (rb.size[s]) SB_CUDA(cudaMemcpyAsync(h, rb.data[s], rb.size[s], cudaMemcpyDeviceToHost, c.stream));
+    out->data[s] = h; out->size[s] = rb.size[s];
+  }
+  const size_t st = (size_t)rb.num_blocks + 1;
+  uint64_t *h_off = c.pool.pin<uint64_t>("rbo.off", RB_NSTREAMS * st);
+  SB_CUDA(cudaMemcpyAsync(h_off, rb.block_off, sizeof(uint64_t) * RB_NSTREAMS * st, cudaMemcpyDeviceToHost, c.stream));
+  for (int s = 0; s < RB_NSTREAMS; s++) out->off[s] = h_off + s * st;
+  if (rb.order) {
+    uint32_t *h_order = c.pool.pin<uint32_t>("rbo.order", e.num_reads + 1);
+    SB_CUDA(cudaMemcpyAsync(h_order, rb.order, sizeof(uint32_t) * e.num_reads, cudaMemcpyDeviceToHost, c.stream));
+    out->order = h_order;
+  }
+  SB_CUDA(cudaStreamSynchronize(c.stream));
+  ctx->stats.ms_reblock = ms(ctx, 6, 7);
+  ctx->stats.gpu_launches = c.launches;
+}
+
 }  // namespace
 
 extern "C" {
@@ -437,6 +504,61 @@ int spring_b200_fetch_reorder(spring_b200_ctx *ctx, spring_b200_reorder_out *out
   });
 }
 
+
+int spring_b200_pe_encode(spring_b200_ctx *ctx, const uint32_t *order, uint32_t num_reads, uint32_t *order_out) {
+  return guarded(ctx, [&] {
+    if (num_reads && (!order || !order_out)) throw ArgError("null pointer");
+    if (num_reads & 1) throw ArgError("pe_encode: odd number of reads");
+    if (!num_reads) return;
+    Ctx &c = ctx->c;
+    c.launches = 0;
+    for (uint32_t i = 0; i < num_reads; i++)
+      if (order[i] >= num_reads) throw ArgError("pe_encode: order is not a permutation of 0..num_reads-1");
+    uint32_t *d_in = c.pool.dev<uint32_t>("pe.in", num_reads), *d_out = c.pool.dev<uint32_t>("pe.out", num_reads);
+    SB_CUDA(cudaMemcpyAsync(d_in, order, sizeof(uint32_t) * num_reads, cudaMemcpyHostToDevice, c.stream));
+    run_pe_encode(c, d_in, num_reads, d_out);
+    SB_CUDA(cudaMemcpyAsync(order_out, d_out, sizeof(uint32_t) * num_reads, cudaMemcpyDeviceToHost, c.stream));
+    SB_CUDA(cudaStreamSynchronize(c.stream));
+    ctx->stats.gpu_launches = c.launches;
+  });
+}
+
+int spring_b200_reblock_streams(spring_b200_ctx *ctx, const spring_b200_streams *streams, const spring_b200_cp *cp,
+                                spring_b200_blocks *out) {
+  return guarded(ctx, [&] { reblock(ctx, streams, cp, out); });
+}
+
+int spring_b200_reblock_files(spring_b200_ctx *ctx, const char *temp_dir, const spring_b200_cp *cp) {
+  return guarded(ctx, [&] {
+    if (!temp_dir || !cp) throw ArgError("null argument");
+    const std::string dir(temp_dir);
+    // the encoder's stream files (reorder_compress_streams.cpp:91-172)
+    std::vector<uint8_t> f_pos = slurp(dir + "/read_pos.bin", true), f_noise = slurp(dir + "/read_noise.txt", true);
+    std::vector<uint8_t> f_np = slurp(dir + "/read_noisepos.bin", true), f_rev = slurp(dir + "/read_rev.txt", true);
+    std::vector<uint8_t> f_order = slurp(dir + "/read_order.bin", true), f_len = slurp(dir + "/read_lengths.bin", true);
+    std::vector<uint8_t> f_un = slurp(dir + "/read_unaligned.txt", true), f_cnt = slurp(dir + "/read_unaligned.txt.count", true);
+    if (f_cnt.size() != 8 || f_pos.size() != 8 * f_rev.size() || f_order.size() != 4 * (size_t)cp->num_reads ||
+        f_len.size() != 2 * (size_t)cp->num_reads)
+      throw IoError("reblock: stream files in " + dir + " are inconsistent with cp.num_reads");
+    spring_b200_streams s{};
+    s.pos = (const uint64_t *)f_pos.data(); s.noise = f_noise.data(); s.noise_bytes = f_noise.size();
+    s.noisepos = (const uint16_t *)f_np.data(); s.num_noise = f_np.size() / 2; s.rev = f_rev.data();
+    s.order = (const uint32_t *)f_order.data(); s.lengths = (const uint16_t *)f_len.data();
+    s.unaligned = f_un.data(); s.unaligned_bytes = f_un.size(); memcpy(&s.unaligned_len, f_cnt.data(), 8);
+    s.num_aligned = f_rev.size(); s.num_reads = cp->num_reads;
+    spring_b200_blocks b{};
+    reblock(ctx, &s, cp, &b);
+    static const char *files[SPRING_B200_NUM_BLOCK_STREAMS] = {"read_flag.txt", "read_pos.bin", "read_noise.txt", "read_noisepos.bin",
+        "read_rev.txt", "read_unaligned.txt", "read_lengths.bin", "read_pos_pair.bin", "read_rev_pair.txt"};
+    for (const char *f : {"read_noise.txt", "read_noisepos.bin", "read_rev.txt", "read_order.bin", "read_lengths.bin",
+                          "read_unaligned.txt", "read_pos.bin", "read_unaligned.txt.count"})
+      unlink((dir + "/" + f).c_str());  // :153, :174-181
+    const int ns = cp->paired_end ? SPRING_B200_NUM_BLOCK_STREAMS : SPRING_B200_NUM_BLOCK_STREAMS - 2;
+    for (uint32_t blk = 0; blk < b.num_blocks; blk++)
+      for (int st = 0; st < ns; st++)
+        spill(dir + "/" + files[st] + "." + std::to_string(blk), b.data[st] + b.off[st][blk], b.off[st][blk + 1] - b.off[st][blk]);
+  });
+}
 
 int spring_b200_bucket_reads(spring_b200_ctx *ctx, const uint64_t *reads, const uint16_t *lengths, uint32_t num_reads,
                              uint32_t max_readlen, uint32_t num_buckets, uint32_t *bucket) {

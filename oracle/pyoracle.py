@@ -16,20 +16,22 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "liboracle.so")
 REF_BIN = os.path.join(HERE, "_ref", "spring_ref")
 SPLICE_BIN = os.path.join(HERE, "_ref", "spring_b200_ref")
+SPLICE2_BIN = os.path.join(HERE, "_ref", "spring_b200_ref2")  # + pe_encode / reorder_compress_streams on the GPU
 REFERENCE_SRC = "/root/reference"
 
 
 def build(force: bool = False) -> None:
     """Compile the restatement; and, where the reference sources exist (this container, not the
     GPU box), the reference itself into oracle/_ref/."""
-    if force or not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < os.path.getmtime(os.path.join(HERE, "spring_oracle.c")):
+    srcs = [os.path.join(HERE, f) for f in ("spring_oracle.c", "reblock_oracle.c")]
+    if force or not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < max(os.path.getmtime(f) for f in srcs):
         subprocess.check_call(["make", "-s", "-C", HERE, "oracle"])
     if os.path.isdir(os.path.join(REFERENCE_SRC, "src")) and (force or not os.path.exists(REF_BIN)):
         subprocess.check_call(["make", "-s", "-j8", "-C", HERE, "ref"])
     # the reference host with our library spliced in at call_reorder / call_encoder (end-to-end parity)
     b200 = os.path.join(HERE, "..", "spring_b200", "libspring_b200.so")
     if os.path.isdir(os.path.join(REFERENCE_SRC, "src")) and os.path.exists(b200):
-        subprocess.check_call(["make", "-s", "-j8", "-C", HERE, "splice"])
+        subprocess.check_call(["make", "-s", "-j8", "-C", HERE, "splice", "splice2"])
 
 
 class _ByteVec(C.Structure):

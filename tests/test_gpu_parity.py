@@ -169,13 +169,17 @@ def _fastq_records(path):
     return [b"\n".join(lines[i:i + 4]) for i in range(0, len(lines) - 1, 4)]
 
 
-@pytest.mark.skipif(not (os.path.exists(po.SPLICE_BIN) and po.have_reference()), reason="oracle/_ref binaries not built")
+@pytest.mark.skipif(not (os.path.exists(po.SPLICE_BIN) and os.path.exists(po.SPLICE2_BIN) and po.have_reference()),
+                    reason="oracle/_ref binaries not built")
+@pytest.mark.parametrize("splice", ["hotpath", "hotpath+reblock"])
 @pytest.mark.parametrize("paired", [False, True])
-def test_end_to_end_archive_decodes_with_reference(paired, tmp_path):
-    """The reference's own `spring -c -r` host pipeline with call_reorder / call_encoder replaced by
-    libspring_b200.so (oracle/_ref/spring_b200_ref) writes an archive; the UNMODIFIED reference
-    (`spring -d`) must decode it to the input, as a multiset of records (pairs kept together) --
-    the check of util/test_script.sh:78-82."""
+@pytest.mark.parametrize("reorder", [True, False])
+def test_end_to_end_archive_decodes_with_reference(paired, reorder, splice, tmp_path):
+    """The reference's own `spring -c [-r]` host pipeline with call_reorder / call_encoder replaced by
+    libspring_b200.so (oracle/_ref/spring_b200_ref), and with pe_encode / reorder_compress_streams
+    replaced as well (oracle/_ref/spring_b200_ref2), writes an archive; the UNMODIFIED reference
+    (`spring -d`) must decode it to the input: with -r as a multiset of records (pairs kept together,
+    the check of util/test_script.sh:78-82), without -r byte for byte (util/test_script.sh:5-21)."""
     import subprocess
     from spring_b200 import synth
     rs = synth.generate(30000, 120, seed=31, paired=paired, n_frac=0.01, var_len=(60, 120), error_model="illumina")
@@ -183,18 +187,22 @@ def test_end_to_end_archive_decodes_with_reference(paired, tmp_path):
     synth.write_fastq(rs, f1, f2 if paired else None)
     arc = str(tmp_path / "out.spring")
     ins = [f1, f2] if paired else [f1]
-    r = subprocess.run([po.SPLICE_BIN, "-c", "-r", "-i", *ins, "-o", arc, "-t", "4", "-w", str(tmp_path)], capture_output=True, text=True)
+    binary = po.SPLICE_BIN if splice == "hotpath" else po.SPLICE2_BIN
+    r = subprocess.run([binary, "-c", *(["-r"] if reorder else []), "-i", *ins, "-o", arc, "-t", "4", "-w", str(tmp_path)],
+                       capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "were unmatched" in r.stdout
     out = str(tmp_path / "dec")
     r = subprocess.run([po.REF_BIN, "-d", "-i", arc, "-o", out, "-t", "3", "-w", str(tmp_path)], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     if not paired:
-        assert sorted(_fastq_records(out)) == sorted(_fastq_records(f1))
+        got, want = _fastq_records(out), _fastq_records(f1)
     else:
-        got = sorted(zip(_fastq_records(out + ".1"), _fastq_records(out + ".2")))
-        want = sorted(zip(_fastq_records(f1), _fastq_records(f2)))
-        assert got == want
+        got = list(zip(_fastq_records(out + ".1"), _fastq_records(out + ".2")))
+        want = list(zip(_fastq_records(f1), _fastq_records(f2)))
+    if reorder:
+        got, want = sorted(got), sorted(want)
+    assert got == want
 
 
 def test_bucket_kernel_matches_numpy_mirror(ctx):

@@ -325,6 +325,13 @@ class Context:
         order = _view(b.order, b.num_reads, np.uint32).copy() if b.order else None
         return BlocksResult(nb, data, off, order)
 
+    def reblock_streams_raw(self, cp: CP) -> Blocks:
+        """Device-resident streams of the last reorder_encode* call; no copies of the result (pointers
+        owned by the context)."""
+        b = Blocks()
+        self._check(self._lib.spring_b200_reblock_streams(self._h, None, C.byref(cp), C.byref(b)))
+        return b
+
     def reblock_files(self, temp_dir: str, cp: CP) -> None:
         self._check(self._lib.spring_b200_reblock_files(self._h, temp_dir.encode(), C.byref(cp)))
 

@@ -269,8 +269,14 @@ __device__ bool scan_bin(const ChainArgs &a, const DictView &d, uint32_t bs, uin
     const uint32_t t = off + (uint32_t)grp;
     uint32_t rid = 0;
     bool live = false;
+    uint64_t cw = 0;
+    int len = 0;
     if (act && t < bc) {
       rid = bc <= 3 ? (t == 0 ? r0 : t == 1 ? r1 : r2) : __ldg(d.bins + bs + t);
+      // row word and length are fetched before the claim bit is known: one memory round trip per
+      // pass instead of two (a claimed candidate costs a wasted sector, not a serialised latency)
+      cw = __ldg(a.reads + (size_t)rid * W + wig);
+      len = __ldg(a.lens + rid);
       live = !is_claimed(a.claimed, rid);
     }
     const unsigned lm = __ballot_sync(FULL, live) & leaders;  // one bit per live candidate, in scan order
@@ -286,12 +292,10 @@ __device__ bool scan_bin(const ChainArgs &a, const DictView &d, uint32_t bs, uin
     const bool ev = live && rank < kMaxSearch;
     int h = 0;
     if (ev) {
-      const int len = __ldg(a.lens + rid);
       int lo, hi;
       if (!rev) { lo = 0; hi = 2 * min(ref_len - s, len); }
       else { lo = 2 * s; hi = 2 * min(ref_len + s, len); }
-      const uint64_t m = range_mask(wig, lo, hi);
-      if (m) h = __popcll((rw ^ __ldg(a.reads + (size_t)rid * W + wig)) & m);
+      h = __popcll((rw ^ cw) & range_mask(wig, lo, hi));
     }
     for (int o = 1; o < W; o <<= 1) {  // sum over the group's W lanes, into its leader
       const int t2 = __shfl_down_sync(FULL, h, o);
@@ -547,14 +551,19 @@ __global__ void __launch_bounds__(WPB * 32, MINB) k_chains(ChainArgs a) {
           iter_started = 1;
         }
         bool found = false;
-        uint32_t k = 0;
-        int shift = 0, prev_rev = 0;
+        uint32_t k = 0, pre_sidx = 0xFFFFFFFFu;
+        uint64_t pre_word = 0;
+        int shift = 0, prev_rev = 0, pre_len = 0;
         if (!stop_searching) {
           int b = 0, S = 0;
           while (S < a.maxshift) {
             if (chain_search(a, ref, revref, ref_len, lane, grp, wig, b, S, k, shift, prev_rev, c_issued, c_seq, c_cmp, c_slot)) {
+              // the claim's round trip overlaps the loads the update will need (row, length, slot indices)
               unsigned old = 0;
               if (lane == 0) old = atomicOr(a.claimed + (k >> 5), 1u << (k & 31));
+              if (lane < W) pre_word = __ldg(a.reads + (size_t)k * W + lane);
+              pre_len = __ldg(a.lens + k);
+              if (lane < kNumDict) pre_sidx = __ldg(a.dict[lane].slot_of_read + k);
               old = __shfl_sync(FULL, old, 0);
               if (!((old >> (k & 31)) & 1u)) { found = true; break; }
               c_lost++;  // another chain took it between the check and the claim: search this batch again
@@ -565,12 +574,10 @@ __global__ void __launch_bounds__(WPB * 32, MINB) k_chains(ChainArgs a) {
           }
         }
         if (found) {
-          if (lane < kNumDict) {
-            const uint32_t sidx = __ldg(a.dict[lane].slot_of_read + k);
-            if (sidx != 0xFFFFFFFFu) atomicSub(&a.dict[lane].slots[sidx].live, 1u);
-          }
-          stage_read(k);
-          const int len = __ldg(a.lens + k), old = ref_len;
+          if (lane < kNumDict && pre_sidx != 0xFFFFFFFFu) atomicSub(&a.dict[lane].slots[pre_sidx].live, 1u);
+          if (lane < W) curw[lane] = pre_word;
+          __syncwarp();
+          const int len = pre_len, old = ref_len;
           int delta, cs, nl, fold = 0;
           if (!prev_rev) { delta = shift; cs = 0; nl = max(old - shift, len); }
           else if (len - shift >= old) { fold = len - shift - old; delta = -fold; cs = 0; nl = len; }

@@ -50,9 +50,10 @@ def exchange_by_bucket(reads: torch.Tensor, lens: torch.Tensor, max_readlen: int
         if key not in _default_ctx:
             _default_ctx[key] = capi.Context(key, torch.cuda.current_stream().cuda_stream)
         bucket_fn = gpu_bucket_fn(_default_ctx[key], max_readlen)
-    bucket = bucket_fn(reads, lens, world).long()
-    order = torch.argsort(bucket, stable=True)
-    send_counts = torch.bincount(bucket, minlength=world)
+    bucket = bucket_fn(reads, lens, world)
+    # stable sort of one-byte keys (a single radix pass) instead of an int64 argsort: rank order = input order
+    order = torch.argsort(bucket.to(torch.uint8), stable=True)
+    send_counts = torch.bincount(bucket.long(), minlength=world)
     recv_counts = torch.empty_like(send_counts)
     dist.all_to_all_single(recv_counts, send_counts, group=group)
     sc, rc = send_counts.tolist(), recv_counts.tolist()

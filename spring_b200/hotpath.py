@@ -59,3 +59,31 @@ def call_encoder(temp_dir: str, cp, bsc_compress=None) -> None:
         if bsc_compress is not None:
             bsc_compress(base, base + ".bsc")
             os.remove(base)
+
+
+def pe_encode(temp_dir: str, cp) -> None:
+    """pe_encode (src/pe_encode.cpp:24-84, called at src/spring.cpp:193).  Nothing is left to do on the
+    host: it only rewrites read_order.bin for reorder_compress_streams, and the GPU re-blocking applies
+    the same mapping on the device (same contract as csrc/host/reorder_compress_streams_b200.cpp)."""
+    _as_cp(cp)
+
+
+def reorder_compress_streams(temp_dir: str, cp, device: int = 0, bsc_compress=None) -> None:
+    """reorder_compress_streams (src/reorder_compress_streams.cpp:31-444): the GPU writes the raw per-block
+    streams <name>.<b>; bsc_compress(infile, outfile), when given, is called on every one of them and the
+    raw file removed, as :363-428 does."""
+    c = _as_cp(cp)
+    try:
+        _context(device).reblock_files(temp_dir, c)
+    except capi.SpringB200Error as e:
+        raise RuntimeError(str(e)) from e
+    if bsc_compress is None:
+        return
+    files = ("read_flag.txt", "read_pos.bin", "read_noise.txt", "read_noisepos.bin", "read_rev.txt", "read_unaligned.txt",
+             "read_lengths.bin", "read_pos_pair.bin", "read_rev_pair.txt")
+    units = c.num_reads // 2 if c.paired_end else c.num_reads
+    for b in range((units + c.num_reads_per_block - 1) // c.num_reads_per_block):
+        for f in files[: 9 if c.paired_end else 7]:
+            raw = os.path.join(temp_dir, f"{f}.{b}")
+            bsc_compress(raw, raw + ".bsc")
+            os.remove(raw)

@@ -203,6 +203,33 @@ int spring_b200_reblock_streams(spring_b200_ctx *ctx, const spring_b200_streams 
  * the raw file (:363-428).  See INTEGRATION.md. */
 int spring_b200_reblock_files(spring_b200_ctx *ctx, const char *temp_dir, const spring_b200_cp *cp);
 
+/* ---- the stage before the dictionaries: preprocess's read path ------------------ */
+/* What preprocess does to the sequence lines of the FASTQ input (src/preprocess.cpp:196-207, :293-304,
+ * :364-378; record packers src/util.cpp:269-294, :322-348): reads that contain 'N' go to input_N.dna
+ * (4 bits/base) with their original index in read_order_N.bin, all others are packed 2 bits/base in
+ * input order -- here straight into the in-memory layout of spring_b200_input (one bitset row per clean
+ * read), so FASTQ bases can go to the hot path without the .dna files.
+ *   bases   : HOST, the reads' sequence lines concatenated without separators, file 1 then file 2
+ *   offsets : HOST, [num_reads + 1], start of read i in bases
+ * Characters other than A, C, G, T, N are refused (the reference's tables are undefined for them);
+ * a read longer than 511 fails with the reference's message (preprocess.cpp:199-206).
+ * out->reads / out->lengths are DEVICE pointers when keep_on_device != 0 (feed them to
+ * spring_b200_reorder_encode_device), HOST pointers otherwise; n_records / order_n are always HOST. */
+typedef struct spring_b200_packed_reads {
+  const uint64_t *reads;      /* [num_clean * W], W = (2*max_readlen-1)/64+1 */
+  const uint16_t *lengths;    /* [num_clean] */
+  uint32_t num_clean;         /* cp.num_reads_clean[0] + cp.num_reads_clean[1] */
+  uint32_t num_clean_file1;   /* cp.num_reads_clean[0] */
+  uint32_t max_readlen;       /* cp.max_readlen */
+  const uint8_t *n_records;   /* contents of input_N.dna */
+  uint64_t n_record_bytes;
+  const uint32_t *order_n;    /* contents of read_order_N.bin */
+  uint32_t num_n;
+  uint32_t num_reads;
+} spring_b200_packed_reads;
+int spring_b200_pack_reads(spring_b200_ctx *ctx, const uint8_t *bases, const uint64_t *offsets, uint32_t num_reads,
+                           uint32_t num_reads_file1, int keep_on_device, spring_b200_packed_reads *out);
+
 /* ---- multi-GPU partitioning ------------------------------------------------------------------ */
 /* DEVICE pointers.  bucket[i] = hash(strand-canonical 16-mer minimizer of read i) mod num_buckets:
  * the owner GPU of read i.  No reference counterpart (the reference is single-process,

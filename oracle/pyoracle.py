@@ -336,3 +336,63 @@ def run_reference_reblock(temp_dir: str, paired_end: bool, num_blocks: int, num_
         data[name] = np.concatenate(parts) if parts else np.zeros(0, np.uint8)
         off[name] = np.array(o, np.uint64)
     return BlockStreams(num_blocks, data, off)
+
+
+# ---------------------------------------------------------------------------------------------
+# preprocess's read path: N split + record packing, as file images
+# ---------------------------------------------------------------------------------------------
+def pack_reads(seqs: list, num_file1: int | None = None) -> dict:
+    """Plain-Python restatement of what preprocess does with the sequence lines (src/preprocess.cpp:196-207,
+    :293-304, :364-378) and of the two record packers (src/util.cpp:269-294 write_dna_in_bits,
+    :322-348 write_dnaN_in_bits).  Returns the byte images of input_clean_1.dna, input_clean_2.dna,
+    input_N.dna, read_order_N.bin and the cp fields preprocess sets (:398-403)."""
+    n = len(seqs)
+    n1 = n if num_file1 is None else num_file1
+    d2 = {ord("A"): 0, ord("C"): 2, ord("G"): 1, ord("T"): 3}
+    d4 = dict(d2); d4[ord("N")] = 4
+    clean = [bytearray(), bytearray()]
+    rec_n, order_n = bytearray(), []
+    num_clean = [0, 0]
+    max_len = 0
+    for i, s in enumerate(seqs):
+        j = 0 if i < n1 else 1
+        L = len(s)
+        if L > 511:
+            raise ValueError("Too long read length (please try --long/-l flag).")   # preprocess.cpp:199-206
+        max_len = max(max_len, L)
+        if b"N" not in s:                                                            # :207-209, :296-298
+            out = clean[j]
+            out += L.to_bytes(2, "little")
+            for k in range(0, L, 4):
+                v = 0
+                for t, ch in enumerate(s[k:k + 4]):
+                    v |= d2[ch] << (2 * t)
+                out.append(v)
+            num_clean[j] += 1
+        else:                                                                        # :299-303
+            order_n.append(i)
+            rec_n += L.to_bytes(2, "little")
+            for k in range(0, L, 2):
+                v = 0
+                for t, ch in enumerate(s[k:k + 2]):
+                    v |= d4[ch] << (4 * t)
+                rec_n.append(v)
+    return dict(clean_1=bytes(clean[0]), clean_2=bytes(clean[1]), n_records=bytes(rec_n),
+                order_n=np.array(order_n, dtype=np.uint32), num_reads_clean=tuple(num_clean), max_readlen=max_len, num_reads=n)
+
+
+def run_reference_preprocess(temp_dir: str, fastq1: str, fastq2: str | None = None, num_thr: int = 2) -> dict:
+    """spring::preprocess of the unmodified reference (-r --no-quality --no-ids) into temp_dir; returns the
+    same dict as pack_reads, read back from the files it wrote."""
+    ins = [fastq1] + ([fastq2] if fastq2 else [])
+    r = subprocess.run([REF_BIN, "--preprocess", "-i", *ins, "--temp", temp_dir, "-r", "--no-quality", "--no-ids", "-t", str(num_thr)],
+                       capture_output=True, text=True, cwd=temp_dir)
+    if r.returncode != 0:
+        raise RuntimeError(f"spring_ref --preprocess failed:\n{r.stdout}\n{r.stderr}")
+    rd = lambda f: open(os.path.join(temp_dir, f), "rb").read() if os.path.exists(os.path.join(temp_dir, f)) else b""
+    import struct
+    cp = rd("cp_in.bin")
+    num_reads, c0, c1, max_readlen = struct.unpack_from("<IIII", cp, 28)
+    return dict(clean_1=rd("input_clean_1.dna"), clean_2=rd("input_clean_2.dna"), n_records=rd("input_N.dna"),
+                order_n=np.frombuffer(rd("read_order_N.bin"), dtype=np.uint32), num_reads_clean=(c0, c1), max_readlen=max_readlen,
+                num_reads=num_reads)

@@ -20,7 +20,7 @@ EXPORTS = [
     "spring_b200_reorder_encode_device", "spring_b200_fetch_streams", "spring_b200_build_dictionary",
     "spring_b200_reorder", "spring_b200_reorder_encode_files", "spring_b200_write_streams",
     "spring_b200_bucket_reads", "spring_b200_set_schedule", "spring_b200_fetch_reorder", "spring_b200_set_stream",
-    "spring_b200_pe_encode", "spring_b200_reblock_streams", "spring_b200_reblock_files",
+    "spring_b200_pe_encode", "spring_b200_reblock_streams", "spring_b200_reblock_files", "spring_b200_pack_reads",
 ]
 
 
@@ -69,6 +69,12 @@ class Blocks(C.Structure):
                 ("off", C.c_void_p * NUM_BLOCK_STREAMS), ("order", C.c_void_p), ("num_reads", C.c_uint64)]
 
 
+class PackedReads(C.Structure):
+    _fields_ = [("reads", C.c_void_p), ("lengths", C.c_void_p), ("num_clean", C.c_uint32), ("num_clean_file1", C.c_uint32),
+                ("max_readlen", C.c_uint32), ("n_records", C.c_void_p), ("n_record_bytes", C.c_uint64), ("order_n", C.c_void_p),
+                ("num_n", C.c_uint32), ("num_reads", C.c_uint32)]
+
+
 class Stats(C.Structure):
     _fields_ = [("num_chains", C.c_uint32), ("unmatched", C.c_uint32), ("rounds", C.c_uint64),
                 ("lost_proposals", C.c_uint64), ("probes_issued", C.c_uint64), ("probes_seq", C.c_uint64),
@@ -110,6 +116,8 @@ def load():
         lib.spring_b200_pe_encode.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
         lib.spring_b200_reblock_streams.argtypes = [C.c_void_p, C.POINTER(Streams), C.POINTER(CP), C.POINTER(Blocks)]
         lib.spring_b200_reblock_files.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(CP)]
+        lib.spring_b200_pack_reads.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int,
+                                               C.POINTER(PackedReads)]
         _lib = lib
     return _lib
 
@@ -292,6 +300,30 @@ class Context:
         return (_view(o.order, o.num, np.uint32).copy(), _view(o.flag, o.num, np.uint8).copy(),
                 _view(o.pos, o.num, np.int64).copy(), _view(o.rev, o.num, np.uint8).copy(),
                 _view(o.singleton_order, o.num_singletons, np.uint32).copy())
+
+    # ---- the stage before the dictionaries -----------------------------------
+    def pack_reads(self, bases: np.ndarray, offsets: np.ndarray, num_reads_file1: int | None = None, keep_on_device: bool = False):
+        """preprocess's read path: N split + 2-bit / 4-bit packing.  bases uint8 (sequence lines
+        concatenated), offsets uint64[n + 1].  Returns a dict with the fields of spring_b200_input
+        (numpy arrays; `reads` / `lengths` are raw device pointers when keep_on_device)."""
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        n = len(offsets) - 1
+        p = PackedReads()
+        self._keep = [bases, offsets]
+        self._check(self._lib.spring_b200_pack_reads(self._h, bases.ctypes.data if bases.size else None, offsets.ctypes.data, n,
+                                                     n if num_reads_file1 is None else num_reads_file1, 1 if keep_on_device else 0,
+                                                     C.byref(p)))
+        w = (2 * max(p.max_readlen, 1) - 1) // 64 + 1
+        res = dict(num_clean=p.num_clean, num_clean_file1=p.num_clean_file1, max_readlen=p.max_readlen, num_n=p.num_n,
+                   num_reads=p.num_reads, n_records=_view(p.n_records, p.n_record_bytes, np.uint8).tobytes(),
+                   order_n=_view(p.order_n, p.num_n, np.uint32).copy())
+        if keep_on_device:
+            res["reads_ptr"], res["lengths_ptr"] = p.reads, p.lengths
+        else:
+            res["packed"] = _view(p.reads, p.num_clean * w, np.uint64).copy().reshape(p.num_clean, w)
+            res["lengths"] = _view(p.lengths, p.num_clean, np.uint16).copy()
+        return res
 
     # ---- the stages after the encoder (SURVEY 8f) ----------------------------------------------
     def pe_encode(self, order: np.ndarray) -> np.ndarray:

@@ -81,6 +81,16 @@ void run_pe_encode(Ctx &c, const uint32_t *order, uint32_t n, uint32_t *slot);
 // reorder_compress_streams.cpp:83-361 on the device-resident encoder streams `e`
 void run_reblock(Ctx &c, const EncodeDev &e, bool paired, bool preserve, uint32_t block, ReblockDev &out);
 
+// ---- pack.cu : preprocess's read path, N split + 2-bit / 4-bit packing -----------
+struct PackDev {
+  uint64_t *reads = nullptr; uint16_t *lengths = nullptr;  // clean reads, input order, [num_clean][W] (device)
+  uint8_t *n_records = nullptr; uint64_t n_record_bytes = 0; uint32_t *order_n = nullptr;  // input_N.dna / read_order_N.bin (device)
+  uint32_t num_reads = 0, num_clean = 0, num_clean_file1 = 0, num_n = 0, max_readlen = 0;
+  int W = 1;
+};
+// d_bases: the reads' sequence lines concatenated, file 1 then file 2; d_offsets[n + 1]: start of read i
+void run_pack_reads(Ctx &c, const uint8_t *d_bases, const unsigned long long *d_offsets, uint32_t n, uint32_t n_file1, PackDev &out);
+
 // ---- bucket.cu : multi-GPU partitioning key --------------------------------------------------
 void bucket_reads(Ctx &c, const uint64_t *reads, const uint16_t *lens, uint32_t n, int L, uint32_t num_buckets, uint32_t *bucket);
 

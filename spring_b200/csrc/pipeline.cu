@@ -505,6 +505,45 @@ int spring_b200_fetch_reorder(spring_b200_ctx *ctx, spring_b200_reorder_out *out
 }
 
 
+int spring_b200_pack_reads(spring_b200_ctx *ctx, const uint8_t *bases, const uint64_t *offsets, uint32_t num_reads,
+                           uint32_t num_reads_file1, int keep_on_device, spring_b200_packed_reads *out) {
+  return guarded(ctx, [&] {
+    if (!out || !offsets || (num_reads && !bases && offsets[num_reads])) throw ArgError("null pointer");
+    if (num_reads_file1 > num_reads) throw ArgError("num_reads_file1 > num_reads");
+    if (num_reads >= 0x7FFFFFF0u) throw ArgError("too many reads for one GPU shard (>= 2^31)");
+    Ctx &c = ctx->c;
+    c.launches = 0;
+    const uint64_t nbytes = offsets[num_reads];
+    uint8_t *d_bases = c.pool.dev<uint8_t>("pk.bases", nbytes + 1);
+    unsigned long long *d_off = c.pool.dev<unsigned long long>("pk.offsets", (size_t)num_reads + 1);
+    if (nbytes) SB_CUDA(cudaMemcpyAsync(d_bases, bases, nbytes, cudaMemcpyHostToDevice, c.stream));
+    SB_CUDA(cudaMemcpyAsync(d_off, offsets, sizeof(uint64_t) * ((size_t)num_reads + 1), cudaMemcpyHostToDevice, c.stream));
+    PackDev pk;
+    try { run_pack_reads(c, d_bases, d_off, num_reads, num_reads_file1, pk); }
+    catch (const LimitError &e) { throw ArgError(e.what()); }  // bad input, not an internal limit
+    memset(out, 0, sizeof(*out));
+    out->num_clean = pk.num_clean; out->num_clean_file1 = pk.num_clean_file1; out->max_readlen = pk.max_readlen;
+    out->n_record_bytes = pk.n_record_bytes; out->num_n = pk.num_n; out->num_reads = pk.num_reads;
+    uint8_t *h_nrec = c.pool.pin<uint8_t>("pk.h_nrec", pk.n_record_bytes + 1);
+    uint32_t *h_on = c.pool.pin<uint32_t>("pk.h_order_n", (size_t)pk.num_n + 1);
+    if (pk.n_record_bytes) SB_CUDA(cudaMemcpyAsync(h_nrec, pk.n_records, pk.n_record_bytes, cudaMemcpyDeviceToHost, c.stream));
+    if (pk.num_n) SB_CUDA(cudaMemcpyAsync(h_on, pk.order_n, sizeof(uint32_t) * pk.num_n, cudaMemcpyDeviceToHost, c.stream));
+    out->n_records = h_nrec; out->order_n = h_on;
+    if (keep_on_device) { out->reads = pk.reads; out->lengths = pk.lengths; }
+    else {
+      uint64_t *h_reads = c.pool.pin<uint64_t>("pk.h_reads", (size_t)pk.num_clean * pk.W + 1);
+      uint16_t *h_len = c.pool.pin<uint16_t>("pk.h_len", (size_t)pk.num_clean + 1);
+      if (pk.num_clean) {
+        SB_CUDA(cudaMemcpyAsync(h_reads, pk.reads, sizeof(uint64_t) * (size_t)pk.num_clean * pk.W, cudaMemcpyDeviceToHost, c.stream));
+        SB_CUDA(cudaMemcpyAsync(h_len, pk.lengths, sizeof(uint16_t) * pk.num_clean, cudaMemcpyDeviceToHost, c.stream));
+      }
+      out->reads = h_reads; out->lengths = h_len;
+    }
+    SB_CUDA(cudaStreamSynchronize(c.stream));
+    ctx->stats.gpu_launches = c.launches;
+  });
+}
+
 int spring_b200_pe_encode(spring_b200_ctx *ctx, const uint32_t *order, uint32_t num_reads, uint32_t *order_out) {
   return guarded(ctx, [&] {
     if (num_reads && (!order || !order_out)) throw ArgError("null pointer");

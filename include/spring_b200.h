@@ -207,7 +207,7 @@ int spring_b200_reblock_files(spring_b200_ctx *ctx, const char *temp_dir, const 
 /* What preprocess does to the sequence lines of the FASTQ input (src/preprocess.cpp:196-207, :293-304,
  * :364-378; record packers src/util.cpp:269-294, :322-348): reads that contain 'N' go to input_N.dna
  * (4 bits/base) with their original index in read_order_N.bin, all others are packed 2 bits/base in
- * input order -- here straight into the in-memory layout of spring_b200_input (one bitset row per clean
+ * input order -- here straight into the in-memory layout that struct spring_b200_input describes (one bitset row per clean
  * read), so FASTQ bases can go to the hot path without the .dna files.
  *   bases   : HOST, the reads' sequence lines concatenated without separators, file 1 then file 2
  *   offsets : HOST, [num_reads + 1], start of read i in bases

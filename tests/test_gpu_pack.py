@@ -22,6 +22,8 @@ def flat(seqs):
 
 def file_image(packed, lengths):
     """write_dna_in_bits records of packed rows (util.cpp:269-294)."""
+    if len(lengths) == 0:
+        return b""
     with tempfile.TemporaryDirectory() as d:
         p = os.path.join(d, "x.dna")
         dnaio.write_dna_file(p, packed, lengths)

@@ -155,7 +155,7 @@ __global__ void k_abs_pos(const uint32_t *__restrict__ cidx1, const int64_t *__r
 }
 
 // ---- consensus (buildcontig, encoder.cpp:32-74) ---------------------------------------------------
-constexpr int kTile = 256, kStage = 64;
+constexpr int kTile = 256, kStage = 128;
 
 // Which sorted reads can touch which 256-column tile, without a binary search per tile (46 dependent
 // HBM loads per block used to be most of the consensus kernel's time): sorted_ap is ascending, so
@@ -174,36 +174,87 @@ __global__ void k_tile_ranges(const uint64_t *__restrict__ sorted_ap, uint32_t m
   for (uint64_t t = hi_prev; t <= hi_now && t <= num_tiles; t++) tile_hi[t] = r;
   for (uint64_t t = lo_prev; t <= lo_now && t <= num_tiles; t++) tile_lo[t] = r;
 }
-__global__ void __launch_bounds__(kTile) k_consensus(const uint64_t *__restrict__ reads, const uint16_t *__restrict__ lens,
-                                                     const uint32_t *__restrict__ order, const uint8_t *__restrict__ rev,
-                                                     const uint64_t *__restrict__ sorted_ap, const uint32_t *__restrict__ perm,
+
+// The contig reads in sorted order, already oriented as they sit in their contig (writetofile applies the
+// reverse complement to 'r' reads, reorder.h:674-677): one gather of the 8W-byte rows, after which the
+// consensus and noise kernels read contiguous rows (the reference's temp.dna.<t>, kept in HBM).
+__global__ void k_gather_sorted(const uint64_t *__restrict__ reads, const uint16_t *__restrict__ lens,
+                                const uint32_t *__restrict__ order, const uint8_t *__restrict__ rev,
+                                const uint32_t *__restrict__ perm, uint32_t m, int W, uint64_t *srt_words, uint16_t *srt_len,
+                                uint32_t *srt_rid, uint8_t *srt_rev) {
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t i = (uint32_t)(t / W);
+  if (i >= m) return;
+  const int w = (int)(t - (uint64_t)i * W);
+  const uint32_t p = perm[i], rid = order[p];
+  const int len = lens[rid];
+  const uint8_t rc = rev[p];
+  srt_words[t] = oriented_word(reads + (size_t)rid * W, W, len, rc == 'r', w);
+  if (w == 0) { srt_len[i] = (uint16_t)len; srt_rid[i] = rid; srt_rev[i] = rc; }
+}
+
+// ---- TMA (bulk async copy) + mbarrier, sm_90+ PTX ------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\tWAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}"
+      ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// global -> shared bulk copy (one TMA request, completion counted in bytes on the mbarrier);
+// dst, src and bytes must be multiples of 16
+__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// One block = one 256-column tile.  The reads that can cover it are rows [r_lo, r_hi) of the sorted,
+// oriented array: contiguous in HBM, staged kStage rows at a time by ONE bulk async copy (TMA) issued by
+// thread 0 and awaited on an mbarrier, while the other threads fetch the rows' positions and lengths.
+// (8W-byte rows start on 8-byte boundaries: the copy starts at the 16-byte boundary below the first row
+// and s_head remembers the slack.)
+__global__ void __launch_bounds__(kTile) k_consensus(const uint64_t *__restrict__ srt_words, const uint16_t *__restrict__ srt_len,
+                                                     const uint64_t *__restrict__ sorted_ap,
                                                      const uint32_t *__restrict__ tile_lo, const uint32_t *__restrict__ tile_hi,
-                                                     uint32_t m, int W, int L, uint64_t seq_len, uint64_t *cons2) {
-  __shared__ uint64_t s_words[kStage * kMaxWords];  // staged reads, already oriented as in the contig
-  __shared__ int s_rel[kStage];                     // read start relative to the tile's first column
-  __shared__ uint32_t s_rid[kStage];
+                                                     int W, int L, uint64_t seq_len, uint64_t *cons2) {
+  __shared__ __align__(16) uint64_t s_buf[kStage * kMaxWords + 2];  // staged rows, stride W, behind up to 8 slack bytes
+  __shared__ int s_rel[kStage];                                     // read start relative to the tile's first column
   __shared__ uint16_t s_len[kStage];
-  __shared__ uint8_t s_rev[kStage];
+  __shared__ __align__(8) uint64_t s_bar;
   const uint64_t x0 = (uint64_t)blockIdx.x * kTile;
   const uint64_t x = x0 + threadIdx.x;
   const int xr = (int)threadIdx.x;
   const uint32_t r_lo = tile_lo[blockIdx.x], r_hi = tile_hi[blockIdx.x + 1];  // reads with ap + L > x0 and ap < x0 + kTile
-  uint32_t cA = 0, cC = 0, cG = 0, cT = 0;
+  if (threadIdx.x == 0) mbar_init(&s_bar, 1);
+  __syncthreads();
+  uint32_t cA = 0, cC = 0, cG = 0, cT = 0, phase = 0;
   for (uint32_t base = r_lo; base < r_hi; base += kStage) {
     const uint32_t cnt = min((uint32_t)kStage, r_hi - base);
+    const uintptr_t g0 = reinterpret_cast<uintptr_t>(srt_words + (size_t)base * W);
+    const uint32_t head = (uint32_t)(g0 & 15u);  // 0 or 8
+    if (threadIdx.x == 0) {
+      const uint32_t bytes = (head + cnt * (uint32_t)W * 8u + 15u) & ~15u;
+      mbar_expect_tx(&s_bar, bytes);
+      tma_bulk_g2s(s_buf, reinterpret_cast<const void *>(g0 - head), bytes, &s_bar);
+    }
     if (threadIdx.x < cnt) {
-      const uint32_t r = base + threadIdx.x, p = perm[r], rid = order[p];
+      const uint32_t r = base + threadIdx.x;
       s_rel[threadIdx.x] = (int)((long long)sorted_ap[r] - (long long)x0);
-      s_rid[threadIdx.x] = rid;
-      s_len[threadIdx.x] = lens[rid];
-      s_rev[threadIdx.x] = rev[p] == 'r';
+      s_len[threadIdx.x] = srt_len[r];
     }
     __syncthreads();
-    for (uint32_t t = threadIdx.x; t < cnt * (uint32_t)W; t += kTile) {
-      const uint32_t q = t / W, w = t - q * W;
-      s_words[q * kMaxWords + w] = oriented_word(reads + (size_t)s_rid[q] * W, W, s_len[q], s_rev[q] != 0, (int)w);
-    }
-    __syncthreads();
+    mbar_wait(&s_bar, phase);
+    phase ^= 1u;
+    const uint64_t *s_words = s_buf + (head >> 3);
     if (x < seq_len) {
       // staged reads are sorted by position: only those starting in (x - L, x] can cover column x
       uint32_t q = 0, qh = cnt;
@@ -212,11 +263,11 @@ __global__ void __launch_bounds__(kTile) k_consensus(const uint64_t *__restrict_
       uint32_t acc = 0;  // four u8 counters {A,G,C,T}; at most kStage (< 256) additions per stage
       for (; q < cnt && s_rel[q] <= xr; q++) {
         const unsigned off = (unsigned)(xr - s_rel[q]);
-        if (off < (unsigned)s_len[q]) acc += 1u << (8 * base_code(s_words + q * kMaxWords, (int)off));
+        if (off < (unsigned)s_len[q]) acc += 1u << (8 * base_code(s_words + q * W, (int)off));
       }
       cA += acc & 0xFFu; cG += (acc >> 8) & 0xFFu; cC += (acc >> 16) & 0xFFu; cT += acc >> 24;
     }
-    __syncthreads();
+    __syncthreads();  // every thread is done with the buffer before the next copy lands in it
   }
   uint32_t code = 0;
   if (x < seq_len) {  // first strict maximum in A,C,G,T order (encoder.cpp:62-71); uncovered -> 'A'
@@ -330,17 +381,17 @@ __global__ void k_single_keys2(const uint32_t *__restrict__ a_idx, const uint32_
 struct FinalArrays {
   uint64_t *pos; uint32_t *order; uint16_t *len; uint8_t *rev; uint32_t *src; uint8_t *kind;
 };
-__global__ void k_place_originals(const uint64_t *__restrict__ sorted_ap, const uint32_t *__restrict__ perm, uint32_t m,
-                                  const uint64_t *__restrict__ skey, uint32_t k, const uint32_t *__restrict__ order,
-                                  const uint8_t *__restrict__ rev, const uint16_t *__restrict__ lens,
-                                  const uint32_t *__restrict__ order_n, uint32_t nn, FinalArrays f) {
+// kind 0: src = index into the sorted, oriented rows (k_gather_sorted); kind 1: src = pool index
+__global__ void k_place_originals(const uint64_t *__restrict__ sorted_ap, uint32_t m, const uint64_t *__restrict__ skey, uint32_t k,
+                                  const uint32_t *__restrict__ srt_rid, const uint8_t *__restrict__ srt_rev,
+                                  const uint16_t *__restrict__ srt_len, const uint32_t *__restrict__ order_n, uint32_t nn,
+                                  FinalArrays f) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= m) return;
   const uint64_t ap = sorted_ap[i];
   const uint32_t q = i + lower_bound_u64(skey, k, ap << 12);
-  const uint32_t p = perm[i], rid = order[p];
-  f.pos[q] = ap; f.order[q] = corrected_order(rid, order_n, nn); f.len[q] = lens[rid]; f.rev[q] = rev[p];
-  f.src[q] = rid; f.kind[q] = 0;
+  f.pos[q] = ap; f.order[q] = corrected_order(srt_rid[i], order_n, nn); f.len[q] = srt_len[i]; f.rev[q] = srt_rev[i];
+  f.src[q] = i; f.kind[q] = 0;
 }
 __global__ void k_place_singles(const uint64_t *__restrict__ skey, const uint32_t *__restrict__ ent,
                                 const uint32_t *__restrict__ a_idx, uint32_t k, const uint64_t *__restrict__ sorted_ap,
@@ -364,7 +415,7 @@ __constant__ char kEncNoise[4][4] = {
     /* ref T */ {'2', '0', '1', 0}};
 
 struct NoiseArgs {
-  const uint64_t *reads; const uint64_t *pool_codes; const uint64_t *pool_nflag; int W;
+  const uint64_t *srt_words; const uint64_t *pool_codes; const uint64_t *pool_nflag; int W;
   const uint64_t *cons2; FinalArrays f; uint32_t m;
   uint32_t *nmis;                  // pass 1 out / pass 2 in (exclusive scan)
   const uint64_t *noise_off;       // exclusive scan of nmis
@@ -377,9 +428,9 @@ __global__ void k_noise(NoiseArgs a) {
   const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= a.m) return;
   const int len = a.f.len[q], W = a.W;
-  const bool rev = a.f.rev[q] == 'r';
   const bool pool = a.f.kind[q] != 0;
-  const uint64_t *r = (pool ? a.pool_codes : a.reads) + (size_t)a.f.src[q] * W;
+  const bool rev = pool && a.f.rev[q] == 'r';  // contig reads are staged already oriented, pool reads are not
+  const uint64_t *r = (pool ? a.pool_codes : a.srt_words) + (size_t)a.f.src[q] * W;
   const uint64_t *nf = pool ? a.pool_nflag + (size_t)a.f.src[q] * W : nullptr;
   const uint64_t pos = a.f.pos[q];
   uint32_t total = 0;
@@ -543,10 +594,15 @@ void run_encode(Ctx &c, const uint64_t *reads, const uint16_t *lens, uint32_t n,
   const uint32_t num_tiles = grid_for(seq_len, kTile);
   uint32_t *tile_lo = c.pool.dev<uint32_t>("en.tile_lo", (size_t)num_tiles + 2), *tile_hi = c.pool.dev<uint32_t>("en.tile_hi", (size_t)num_tiles + 2);
   uint32_t *tile_contig = c.pool.dev<uint32_t>("en.tile_contig", (size_t)num_tiles + 2);
+  uint64_t *srt_words = c.pool.dev<uint64_t>("en.srt_words", (size_t)Mn * W + 2);  // + slack: bulk copies round up to 16 B
+  uint16_t *srt_len = c.pool.dev<uint16_t>("en.srt_len", Mn);
+  uint32_t *srt_rid = c.pool.dev<uint32_t>("en.srt_rid", Mn);
+  uint8_t *srt_rev = c.pool.dev<uint8_t>("en.srt_rev", Mn);
   if (seq_len) {
+    k_gather_sorted<<<grid_for((uint64_t)M * W, 256), 256, 0, st>>>(reads, lens, ro.order, ro.rev, perm, M, W, srt_words, srt_len, srt_rid, srt_rev);
     k_tile_ranges<<<grid_for((uint64_t)M + 1, 256), 256, 0, st>>>(sorted_ap, M, L, num_tiles, tile_lo, tile_hi);
-    k_consensus<<<num_tiles, kTile, 0, st>>>(reads, lens, ro.order, ro.rev, sorted_ap, perm, tile_lo, tile_hi, M, W, L, seq_len, cons2);
-    c.launches += 2;
+    k_consensus<<<num_tiles, kTile, 0, st>>>(srt_words, srt_len, sorted_ap, tile_lo, tile_hi, W, L, seq_len, cons2);
+    c.launches += 3;
   }
 
   // ---- singleton / N re-alignment ------------------------------------------------------------------
@@ -617,14 +673,14 @@ void run_encode(Ctx &c, const uint64_t *reads, const uint16_t *lens, uint32_t n,
   out.lengths = c.pool.dev<uint16_t>("en.out_len", NT);
   out.rev = c.pool.dev<uint8_t>("en.out_rev", MAn);
   FinalArrays f{out.pos, out.order, out.lengths, out.rev, c.pool.dev<uint32_t>("en.f_src", MAn), c.pool.dev<uint8_t>("en.f_kind", MAn)};
-  if (M) { k_place_originals<<<grid_for(M, 256), 256, 0, st>>>(sorted_ap, perm, M, skey, K, ro.order, ro.rev, lens, nr.order, nr.num, f); c.launches++; }
+  if (M) { k_place_originals<<<grid_for(M, 256), 256, 0, st>>>(sorted_ap, M, skey, K, srt_rid, srt_rev, srt_len, nr.order, nr.num, f); c.launches++; }
   if (K) { k_place_singles<<<grid_for(K, 256), 256, 0, st>>>(skey, ent, a_idx, K, sorted_ap, M, pool_len, pool_order, f); c.launches++; }
 
   uint32_t *nmis = c.pool.dev<uint32_t>("en.nmis", MAn + 1);
   uint64_t *noise_off = c.pool.dev<uint64_t>("en.noise_off", MAn + 1);
   uint64_t total_noise = 0;
   NoiseArgs na{};
-  na.reads = reads; na.pool_codes = pool_codes; na.pool_nflag = pool_nflag; na.W = W; na.cons2 = cons2; na.f = f; na.m = MA;
+  na.srt_words = srt_words; na.pool_codes = pool_codes; na.pool_nflag = pool_nflag; na.W = W; na.cons2 = cons2; na.f = f; na.m = MA;
   na.nmis = nmis; na.noise_off = noise_off;
   if (MA) {
     SB_CUDA(cudaMemsetAsync(nmis + MA, 0, sizeof(uint32_t), st));

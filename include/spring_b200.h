@@ -203,6 +203,23 @@ int spring_b200_reblock_streams(spring_b200_ctx *ctx, const spring_b200_streams 
  * the raw file (:363-428).  See INTEGRATION.md. */
 int spring_b200_reblock_files(spring_b200_ctx *ctx, const char *temp_dir, const spring_b200_cp *cp);
 
+/* ---- the decoder's mirror of the re-blocking: decompress_short's block decode ----- */
+/* src/decompress.cpp:230-320: the nine per-block streams (HOST, layout of spring_b200_blocks; `order` is
+ * not used) + the consensus (read_seq.bin's coding: 2 bits/base A0 C1 G2 T3, 4 bases per byte LSB first,
+ * all shards concatenated, src/decompress.cpp:106-120,615-660) -> every read as ASCII.  bases: the reads
+ * concatenated without separators, file 1's reads in output order followed by file 2's (paired end);
+ * offsets[num_reads + 1].  HOST arrays owned by the context.  Streams that do not belong together
+ * (block boundaries, line counts, positions beyond the consensus, noise beyond a read) are refused.
+ * The reference decompressor remains the parity oracle of the compressor; this entry point is the GPU
+ * counterpart of its inner loop. */
+typedef struct spring_b200_decoded {
+  const uint8_t *bases;
+  const uint64_t *offsets;
+  uint64_t num_reads;
+} spring_b200_decoded;
+int spring_b200_decode_blocks(spring_b200_ctx *ctx, const spring_b200_blocks *blocks, const uint8_t *seq_packed,
+                              uint64_t seq_len, const spring_b200_cp *cp, spring_b200_decoded *out);
+
 /* ---- the stage before the dictionaries: preprocess's read path ------------------ */
 /* What preprocess does to the sequence lines of the FASTQ input (src/preprocess.cpp:196-207, :293-304,
  * :364-378; record packers src/util.cpp:269-294, :322-348): reads that contain 'N' go to input_N.dna

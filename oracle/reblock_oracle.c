@@ -206,3 +206,102 @@ int orc_reblock(const uint64_t *pos, const uint8_t *noise, uint64_t noise_bytes,
   free(RC_arr); free(len_arr); free(flag_arr); free(pos_in_noise); free(pos_arr); free(noise_len); free(noise_arr); free(unal);
   return 0;
 }
+
+/* ---- the inverse: decompress_short's block decode, reference src/decompress.cpp:230-320 -------------------
+ * (SURVEY.md 8f rank 4).  Input: the nine per-block streams in the layout of orc_blocks_out (blocks
+ * concatenated + per-block byte offsets) and the consensus as ASCII; output: every read as ASCII, file 1's
+ * reads in output order followed by file 2's (paired end), with their lengths.  dec_noise: decompress.cpp:664-685. */
+static char DEC[128][128];
+static int dec_ready = 0;
+static void dec_init(void) {
+  if (dec_ready) return;
+  memset(DEC, 0, sizeof(DEC));
+  DEC['A']['0'] = 'C'; DEC['A']['1'] = 'G'; DEC['A']['2'] = 'T'; DEC['A']['3'] = 'N';
+  DEC['C']['0'] = 'A'; DEC['C']['1'] = 'G'; DEC['C']['2'] = 'T'; DEC['C']['3'] = 'N';
+  DEC['G']['0'] = 'T'; DEC['G']['1'] = 'A'; DEC['G']['2'] = 'C'; DEC['G']['3'] = 'N';
+  DEC['T']['0'] = 'G'; DEC['T']['1'] = 'C'; DEC['T']['2'] = 'A'; DEC['T']['3'] = 'N';
+  DEC['N']['0'] = 'A'; DEC['N']['1'] = 'G'; DEC['N']['2'] = 'C'; DEC['N']['3'] = 'T';
+  dec_ready = 1;
+}
+static char rcomp(char c) { /* util.h:23-29 */
+  switch (c) { case 'A': return 'T'; case 'C': return 'G'; case 'G': return 'C'; case 'T': return 'A'; default: return 'N'; }
+}
+
+/* out_reads: capacity >= sum of all lengths; out_len[num_reads]; reads of file 1 (units 0..U-1) first, then file 2.
+ * returns 0, or a negative code when a stream runs out. */
+int orc_decode_blocks(const uint8_t *const data[RB_NSTREAMS], const uint64_t *const off[RB_NSTREAMS], uint32_t num_blocks,
+                      const uint8_t *seq, uint64_t seq_len, uint64_t num_reads, int paired_end, int preserve_order,
+                      uint32_t num_reads_per_block, uint8_t *out_reads, uint64_t *out_off, uint16_t *out_len) {
+  dec_init();
+  const uint64_t units = paired_end ? num_reads / 2 : num_reads, B = num_reads_per_block;
+  /* lengths first: they decide where every read lands in out_reads (file 1, then file 2) */
+  for (uint32_t b = 0; b < num_blocks; b++) {
+    const uint64_t start = (uint64_t)b * B, end = start + B < units ? start + B : units;
+    const uint8_t *pl = data[RB_LENGTHS] + off[RB_LENGTHS][b];
+    for (uint64_t i = start; i < end; i++) {
+      memcpy(&out_len[i], pl, 2); pl += 2;
+      if (paired_end) { memcpy(&out_len[units + i], pl, 2); pl += 2; }
+    }
+  }
+  uint64_t acc = 0;
+  for (uint64_t i = 0; i < num_reads; i++) { out_off[i] = acc; acc += out_len[i]; }
+  out_off[num_reads] = acc;
+  for (uint32_t b = 0; b < num_blocks; b++) {
+    const uint64_t start = (uint64_t)b * B, end = start + B < units ? start + B : units;
+    const uint8_t *pf = data[RB_FLAG] + off[RB_FLAG][b], *pp = data[RB_POS] + off[RB_POS][b];
+    const uint8_t *pn = data[RB_NOISE] + off[RB_NOISE][b], *pnp = data[RB_NOISEPOS] + off[RB_NOISEPOS][b];
+    const uint8_t *prc = data[RB_RC] + off[RB_RC][b], *pu = data[RB_UNALIGNED] + off[RB_UNALIGNED][b];
+    const uint8_t *ppp = data[RB_POS_PAIR] + off[RB_POS_PAIR][b], *prp = data[RB_RC_PAIR] + off[RB_RC_PAIR][b];
+    int first_read_of_block = 1;
+    uint64_t prevpos = 0;
+    for (uint64_t i = start; i < end; i++) {
+      const char flag = (char)*pf++;
+      uint64_t pos_1 = 0;
+      char RC_1 = 'd';
+      for (int mate = 0; mate < (paired_end ? 2 : 1); mate++) {
+        const uint64_t slot = mate ? units + i : i;
+        const uint16_t rl = out_len[slot];
+        uint8_t *dst = out_reads + out_off[slot];
+        const int singleton = mate == 0 ? (flag == '2' || flag == '4') : (flag == '2' || flag == '3'); /* :234, :286 */
+        if (singleton) { memcpy(dst, pu, rl); pu += rl; continue; }                                   /* :275-278 */
+        uint64_t pos;
+        char RC;
+        if (mate == 0) { /* :236-254 */
+          if (preserve_order) { memcpy(&pos, pp, 8); pp += 8; }
+          else if (first_read_of_block) { first_read_of_block = 0; memcpy(&pos, pp, 8); pp += 8; prevpos = pos; }
+          else {
+            uint16_t d16; memcpy(&d16, pp, 2); pp += 2;
+            if (d16 == 65535) { memcpy(&pos, pp, 8); pp += 8; } else pos = prevpos + d16;
+            prevpos = pos;
+          }
+          RC = (char)*prc++;
+          pos_1 = pos; RC_1 = RC;
+        } else if (flag == '1' || flag == '4') { /* :290-294 */
+          memcpy(&pos, pp, 8); pp += 8;
+          RC = (char)*prc++;
+        } else { /* :295-305 */
+          int16_t pp16; memcpy(&pp16, ppp, 2); ppp += 2;
+          pos = pos_1 + (int64_t)pp16;
+          const char rel = (char)*prp++;
+          RC = rel == '0' ? (RC_1 == 'd' ? 'r' : 'd') : (RC_1 == 'd' ? 'd' : 'r');
+        }
+        if (pos + rl > seq_len) return -3;
+        char tmp[512];
+        memcpy(tmp, seq + pos, rl);
+        uint16_t prevnp = 0;
+        while (*pn != '\n') { /* :258-266 */
+          uint16_t np; memcpy(&np, pnp, 2); pnp += 2;
+          np = (uint16_t)(np + prevnp);
+          if (np >= rl) return -4;
+          tmp[np] = DEC[(uint8_t)tmp[np]][*pn];
+          prevnp = np;
+          pn++;
+        }
+        pn++;
+        if (RC == 'd') memcpy(dst, tmp, rl);
+        else for (uint16_t k = 0; k < rl; k++) dst[k] = (uint8_t)rcomp(tmp[rl - 1 - k]); /* util.cpp:376-381 */
+      }
+    }
+  }
+  return 0;
+}

@@ -18,6 +18,8 @@
 //        reads DIR/cp_in.bin, runs pe_encode (spring.cpp:193, only for -r paired input) and
 //        reorder_compress_streams (spring.cpp:206) on the encoder streams in DIR, then BSC-decodes
 //        every per-block file it wrote (X.<b>.bsc -> X.<b>) so the raw block streams can be compared
+//   spring_ref --bsc-decode -i F.bsc [G.bsc ...]
+//        bsc::BSC_decompress of each file into the same name without ".bsc" (to look inside an archive)
 //
 // When built with -DSPRING_B200_SPLICE the two call_* symbols come from
 // spring_b200/csrc/host/call_template_functions_b200.cpp (our CUDA library
@@ -52,7 +54,7 @@ static double now_s() {
 int main(int argc, char **argv) {
   bool compress_flag = false, decompress_flag = false, pairing_only = false,
        no_quality = false, no_ids = false, pre_flag = false, hot_flag = false,
-       unbsc = false, reblock_flag = false;
+       unbsc = false, reblock_flag = false, bscdec_flag = false;
   std::vector<std::string> in_vec, out_vec, quality_opts;
   std::vector<uint64_t> range_vec;
   std::string working_dir = ".", temp_given;
@@ -69,6 +71,7 @@ int main(int argc, char **argv) {
     else if (a == "--hotpath") { hot_flag = true; cur = NULL; }
     else if (a == "--unbsc") { unbsc = true; cur = NULL; }
     else if (a == "--reblock") { reblock_flag = true; cur = NULL; }
+    else if (a == "--bsc-decode") { bscdec_flag = true; cur = NULL; }
     else if (a == "-i" || a == "--input-file") cur = &in_vec;
     else if (a == "-o" || a == "--output-file") cur = &out_vec;
     else if ((a == "-t" || a == "--num-threads") && i + 1 < argc) { num_thr = atoi(argv[++i]); cur = NULL; }
@@ -116,6 +119,13 @@ int main(int argc, char **argv) {
           std::string b = temp_given + "/read_seq.bin." + std::to_string(t);
           spring::bsc::BSC_decompress((b + ".bsc").c_str(), b.c_str());
         }
+      return 0;
+    }
+    if (bscdec_flag) {
+      for (const std::string &f : in_vec) {
+        if (f.size() < 5 || f.substr(f.size() - 4) != ".bsc") throw std::runtime_error("not a .bsc file: " + f);
+        spring::bsc::BSC_decompress(f.c_str(), f.substr(0, f.size() - 4).c_str());
+      }
       return 0;
     }
     if (reblock_flag) {

@@ -21,6 +21,7 @@ EXPORTS = [
     "spring_b200_reorder", "spring_b200_reorder_encode_files", "spring_b200_write_streams",
     "spring_b200_bucket_reads", "spring_b200_set_schedule", "spring_b200_fetch_reorder", "spring_b200_set_stream",
     "spring_b200_pe_encode", "spring_b200_reblock_streams", "spring_b200_reblock_files", "spring_b200_pack_reads",
+    "spring_b200_decode_blocks",
 ]
 
 
@@ -67,6 +68,10 @@ BLOCK_STREAMS = ("flag", "pos", "noise", "noisepos", "rc", "unaligned", "lengths
 class Blocks(C.Structure):
     _fields_ = [("num_blocks", C.c_uint32), ("data", C.c_void_p * NUM_BLOCK_STREAMS), ("size", C.c_uint64 * NUM_BLOCK_STREAMS),
                 ("off", C.c_void_p * NUM_BLOCK_STREAMS), ("order", C.c_void_p), ("num_reads", C.c_uint64)]
+
+
+class Decoded(C.Structure):
+    _fields_ = [("bases", C.c_void_p), ("offsets", C.c_void_p), ("num_reads", C.c_uint64)]
 
 
 class PackedReads(C.Structure):
@@ -116,6 +121,8 @@ def load():
         lib.spring_b200_pe_encode.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
         lib.spring_b200_reblock_streams.argtypes = [C.c_void_p, C.POINTER(Streams), C.POINTER(CP), C.POINTER(Blocks)]
         lib.spring_b200_reblock_files.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(CP)]
+        lib.spring_b200_decode_blocks.argtypes = [C.c_void_p, C.POINTER(Blocks), C.c_void_p, C.c_uint64, C.POINTER(CP),
+                                                  C.POINTER(Decoded)]
         lib.spring_b200_pack_reads.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int,
                                                C.POINTER(PackedReads)]
         _lib = lib
@@ -363,6 +370,29 @@ class Context:
         b = Blocks()
         self._check(self._lib.spring_b200_reblock_streams(self._h, None, C.byref(cp), C.byref(b)))
         return b
+
+    def decode_blocks(self, blocks, seq_packed: np.ndarray, seq_len: int, cp: CP):
+        """decompress_short's block decode (src/decompress.cpp:230-320): blocks in the BlocksResult /
+        oracle BlockStreams layout + packed consensus -> (bases uint8, offsets uint64[n + 1]); file 1's
+        reads first, then file 2's."""
+        b = Blocks()
+        b.num_blocks = blocks.num_blocks
+        keep = []
+        for i, name in enumerate(BLOCK_STREAMS):
+            d = np.ascontiguousarray(blocks.data[name], dtype=np.uint8)
+            o = np.ascontiguousarray(blocks.off[name], dtype=np.uint64)
+            keep += [d, o]
+            b.data[i] = d.ctypes.data if d.size else None
+            b.size[i] = d.size
+            b.off[i] = o.ctypes.data
+        sp = np.ascontiguousarray(seq_packed, dtype=np.uint8)
+        keep.append(sp)
+        self._keep = keep
+        out = Decoded()
+        self._check(self._lib.spring_b200_decode_blocks(self._h, C.byref(b), sp.ctypes.data if sp.size else None, seq_len,
+                                                        C.byref(cp), C.byref(out)))
+        offs = _view(out.offsets, out.num_reads + 1, np.uint64).copy()
+        return _view(out.bases, int(offs[-1]) if len(offs) else 0, np.uint8).copy(), offs
 
     def reblock_files(self, temp_dir: str, cp: CP) -> None:
         self._check(self._lib.spring_b200_reblock_files(self._h, temp_dir.encode(), C.byref(cp)))

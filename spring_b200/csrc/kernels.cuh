@@ -81,6 +81,16 @@ void run_pe_encode(Ctx &c, const uint32_t *order, uint32_t n, uint32_t *slot);
 // reorder_compress_streams.cpp:83-361 on the device-resident encoder streams `e`
 void run_reblock(Ctx &c, const EncodeDev &e, bool paired, bool preserve, uint32_t block, ReblockDev &out);
 
+// ---- decode.cu : decompress_short's block decode -----------------------------------
+struct DecodeDev {
+  uint8_t *bases = nullptr;                 // every read as ASCII, file 1's reads in output order, then file 2's (device)
+  unsigned long long *offsets = nullptr;    // [num_reads + 1] (device)
+  uint64_t total = 0, num_reads = 0;
+};
+// b: the nine block streams + block offsets on the device (layout of run_reblock's output); sizes[s]: bytes of stream s
+void run_decode_blocks(Ctx &c, const ReblockDev &b, const uint64_t *sizes, const uint8_t *d_seq_packed, uint64_t seq_len,
+                       uint64_t num_reads, bool paired, bool preserve, uint32_t block, DecodeDev &out);
+
 // ---- pack.cu : preprocess's read path, N split + 2-bit / 4-bit packing -----------
 struct PackDev {
   uint64_t *reads = nullptr; uint16_t *lengths = nullptr;  // clean reads, input order, [num_clean][W] (device)

@@ -505,6 +505,54 @@ int spring_b200_fetch_reorder(spring_b200_ctx *ctx, spring_b200_reorder_out *out
 }
 
 
+int spring_b200_decode_blocks(spring_b200_ctx *ctx, const spring_b200_blocks *blocks, const uint8_t *seq_packed,
+                              uint64_t seq_len, const spring_b200_cp *cp, spring_b200_decoded *out) {
+  return guarded(ctx, [&] {
+    if (!blocks || !cp || !out || (seq_len && !seq_packed)) throw ArgError("null argument");
+    if (cp->long_flag) throw ArgError("long mode archives hold no block streams of this kind (spring.cpp:150)");
+    if (cp->num_reads_per_block <= 0) throw ArgError("cp.num_reads_per_block <= 0");
+    if (cp->num_reads >= 0x7FFFFFF0u) throw ArgError("too many reads for one GPU shard (>= 2^31)");
+    Ctx &c = ctx->c;
+    c.launches = 0;
+    static const char *names[RB_NSTREAMS] = {"dcin.flag", "dcin.pos", "dcin.noise", "dcin.noisepos", "dcin.rc", "dcin.unal", "dcin.len",
+                                             "dcin.pos_pair", "dcin.rc_pair"};
+    ReblockDev rb;
+    rb.num_blocks = blocks->num_blocks;
+    const size_t st = (size_t)blocks->num_blocks + 1;
+    std::vector<unsigned long long> h_off(RB_NSTREAMS * st);
+    for (int s = 0; s < RB_NSTREAMS; s++) {
+      if (!blocks->off[s]) throw ArgError("blocks: null offsets");
+      for (size_t b = 0; b < st; b++) {
+        h_off[s * st + b] = blocks->off[s][b];
+        if ((b && blocks->off[s][b] < blocks->off[s][b - 1]) || blocks->off[s][b] > blocks->size[s]) throw ArgError("blocks: offsets out of order");
+      }
+      if (blocks->off[s][0] != 0 || blocks->off[s][st - 1] != blocks->size[s]) throw ArgError("blocks: offsets do not span the stream");
+      rb.size[s] = blocks->size[s];
+      rb.data[s] = c.pool.dev<uint8_t>(names[s], blocks->size[s] + 16);
+      if (blocks->size[s]) {
+        if (!blocks->data[s]) throw ArgError("blocks: null stream");
+        SB_CUDA(cudaMemcpyAsync(rb.data[s], blocks->data[s], blocks->size[s], cudaMemcpyHostToDevice, c.stream));
+      }
+    }
+    rb.block_off = c.pool.dev<unsigned long long>("dcin.off", RB_NSTREAMS * st);
+    SB_CUDA(cudaMemcpyAsync(rb.block_off, h_off.data(), sizeof(unsigned long long) * RB_NSTREAMS * st, cudaMemcpyHostToDevice, c.stream));
+    uint8_t *d_seq = c.pool.dev<uint8_t>("dcin.seq", (seq_len + 3) / 4 + 16);
+    if (seq_len) SB_CUDA(cudaMemcpyAsync(d_seq, seq_packed, (seq_len + 3) / 4, cudaMemcpyHostToDevice, c.stream));
+    DecodeDev dd;
+    try {
+      run_decode_blocks(c, rb, rb.size, d_seq, seq_len, cp->num_reads, cp->paired_end != 0, cp->preserve_order != 0,
+                        (uint32_t)cp->num_reads_per_block, dd);
+    } catch (const LimitError &e) { throw ArgError(e.what()); }  // bad input, not an internal limit
+    uint8_t *h_bases = c.pool.pin<uint8_t>("dc.h_bases", dd.total + 1);
+    uint64_t *h_offs = c.pool.pin<uint64_t>("dc.h_offsets", dd.num_reads + 1);
+    if (dd.total) SB_CUDA(cudaMemcpyAsync(h_bases, dd.bases, dd.total, cudaMemcpyDeviceToHost, c.stream));
+    SB_CUDA(cudaMemcpyAsync(h_offs, dd.offsets, sizeof(uint64_t) * (dd.num_reads + 1), cudaMemcpyDeviceToHost, c.stream));
+    SB_CUDA(cudaStreamSynchronize(c.stream));
+    out->bases = h_bases; out->offsets = h_offs; out->num_reads = dd.num_reads;
+    ctx->stats.gpu_launches = c.launches;
+  });
+}
+
 int spring_b200_pack_reads(spring_b200_ctx *ctx, const uint8_t *bases, const uint64_t *offsets, uint32_t num_reads,
                            uint32_t num_reads_file1, int keep_on_device, spring_b200_packed_reads *out) {
   return guarded(ctx, [&] {

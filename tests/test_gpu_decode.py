@@ -49,16 +49,14 @@ def test_decode_blocks_with_position_escapes(ctx):
         n = n_units * (2 if paired else 1)
         jump = rng.random(n) < 0.2
         pos = np.cumsum(np.where(jump, rng.integers(65535, 200000, n), rng.integers(0, 300, n))).astype(np.uint64)
-        pos = pos % np.uint64(len(seq) - L)
-        if not paired:
-            pos = np.sort(pos)
+        pos = pos % np.uint64(len(seq) - L)          # not monotone: backward jumps wrap and take the escape too
         er = SimpleNamespace(seq=np.frombuffer(b"ACGT", np.uint8)[seq], pos=pos, noise=np.full(n, ord("\n"), np.uint8),
                              noisepos=np.zeros(0, np.uint16), rc=rng.choice(np.frombuffer(b"dr", np.uint8), n),
                              order=rng.permutation(n).astype(np.uint32), lengths=np.full(n, L, np.uint16),
                              unaligned=np.zeros(0, np.uint8), unaligned_len=0, num_aligned=n)
         order = po.pe_encode(er.order) if paired else None
         blocks = po.reblock(er, paired, False, 1000, order=order)
-        assert (np.frombuffer(blocks.data["pos"].tobytes(), np.uint8) == 255).sum() > 100   # escapes are present
+        assert len(blocks.data["pos"]) > 2 * n_units + 8 * 300                                 # escapes are present
         want = po.decode_blocks(blocks, er.seq, n, paired, False, 1000)
         sp, sl = packed_seq(er)
         bases, offs = ctx.decode_blocks(blocks, sp, sl, make_cp(n, L, paired, False, 1000))

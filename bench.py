@@ -212,9 +212,16 @@ def main() -> None:
         torch.cuda.synchronize()
 
     # ---- value: inputs already in HBM ---------------------------------------------------------------
+    xe0, xe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    exchange_ms = []
+
     def device_step():
         if world > 1:
+            xe0.record(stream)
             r, l = multigpu.exchange_by_bucket(d_reads, d_lens, READ_LEN, world)
+            xe1.record(stream)
+            xe1.synchronize()
+            exchange_ms.append(xe0.elapsed_time(xe1))
         else:
             r, l = d_reads, d_lens
         inp = ctx.make_input(r.data_ptr(), l.data_ptr(), r.shape[0], READ_LEN)
@@ -326,6 +333,8 @@ def main() -> None:
             "stages_ms": {k: stats_acc[k] for k in stats_acc if k.startswith("ms_")},
             "chains": stats_acc["num_chains"], "rounds": stats_acc["rounds"], "unmatched": stats_acc["unmatched"],
             "mb_per_s_fastq": value * (2 * READ_LEN + 12)}
+    if exchange_ms:  # rank 0's bucket kernel + owner sort + gathers + all-to-alls, per step (inside ms_per_step)
+        line["exchange_ms"] = sum(exchange_ms[-args.steps:]) / args.steps
     if after is not None:
         line["after_encoder"] = after
     if world == 1 and not args.no_cpu_baseline:

@@ -54,6 +54,7 @@ struct ChainArgs {
   uint32_t G;            // scan_bin: candidates verified per pass = 32 / W
   unsigned leader_mask;  // scan_bin: lanes g * W, g < G
   int generic_update;    // debugging aid: always use the per-column update_ref
+  int steal_probes;      // free-running schedule: random slices an idle chain probes for an unclaimed read (0 = off)
   unsigned long long *chain_dbg;  // [2 * chains]: steps, globaltimer ns at finish (profiling aid)
 };
 
@@ -625,6 +626,24 @@ __global__ void __launch_bounds__(WPB * 32, MINB) k_chains(ChainArgs a) {
           cursor = (int)j - 1;
           if (!((old >> (j & 31)) & 1u)) { got = true; break; }
         }
+        // Own slice exhausted: instead of idling until the slowest chain is done, seed the next contig from
+        // the slice of a randomly chosen other chain (the reference's threads all pick from ONE pool,
+        // reorder.h:576-592).  Random victims keep thieves apart; a bounded number of probes bounds the
+        // work once nothing is left.  Every slice is still drained by its owner, so coverage is unaffected.
+        if (!got && a.steal_probes > 0) {
+          uint32_t rnd = cid * 2654435761u + num_reads_thr;
+          for (int t = 0; t < a.steal_probes && !got; t++) {
+            rnd = rnd * 1664525u + 1013904223u;
+            const uint32_t v = (rnd >> 8) % a.num_chains;
+            const long long vlo = (long long)v * a.per;
+            const long long vhi = v == a.num_chains - 1 ? (long long)a.N - 1 : vlo + a.per - 1;
+            if (!find_unclaimed(a.claimed, vlo, vhi, lane, j)) continue;
+            unsigned old = 0;
+            if (lane == 0) old = atomicOr(a.claimed + (j >> 5), 1u << (j & 31));
+            old = __shfl_sync(FULL, old, 0);
+            if (!((old >> (j & 31)) & 1u)) got = true;
+          }
+        }
         if (prev_unmatched) {
           if (lane == 0) { a.rec_chain[prev] = cid; a.rec_k[prev] = n_single; a.rec_meta[prev] = 4; }
           n_single++;
@@ -874,6 +893,7 @@ void run_reorder(Ctx &c, const uint64_t *reads, const uint16_t *lens, uint32_t n
   a.leader_mask = 0;
   for (uint32_t g = 0; g < a.G; g++) a.leader_mask |= 1u << (g * W);
   a.generic_update = getenv("SPRING_B200_GENERIC_UPDATE") ? 1 : 0;
+  a.steal_probes = lockstep ? 0 : (getenv("SPRING_B200_STEAL") ? atoi(getenv("SPRING_B200_STEAL")) : 64);
   a.max_rounds = 8ull * n + 4096ull;
   SB_CUDA(cudaMemsetAsync(a.claimed, 0, bm_words * sizeof(uint32_t), st));
   SB_CUDA(cudaMemsetAsync(a.winner, 0xFF, (size_t)n * sizeof(uint32_t), st));

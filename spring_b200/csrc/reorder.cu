@@ -896,7 +896,7 @@ void run_reorder(Ctx &c, const uint64_t *reads, const uint16_t *lens, uint32_t n
   a.steal_probes = lockstep ? 0 : (getenv("SPRING_B200_STEAL") ? atoi(getenv("SPRING_B200_STEAL")) : 64);
   a.max_rounds = 8ull * n + 4096ull;
   SB_CUDA(cudaMemsetAsync(a.claimed, 0, bm_words * sizeof(uint32_t), st));
-  SB_CUDA(cudaMemsetAsync(a.winner, 0xFF, (size_t)n * sizeof(uint32_t), st));
+  if (lockstep) SB_CUDA(cudaMemsetAsync(a.winner, 0xFF, (size_t)n * sizeof(uint32_t), st));  // proposals: deterministic schedule only
   SB_CUDA(cudaMemsetAsync(sync, 0, (2 + CTR_N) * sizeof(unsigned long long), st));
   SB_CUDA(cudaMemsetAsync(a.chain_aligned, 0, (nslots + 1) * sizeof(uint32_t), st));
   SB_CUDA(cudaMemsetAsync(a.chain_single, 0, (nslots + 1) * sizeof(uint32_t), st));

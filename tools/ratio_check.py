@@ -5,13 +5,17 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from oracle import pyoracle as po
 from spring_b200 import synth
 
-n = int(sys.argv[1]) if len(sys.argv) > 1 else 2_000_000
+n = int(sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1].isdigit() else 2_000_000
 threads = os.cpu_count() or 8
 rs = synth.generate(n, 150, genome_len=n * 150 // 30, seed=3, sub_rate=0.005, device="cuda")
 d = tempfile.mkdtemp(dir="/dev/shm")
 fq = os.path.join(d, "in.fastq")
 t0 = time.time(); synth.write_fastq(rs, fq); print(f"wrote {n} reads in {time.time()-t0:.1f}s")
-for name, binary, env in (("reference", po.REF_BIN, {}), ("b200 auto chains", po.SPLICE_BIN, {}), ("b200 1 chain", po.SPLICE_BIN, {"SPRING_B200_CHAINS": "1"})):
+runs = [("reference", po.REF_BIN, {}), ("b200 auto chains", po.SPLICE_BIN, {}), ("b200 + reblock", po.SPLICE2_BIN, {}),
+        ("b200 1 chain", po.SPLICE_BIN, {"SPRING_B200_CHAINS": "1"})]
+if "--quick" in sys.argv:
+    runs = runs[:3]
+for name, binary, env in runs:
     out = os.path.join(d, name.replace(" ", "_") + ".spring")
     t0 = time.time()
     r = subprocess.run([binary, "-c", "-r", "--no-quality", "-i", fq, "-o", out, "-t", str(threads), "-w", d], capture_output=True, text=True, env={**os.environ, **env})

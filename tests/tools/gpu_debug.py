@@ -1,7 +1,7 @@
 """Debug helper (GPU box): first divergence between the CUDA reorder stream and the oracle, per case."""
 import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 import numpy as np
 from helpers import CASES, make_input
 from oracle import pyoracle as po

@@ -1,7 +1,7 @@
 """GPU box: compressed size + stage times of the reference vs the reference host with libspring_b200
 spliced in (oracle/_ref/spring_b200_ref), same FASTQ, `-c -r --no-quality`."""
 import os, re, subprocess, sys, tempfile, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle import pyoracle as po
 from spring_b200 import synth
 

@@ -37,3 +37,35 @@ def test_no_gpu_fails_loudly():
     with pytest.raises(capi.SpringB200Error) as e:
         capi.Context(0)
     assert e.value.code == -2
+
+
+def test_ctypes_structs_match_the_c_header(tmp_path):
+    """Every ctypes mirror in spring_b200/capi.py has the size and field offsets gcc gives the struct of
+    include/spring_b200.h (a silent layout drift would corrupt arguments, not fail)."""
+    import subprocess
+    pairs = {"spring_b200_cp": capi.CP, "spring_b200_input": capi.Input, "spring_b200_streams": capi.Streams,
+             "spring_b200_reorder_out": capi.ReorderOut, "spring_b200_stats": capi.Stats, "spring_b200_blocks": capi.Blocks,
+             "spring_b200_packed_reads": capi.PackedReads, "spring_b200_decoded": capi.Decoded}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "spring_b200.h"', 'int main(void) {']
+    for cname, ct in pairs.items():
+        lines.append(f'  printf("{cname} SIZEOF %zu\\n", sizeof({cname}));')
+        for fname, _ in ct._fields_:
+            lines.append(f'  printf("{cname} {fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-std=c11", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    out = subprocess.check_output([str(exe)], text=True).split("\n")
+    seen = 0
+    for ln in out:
+        if not ln:
+            continue
+        cname, field, val = ln.split()
+        ct = pairs[cname]
+        if field == "SIZEOF":
+            assert ctypes.sizeof(ct) == int(val), cname
+        else:
+            assert getattr(ct, field).offset == int(val), f"{cname}.{field}"
+        seen += 1
+    assert seen == sum(len(ct._fields_) + 1 for ct in pairs.values())

@@ -1,31 +1,35 @@
-// reorder.cu -- the greedy overlap search (reference src/reorder.h:320-641) as one persistent,
-// cooperative sm_100a kernel.
+// reorder.cu -- the greedy overlap search (reference src/reorder.h:320-641) as one persistent sm_100a
+// kernel.
 //
 // Mapping.  One warp = one "chain" = one reference OpenMP thread (reorder.h:351): it owns a
 // consensus window (per-column base counts in shared memory, ref / revref bitsets), and repeats
 // { search the dictionaries for an overlapping read, claim it, fold it into the consensus }.
-//   * the reference tries shift 0,1,2,... one after the other, 4 dictionary probes per shift
-//     (search_match, reorder.h:246-318).  Here the 32 lanes take 32 consecutive shifts at once:
-//     each lane extracts its 4 window keys from the shared-memory bitsets, issues its 4 slot loads
-//     back to back (128 independent 16 B loads in flight per warp) and the warp then walks the hits
-//     in the reference's priority order (shift, forward before reverse, dict 0 before dict 1,
-//     highest read id first) so the read it picks is the one the sequential search would pick.
-//   * candidates of a bin are verified 32 at a time: lane t loads candidate t's packed words,
-//     XORs them with the shifted reference, masks the overlap and popcounts (THRESH_REORDER = 4).
+//   * search: the reference tries shift 0,1,2,... one after the other, 4 dictionary probes per shift
+//     (search_match, reorder.h:246-318).  Here lane l owns probe kind l & 3 (strand x dictionary) and the
+//     shifts S + (l >> 2) + 8j of a batch: every probe tests one bit of an L2-resident key filter, the
+//     positives load their 32-byte slot from HBM, and the warp walks the hits in the reference's priority
+//     order (shift, forward before reverse, dict 0 before dict 1, highest read id first), so the read it
+//     picks is the one the sequential search would pick.
+//   * verification (scan_bin): the warp is cut into 32 / W groups of W lanes, one candidate per group, one
+//     bitset word per lane: XOR with the shifted reference, mask the overlap, popcount, W-lane sum
+//     (THRESH_REORDER = 4).
 //   * updaterefcount (reorder.h:110-220): the four count-shift cases collapse to one remap
-//     "new column i <- old column i+delta" done 32 columns per step; majority bases are turned
-//     back into the 2-bit bitsets with two ballots per 32 columns.
+//     "new column i <- old column i + delta", 32 columns per step; the consensus is rebuilt by word
+//     operations and re-voted only where read and old consensus differ (update_ref_fast).
 //
 // Scheduling.  The reference is racy (try-locks) and non-reproducible for more than one thread.
-// Chains here run in lock step: phase A every chain searches against the claim bitmap as of the
-// round start and proposes one read (atomicMin of its chain id into winner[rid]); grid barrier;
-// phase B the winner claims and updates, losers retry; grid barrier.  The result is a pure
-// function of (input, num_chains) and is restated exactly by oracle/spring_oracle.c, which for
-// one chain is the reference's single-thread execution.
+//   * free-running (default): chains claim reads with an atomic test-and-set like the reference's threads;
+//     a chain that has drained its slice of the read ids seeds further contigs from randomly probed other
+//     slices.  Output depends on timing for more than one chain, as the reference's does for -t > 1.
+//   * deterministic (cooperative launch): chains run in lock step: phase A every chain searches against
+//     the claim bitmap as of the round start and proposes one read (atomicMin of its chain id into
+//     winner[rid]); grid barrier; phase B the winner claims and updates, losers retry; grid barrier.  The
+//     result is a pure function of (input, num_chains) and is restated exactly by oracle/spring_oracle.c,
+//     which for one chain is the reference's single-thread execution.
 //
-// Memory traffic per claimed read (L = 150): ~128 slot probes x 32 B sectors per round, one
-// read_id sector + one or two 40 B candidate rows per hit, 17 B of records; all other state stays
-// in shared memory / registers for the life of the kernel.
+// Memory traffic per claimed read (L = 150): ~39 filter words (L2), ~7.5 slot sectors, one or two 40-byte
+// candidate rows + their claim words, 17 B of records; all other state stays in shared memory / registers
+// for the life of the kernel (DESIGN.md sections 5, 6).
 #include <algorithm>
 #include <cub/cub.cuh>
 #include "kernels.cuh"

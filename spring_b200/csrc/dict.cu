@@ -3,7 +3,8 @@
 // Replaces constructdictionary<> (reference src/bitset_util.h:74-221): window key per read ->
 // (drop reads shorter than the window) -> sort -> unique keys -> bins with ascending read ids.
 // The reference maps key -> bin through BooPHF and a CSR startpos[]; here the unique keys go into
-// an open-addressing table of 16-byte slots {key, bin start, bin size} (one 32 B sector per probe),
+// an open-addressing table of 32-byte slots {key, bin start, live count, bin size, three highest ids}
+// (one 32 B sector per probe),
 // and read_id[] is the value array of a stable radix sort of (key, read id) pairs, so ids are
 // ascending inside every bin exactly as bitset_util.h:188-206 leaves them.
 #include <cub/cub.cuh>

@@ -8,8 +8,9 @@
 //      the concatenated consensus (abs_pos in writecontig, encoder.cpp:98,107)
 //   3. absolute position of every read; stable radix sort by it.  Contigs occupy disjoint
 //      ascending ranges, so this one sort is list::sort per contig (encoder.h:221) for all contigs.
-//   4. consensus: one thread per consensus column, the reads overlapping a 256-column tile are
-//      staged in shared memory, majority vote in registers                   (buildcontig)
+//   4. consensus: the contig reads are gathered once into sorted, oriented rows (the reference's
+//      temp.dna.<t>, kept in HBM); one block per 256-column tile stages the rows that can cover it
+//      with bulk async copies (TMA) and votes, one thread per column         (buildcontig)
 //   5. singleton/N re-alignment: one thread per consensus window position; 4 dictionary probes
 //      (2 strands x 2 dicts) against a dictionary of the singleton pool; a passing candidate
 //      records min(priority) with atomicMin, priority = (window position, strand, dict), i.e.

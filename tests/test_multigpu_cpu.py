@@ -102,6 +102,12 @@ def test_multi_rank_exchange_and_merge(world):
     orig = original_reads(hp)
     for i, o in enumerate(merged.order):
         assert dec[i] == orig[int(o)]
+    # the merged job goes through the stages after the encoder like a single-shard one: re-blocking
+    # (reorder_compress_streams.cpp:83-361) and the decompressor's block decode give the reads back
+    s.order, s.unaligned_len = merged.order, merged.unaligned_len
+    blocks = po.reblock(s, False, False, 1500)
+    back = po.decode_blocks(blocks, s.seq, len(hp.lengths), False, False, 1500)
+    assert back == [orig[int(o)] for o in merged.order]
     # sharding costs matches but must stay in the same range as one shard
     _, one = po.reorder_encode(hp.packed, hp.lengths, hp.max_readlen, num_chains=3)
     assert merged.num_aligned > 0.9 * one.num_aligned

@@ -428,7 +428,7 @@ def load_archive_blocks(archive: str, work_dir: str):
     (cp bytes, BlockStreams, ASCII consensus): what decompress_short starts from (decompress.cpp:83-229)."""
     import tarfile
     with tarfile.open(archive) as t:
-        t.extractall(work_dir)
+        t.extractall(work_dir, filter="data")
     cpb = open(os.path.join(work_dir, "cp.bin"), "rb").read()
     bsc = sorted(os.path.join(work_dir, f) for f in os.listdir(work_dir) if f.startswith("read_") and f.endswith(".bsc"))
     r = subprocess.run([REF_BIN, "--bsc-decode", "-i", *bsc], capture_output=True, text=True)

@@ -243,7 +243,7 @@ void run_pe_encode(Ctx &c, const uint32_t *order, uint32_t n, uint32_t *slot) {
   k_is_file1<<<grid_for(n, 256), 256, 0, st>>>(order, n, half, f1);
   size_t need = 0;
   cub::DeviceScan::ExclusiveSum(nullptr, need, f1, rank1, (int)n, st);
-  void *tmp = c.pool.device("rb.cubtmp", need);
+  void *tmp = c.pool.device("pe.cubtmp", need);  // its own buffer: run_reblock holds a pointer into "rb.cubtmp" across this call
   cub::DeviceScan::ExclusiveSum(tmp, need, f1, rank1, (int)n, st);
   k_pe_slots<<<grid_for(n, 256), 256, 0, st>>>(order, inverse, rank1, n, half, slot);
   c.launches += 5;

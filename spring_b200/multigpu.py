@@ -7,7 +7,8 @@ so a GPU plays the role of one reference thread:
 
   1. every rank holds a block of the clean reads (global id = rank offset + local index)
   2. owner(read) = minimizer bucket mod world (CUDA kernel, csrc/bucket.cu)
-  3. ONE all-to-all(v) of {packed read, length, global id} over NCCL / NVLink
+  3. ONE all-to-all(v) of fused {packed read, length[, global id]} byte records over NCCL / NVLink
+     (preceded by the tiny all-to-all of the split sizes)
   4. each rank runs the unchanged single-GPU reorder + encode on the reads it owns
   5. the per-rank streams are merged on the host: consensus shards concatenated, positions offset,
      local indices mapped back to global ids, and -- the invariant the downstream stages rely on
@@ -59,19 +60,20 @@ def exchange_by_bucket(reads: torch.Tensor, lens: torch.Tensor, max_readlen: int
     sc, rc = send_counts.tolist(), recv_counts.tolist()
     n_recv = int(sum(rc))
 
-    def a2a(x: torch.Tensor) -> torch.Tensor:
-        # rows travel as raw bytes: every backend moves uint8 (gloo has no int16 all-to-all)
-        xs = x[order].contiguous()
-        row = xs.element_size() * (xs[0].numel() if xs.shape[0] else int(np.prod(x.shape[1:], dtype=np.int64)))
-        xb = xs.view(torch.uint8).reshape(xs.shape[0], row)
-        out = torch.empty((n_recv, row), dtype=torch.uint8, device=x.device)
-        dist.all_to_all_single(out, xb, output_split_sizes=rc, input_split_sizes=sc, group=group)
-        return out.view(x.dtype).reshape((n_recv,) + tuple(x.shape[1:]))
-
-    r, l = a2a(reads), a2a(lens)
-    if ids is None:
-        return r, l
-    return r, l, a2a(ids)
+    # ONE all-to-all for everything a read carries: the 8W-byte row, its u16 length and (optionally) its
+    # u32 global id travel as one fused byte record (every backend moves uint8; gloo has no int16 all-to-all)
+    fields = [reads, lens] + ([ids] if ids is not None else [])
+    n = reads.shape[0]
+    parts = [x[order].contiguous().view(torch.uint8).reshape(n, -1) for x in fields]
+    widths = [int(x.element_size() * int(np.prod(x.shape[1:], dtype=np.int64))) for x in fields]
+    rec = torch.cat(parts, dim=1) if n else torch.empty((0, sum(widths)), dtype=torch.uint8, device=reads.device)
+    got = torch.empty((n_recv, sum(widths)), dtype=torch.uint8, device=reads.device)
+    dist.all_to_all_single(got, rec, output_split_sizes=rc, input_split_sizes=sc, group=group)
+    out, off = [], 0
+    for x, w in zip(fields, widths):
+        out.append(got[:, off:off + w].contiguous().view(x.dtype).reshape((n_recv,) + tuple(x.shape[1:])))
+        off += w
+    return tuple(out)
 
 
 @dataclass

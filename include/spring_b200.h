@@ -220,6 +220,21 @@ typedef struct spring_b200_decoded {
 int spring_b200_decode_blocks(spring_b200_ctx *ctx, const spring_b200_blocks *blocks, const uint8_t *seq_packed,
                               uint64_t seq_len, const spring_b200_cp *cp, spring_b200_decoded *out);
 
+/* ---- full-size round trip, resident in HBM --------------------------------------------------------------- */
+/* The reference's -r check (util/test_script.sh:78-82: compress, decompress, sort, compare) for the streams the
+ * last spring_b200_reorder_encode* call left in HBM: re-blocking (src/reorder_compress_streams.cpp:83-361, with
+ * pe_encode for paired -r input) -> block decode (src/decompress.cpp:230-320) -> every decoded read compared
+ * base by base with the input read that read_order.bin names, and read_order.bin checked to be a permutation.
+ * Nothing is copied to the host, so it runs at 100 M reads.  After a *_device call the caller's input arrays
+ * must still be alive.  Uses cp->paired_end, preserve_order, num_reads, num_reads_per_block. */
+typedef struct spring_b200_verify {
+  int32_t ok;                       /* 1: every read decoded to its original */
+  uint64_t num_reads, reads_checked;
+  uint64_t base_mismatch_reads, length_mismatch_reads, bad_order;
+  uint64_t num_blocks, block_stream_bytes, decoded_bases;
+} spring_b200_verify;
+int spring_b200_verify_roundtrip(spring_b200_ctx *ctx, const spring_b200_cp *cp, spring_b200_verify *out);
+
 /* ---- the stage before the dictionaries: preprocess's read path ------------------ */
 /* What preprocess does to the sequence lines of the FASTQ input (src/preprocess.cpp:196-207, :293-304,
  * :364-378; record packers src/util.cpp:269-294, :322-348): reads that contain 'N' go to input_N.dna

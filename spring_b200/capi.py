@@ -21,7 +21,7 @@ EXPORTS = [
     "spring_b200_reorder", "spring_b200_reorder_encode_files", "spring_b200_write_streams",
     "spring_b200_bucket_reads", "spring_b200_set_schedule", "spring_b200_fetch_reorder", "spring_b200_set_stream",
     "spring_b200_pe_encode", "spring_b200_reblock_streams", "spring_b200_reblock_files", "spring_b200_pack_reads",
-    "spring_b200_decode_blocks",
+    "spring_b200_decode_blocks", "spring_b200_verify_roundtrip",
 ]
 
 
@@ -80,6 +80,15 @@ class PackedReads(C.Structure):
                 ("num_n", C.c_uint32), ("num_reads", C.c_uint32)]
 
 
+class Verify(C.Structure):
+    _fields_ = [("ok", C.c_int32), ("num_reads", C.c_uint64), ("reads_checked", C.c_uint64), ("base_mismatch_reads", C.c_uint64),
+                ("length_mismatch_reads", C.c_uint64), ("bad_order", C.c_uint64), ("num_blocks", C.c_uint64),
+                ("block_stream_bytes", C.c_uint64), ("decoded_bases", C.c_uint64)]
+
+    def as_dict(self) -> dict:
+        return {f: getattr(self, f) for f, _ in self._fields_}
+
+
 class Stats(C.Structure):
     _fields_ = [("num_chains", C.c_uint32), ("unmatched", C.c_uint32), ("rounds", C.c_uint64),
                 ("lost_proposals", C.c_uint64), ("probes_issued", C.c_uint64), ("probes_seq", C.c_uint64),
@@ -125,6 +134,7 @@ def load():
                                                   C.POINTER(Decoded)]
         lib.spring_b200_pack_reads.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int,
                                                C.POINTER(PackedReads)]
+        lib.spring_b200_verify_roundtrip.argtypes = [C.c_void_p, C.POINTER(CP), C.POINTER(Verify)]
         _lib = lib
     return _lib
 
@@ -393,6 +403,12 @@ class Context:
                                                         C.byref(cp), C.byref(out)))
         offs = _view(out.offsets, out.num_reads + 1, np.uint64).copy()
         return _view(out.bases, int(offs[-1]) if len(offs) else 0, np.uint8).copy(), offs
+
+    def verify_roundtrip(self, cp: CP) -> dict:
+        """Re-block -> block decode -> exact compare with the input of the last reorder_encode* call, all in HBM."""
+        v = Verify()
+        self._check(self._lib.spring_b200_verify_roundtrip(self._h, C.byref(cp), C.byref(v)))
+        return v.as_dict()
 
     def reblock_files(self, temp_dir: str, cp: CP) -> None:
         self._check(self._lib.spring_b200_reblock_files(self._h, temp_dir.encode(), C.byref(cp)))

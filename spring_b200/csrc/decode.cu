@@ -233,7 +233,7 @@ __global__ void k_dec_reads(DecArgs a) {
       rc = a.rc_pair[o.pair] == '0' ? (rc1 == 'd' ? 'r' : 'd') : (rc1 == 'd' ? 'd' : 'r');
     }
   }
-  if (pos + (unsigned long long)len > a.seq_len) { *a.err = 5; return; }
+  if (pos > a.seq_len || (unsigned long long)len > a.seq_len - pos) { *a.err = 5; return; }  // no wrap for pos near 2^64
   const bool rev = rc != 'd';
   // consensus window, written in the read's final orientation; noise positions refer to the forward window
   for (int k = 0; k < len; k++) {

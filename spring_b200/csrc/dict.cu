@@ -168,6 +168,8 @@ void build_dictionary(Ctx &c, const uint64_t *reads, const uint16_t *lens, const
     SB_CUDA(cudaStreamSynchronize(st));
     out.numkeys = h_count[2];
   }
+  // slot indices are 32 bits: at most 2^30 unique keys per dictionary (capacity 2^31)
+  if (out.numkeys > (1u << 30)) throw LimitError("dictionary: more than 2^30 unique keys in one GPU shard");
   uint32_t cap = 16;
   while (cap < 2ull * out.numkeys) cap <<= 1;
   out.capacity = cap;

@@ -91,6 +91,15 @@ struct DecodeDev {
 void run_decode_blocks(Ctx &c, const ReblockDev &b, const uint64_t *sizes, const uint8_t *d_seq_packed, uint64_t seq_len,
                        uint64_t num_reads, bool paired, bool preserve, uint32_t block, DecodeDev &out);
 
+// ---- verify.cu : re-block -> block decode -> compare with the input, all in HBM ---------------------------
+struct VerifyReport {
+  uint64_t num_reads = 0, reads_checked = 0;
+  uint64_t base_mismatch_reads = 0, length_mismatch_reads = 0, bad_order = 0;
+  uint64_t num_blocks = 0, block_stream_bytes = 0, decoded_bases = 0;
+};
+void run_verify(Ctx &c, const EncodeDev &e, const uint64_t *reads, const uint16_t *lens, uint32_t num_clean, int W,
+                const NReads &nr, bool paired, bool preserve, uint32_t block, VerifyReport &out);
+
 // ---- pack.cu : preprocess's read path, N split + 2-bit / 4-bit packing -----------
 struct PackDev {
   uint64_t *reads = nullptr; uint16_t *lengths = nullptr;  // clean reads, input order, [num_clean][W] (device)

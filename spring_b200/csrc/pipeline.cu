@@ -27,6 +27,9 @@ struct spring_b200_ctx {
   EncodeDev last_enc{};
   ReorderDev last_ro{};
   bool have_enc = false;
+  // the input of that call, for spring_b200_verify_roundtrip (device pointers; the caller's own for *_device)
+  const uint64_t *last_reads = nullptr; const uint16_t *last_lens = nullptr; uint32_t last_num_clean = 0; int last_W = 1;
+  NReads last_nr{};
   cudaEvent_t ev[8]{};  // 0-5: the hot path's stages, 6-7: around the re-blocking
 };
 
@@ -206,6 +209,7 @@ void run_all(spring_b200_ctx *ctx, const spring_b200_input *in, uint32_t num_cha
   run_encode(c, d.reads, d.lens, in->num_clean, L, ro, nr, in->num_reads, ctx->last_enc);
   ctx->last_ro = ro;
   ctx->have_enc = true;
+  ctx->last_reads = d.reads; ctx->last_lens = d.lens; ctx->last_num_clean = in->num_clean; ctx->last_W = W; ctx->last_nr = nr;
   rec(ctx, 4);
   memset(out, 0, sizeof(*out));
   if (host_in) {
@@ -599,11 +603,10 @@ int spring_b200_pe_encode(spring_b200_ctx *ctx, const uint32_t *order, uint32_t 
     if (!num_reads) return;
     Ctx &c = ctx->c;
     c.launches = 0;
-    for (uint32_t i = 0; i < num_reads; i++)
-      if (order[i] >= num_reads) throw ArgError("pe_encode: order is not a permutation of 0..num_reads-1");
     uint32_t *d_in = c.pool.dev<uint32_t>("pe.in", num_reads), *d_out = c.pool.dev<uint32_t>("pe.out", num_reads);
     SB_CUDA(cudaMemcpyAsync(d_in, order, sizeof(uint32_t) * num_reads, cudaMemcpyHostToDevice, c.stream));
-    run_pe_encode(c, d_in, num_reads, d_out);
+    try { run_pe_encode(c, d_in, num_reads, d_out); }  // checks on the device that order is a permutation
+    catch (const LimitError &e) { throw ArgError(e.what()); }
     SB_CUDA(cudaMemcpyAsync(order_out, d_out, sizeof(uint32_t) * num_reads, cudaMemcpyDeviceToHost, c.stream));
     SB_CUDA(cudaStreamSynchronize(c.stream));
     ctx->stats.gpu_launches = c.launches;
@@ -613,6 +616,26 @@ int spring_b200_pe_encode(spring_b200_ctx *ctx, const uint32_t *order, uint32_t 
 int spring_b200_reblock_streams(spring_b200_ctx *ctx, const spring_b200_streams *streams, const spring_b200_cp *cp,
                                 spring_b200_blocks *out) {
   return guarded(ctx, [&] { reblock(ctx, streams, cp, out); });
+}
+
+int spring_b200_verify_roundtrip(spring_b200_ctx *ctx, const spring_b200_cp *cp, spring_b200_verify *out) {
+  return guarded(ctx, [&] {
+    if (!cp || !out) throw ArgError("null argument");
+    if (!ctx->have_enc) throw ArgError("no streams resident on the device (run spring_b200_reorder_encode* first)");
+    if (cp->num_reads_per_block <= 0) throw ArgError("cp.num_reads_per_block <= 0");
+    if (ctx->last_enc.num_reads != cp->num_reads) throw ArgError("streams hold a different number of reads than cp.num_reads");
+    Ctx &c = ctx->c;
+    c.launches = 0;
+    VerifyReport r;
+    run_verify(c, ctx->last_enc, ctx->last_reads, ctx->last_lens, ctx->last_num_clean, ctx->last_W, ctx->last_nr,
+               cp->paired_end != 0, cp->preserve_order != 0, (uint32_t)cp->num_reads_per_block, r);
+    memset(out, 0, sizeof(*out));
+    out->num_reads = r.num_reads; out->reads_checked = r.reads_checked; out->base_mismatch_reads = r.base_mismatch_reads;
+    out->length_mismatch_reads = r.length_mismatch_reads; out->bad_order = r.bad_order; out->num_blocks = r.num_blocks;
+    out->block_stream_bytes = r.block_stream_bytes; out->decoded_bases = r.decoded_bases;
+    out->ok = (r.reads_checked == r.num_reads && !r.base_mismatch_reads && !r.length_mismatch_reads && !r.bad_order) ? 1 : 0;
+    ctx->stats.gpu_launches = c.launches;
+  });
 }
 
 int spring_b200_reblock_files(spring_b200_ctx *ctx, const char *temp_dir, const spring_b200_cp *cp) {

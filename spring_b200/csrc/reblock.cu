@@ -24,9 +24,14 @@ namespace {
 static inline uint32_t grid_for(uint64_t n, int block) { return (uint32_t)((n + block - 1) / block); }
 
 // ---- pe_encode ----------------------------------------------------------------------------------------
-__global__ void k_invert(const uint32_t *__restrict__ order, uint32_t n, uint32_t *inverse) {
+// inverse[] starts as all ones; an index out of range or taken twice sets *err instead of being used
+// (order comes from a file or a caller when the streams are not the library's own)
+__global__ void k_invert(const uint32_t *__restrict__ order, uint32_t n, uint32_t *inverse, int *err) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) inverse[order[i]] = i;
+  if (i >= n) return;
+  const uint32_t o = order[i];
+  if (o >= n) { *err = 1; return; }
+  if (atomicExch(inverse + o, i) != 0xFFFFFFFFu) *err = 1;
 }
 __global__ void k_is_file1(const uint32_t *__restrict__ order, uint32_t n, uint32_t half, uint32_t *f1) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -239,7 +244,16 @@ void run_pe_encode(Ctx &c, const uint32_t *order, uint32_t n, uint32_t *slot) {
   if (!n) return;
   const uint32_t half = n / 2;
   uint32_t *inverse = c.pool.dev<uint32_t>("rb.inverse", n), *f1 = c.pool.dev<uint32_t>("rb.f1", n), *rank1 = c.pool.dev<uint32_t>("rb.rank1", n);
-  k_invert<<<grid_for(n, 256), 256, 0, st>>>(order, n, inverse);
+  int *err = c.pool.dev<int>("rb.perm_err", 1);
+  SB_CUDA(cudaMemsetAsync(err, 0, sizeof(int), st));
+  SB_CUDA(cudaMemsetAsync(inverse, 0xFF, sizeof(uint32_t) * n, st));
+  k_invert<<<grid_for(n, 256), 256, 0, st>>>(order, n, inverse, err);
+  {
+    int bad = 0;
+    SB_CUDA(cudaMemcpyAsync(&bad, err, sizeof(int), cudaMemcpyDeviceToHost, st));
+    SB_CUDA(cudaStreamSynchronize(st));
+    if (bad) throw LimitError("pe_encode: order is not a permutation of 0..num_reads-1");
+  }
   k_is_file1<<<grid_for(n, 256), 256, 0, st>>>(order, n, half, f1);
   size_t need = 0;
   cub::DeviceScan::ExclusiveSum(nullptr, need, f1, rank1, (int)n, st);
@@ -277,8 +291,15 @@ void run_reblock(Ctx &c, const EncodeDev &e, bool paired, bool preserve, uint32_
     if (paired && !preserve) run_pe_encode(c, e.order, n, slot);
     else SB_CUDA(cudaMemcpyAsync(slot, e.order, sizeof(uint32_t) * n, cudaMemcpyDeviceToDevice, st));
     uint32_t *inv = c.pool.dev<uint32_t>("rb.inv", n);
-    k_invert<<<grid_for(n, 256), 256, 0, st>>>(slot, n, inv);
+    int *err = c.pool.dev<int>("rb.perm_err", 1);
+    SB_CUDA(cudaMemsetAsync(err, 0, sizeof(int), st));
+    SB_CUDA(cudaMemsetAsync(inv, 0xFF, sizeof(uint32_t) * n, st));
+    k_invert<<<grid_for(n, 256), 256, 0, st>>>(slot, n, inv, err);
     c.launches++;
+    int bad = 0;
+    SB_CUDA(cudaMemcpyAsync(&bad, err, sizeof(int), cudaMemcpyDeviceToHost, st));
+    SB_CUDA(cudaStreamSynchronize(st));
+    if (bad) throw LimitError("reblock: read_order.bin is not a permutation of 0..num_reads-1");
     a.inv = inv;
     out.order = slot;
   }

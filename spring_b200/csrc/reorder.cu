@@ -54,7 +54,6 @@ struct ChainArgs {
   uint32_t num_chains, per;
   unsigned long long *barrier; int *active; unsigned long long *ctr;
   unsigned long long max_rounds;
-  int *overflow;  // set when a packed u16 column count would overflow
   uint32_t G;            // scan_bin: candidates verified per pass = 32 / W
   unsigned leader_mask;  // scan_bin: lanes g * W, g < G
   int generic_update;    // debugging aid: always use the per-column update_ref
@@ -85,6 +84,18 @@ __device__ __forceinline__ void grid_barrier(unsigned long long *ctr, unsigned l
   __syncthreads();
 }
 
+// cnt[col] packs the four per-base counts of a column as u16 fields, rows A,C,T,G (reorder.h:120-123);
+// 2-bit read codes are A0 G1 C2 T3 -> field shift 0, 48, 16, 32.  The reference counts in int
+// (reorder.h:383-384); here a column whose field reaches 0xFFFF is halved (all four fields >> 1), which
+// keeps the order of the counts -- and so the majority -- instead of failing: exact up to 65534 reads
+// stacked on one column, an approximation of the vote beyond (the output stays decodable either way).
+__device__ __forceinline__ uint64_t count_add(uint64_t v, int b) {
+  const int sh = (int)((0x20103000u >> (8 * b)) & 0xFFu);
+  v += 1ull << sh;
+  if (((v >> sh) & 0xFFFFull) == 0xFFFFull) v = (v >> 1) & 0x7FFF7FFF7FFF7FFFull;
+  return v;
+}
+
 // Fold the read staged in curw (cur_len bases; rev: use its reverse complement) into the window.
 // new column i takes old column i+delta when that lies in [0, old_len), else starts from zero;
 // the read covers new columns [cs, cs+cur_len).  Then majority -> ref, RC(ref) -> revref.
@@ -95,9 +106,7 @@ __device__ __forceinline__ void grid_barrier(unsigned long long *ctr, unsigned l
 // that was already rewritten is read again: column i = q*fold + r ends up as
 // old[r] + sum_{t=1..q} e(read base at t*fold + r) rather than old[i - fold] + e(read base at i).
 __device__ __noinline__ void update_ref(uint64_t *ref, uint64_t *revref, const uint64_t *curw, uint64_t *cnt, int W, int lane,
-                           int old_len, int delta, int cs, int cur_len, bool rev, int new_len, int fold, int *overflow) {
-  // cnt[col] packs the four per-base counts of a column as u16 fields, rows A,C,T,G
-  // (reorder.h:120-123); 2-bit read codes are A0 G1 C2 T3 -> field shift 0, 48, 16, 32
+                           int old_len, int delta, int cs, int cur_len, bool rev, int new_len, int fold) {
   const int nchunks = (new_len + 31) >> 5;
   for (int cc = 0; cc < nchunks; cc++) {
     const int ck = delta >= 0 ? cc : nchunks - 1 - cc;  // move direction decides the safe order
@@ -110,8 +119,7 @@ __device__ __noinline__ void update_ref(uint64_t *ref, uint64_t *revref, const u
         const int r = i % fold, q = i / fold;
         v = cnt[r];
         for (int t = 1; t < q; t++) {  // the t == q term is the read's own base at column i, added below
-          const int b = 3 - base_code(curw, cur_len - 1 - (t * fold + r));
-          v += 1ull << ((0x20103000u >> (8 * b)) & 0xFFu);
+          v = count_add(v, 3 - base_code(curw, cur_len - 1 - (t * fold + r)));
         }
       } else {
         v = cnt[src];
@@ -122,8 +130,7 @@ __device__ __noinline__ void update_ref(uint64_t *ref, uint64_t *revref, const u
     if (in) {
       const int ci = i - cs;
       if (ci >= 0 && ci < cur_len) {
-        const int b = rev ? 3 - base_code(curw, cur_len - 1 - ci) : base_code(curw, ci);
-        v += 1ull << ((0x20103000u >> (8 * b)) & 0xFFu);
+        v = count_add(v, rev ? 3 - base_code(curw, cur_len - 1 - ci) : base_code(curw, ci));
       }
       cnt[i] = v;
       const uint32_t f0 = (uint32_t)v & 0xFFFFu, f1 = (uint32_t)(v >> 16) & 0xFFFFu;
@@ -132,7 +139,6 @@ __device__ __noinline__ void update_ref(uint64_t *ref, uint64_t *revref, const u
       if (f1 > mx) { mx = f1; code = 2; }
       if (f2 > mx) { mx = f2; code = 3; }
       if (f3 > mx) { mx = f3; code = 1; }
-      if (mx == 0xFFFFu) *overflow = 1;  // a u16 field is about to wrap: > 65535 reads stacked on one column
     }
     // 32 two-bit codes -> one 64-bit word: lanes 0-15 fill the low half, 16-31 the high half
     const uint32_t part = code << (2 * (lane & 15));
@@ -188,7 +194,7 @@ __device__ __forceinline__ uint64_t revcomp_word(const uint64_t *a, int W, int l
 //     of them, the match passed the Hamming test on exactly these bits -- need the vote.
 // curw is overwritten with the read as oriented in the contig.
 __device__ void update_ref_fast(uint64_t *ref, uint64_t *revref, uint64_t *curw, uint64_t *cnt, int W, int lane, int old_len,
-                                int delta, int cs, int cur_len, bool rev, int new_len, int *overflow) {
+                                int delta, int cs, int cur_len, bool rev, int new_len) {
   if (rev) {
     uint64_t o = 0;
     if (lane < W) o = revcomp_word(curw, W, cur_len, lane);
@@ -213,7 +219,9 @@ __device__ void update_ref_fast(uint64_t *ref, uint64_t *revref, uint64_t *curw,
         const int sh = ((b ^ (b >> 1)) & 1) << 4;
         uint32_t f;
         if (b & 1) { v.y += 1u << sh; f = v.y; } else { v.x += 1u << sh; f = v.x; }
-        if (((f >> sh) & 0xFFFFu) == 0xFFFFu) *overflow = 1;  // > 65535 reads stacked on one column
+        if (((f >> sh) & 0xFFFFu) == 0xFFFFu) {  // saturated: halve the column (count_add)
+          v.x = (v.x >> 1) & 0x7FFF7FFFu; v.y = (v.y >> 1) & 0x7FFF7FFFu;
+        }
       }
       reinterpret_cast<uint2 *>(cnt)[i] = v;
     }
@@ -496,13 +504,6 @@ __global__ void __launch_bounds__(WPB * 32, MINB) k_chains(ChainArgs a) {
   };
 
   // claim bit + "remove from both dictionaries" (reorder.h:458-472): one decrement per bin
-  auto claim = [&](uint32_t rid) {
-    if (lane == 0) atomicOr(a.claimed + (rid >> 5), 1u << (rid & 31));
-    if (lane < kNumDict) {
-      const uint32_t sidx = __ldg(a.dict[lane].slot_of_read + rid);
-      if (sidx != 0xFFFFFFFFu) atomicSub(&a.dict[lane].slots[sidx].live, 1u);
-    }
-  };
   auto claim_pre = [&](uint32_t rid, uint32_t sidx) {  // slot index fetched in phase A
     if (lane == 0) atomicOr(a.claimed + (rid >> 5), 1u << (rid & 31));
     if (lane < kNumDict && sidx != 0xFFFFFFFFu) atomicSub(&a.dict[lane].slots[sidx].live, 1u);
@@ -514,8 +515,8 @@ __global__ void __launch_bounds__(WPB * 32, MINB) k_chains(ChainArgs a) {
   // fold the read staged in curw into the window: word-parallel fast path, or the per-column generic
   // version for the reference's in-place "fold" quirk (and on request, as a cross-check)
   auto upd = [&](int old_len, int delta, int cs, int cur_len, bool rev, int new_len, int fold) {
-    if (fold > 0 || a.generic_update) update_ref(ref, revref, curw, cnt, W, lane, old_len, delta, cs, cur_len, rev, new_len, fold, a.overflow);
-    else update_ref_fast(ref, revref, curw, cnt, W, lane, old_len, delta, cs, cur_len, rev, new_len, a.overflow);
+    if (fold > 0 || a.generic_update) update_ref(ref, revref, curw, cnt, W, lane, old_len, delta, cs, cur_len, rev, new_len, fold);
+    else update_ref_fast(ref, revref, curw, cnt, W, lane, old_len, delta, cs, cur_len, rev, new_len);
   };
   // the read must already be staged in curw
   auto new_contig = [&](uint32_t rid) {  // updaterefcount(..., resetcount = true, rev = false) + reorder.h:426-430,:601-612
@@ -531,10 +532,23 @@ __global__ void __launch_bounds__(WPB * 32, MINB) k_chains(ChainArgs a) {
     const uint32_t first = cid * a.per;
     slice_lo = (int)first;
     cursor = cid == a.num_chains - 1 ? (int)a.N - 1 : (int)((cid + 1) * a.per) - 1;
-    claim(first);
-    c_unmatched++;
-    stage_read(first);
-    new_contig(first);
+    // reorder.h:411-419: a thread gives up its start read if somebody already took it.  Chains of the
+    // free-running schedule start whenever their block gets an SM, so an earlier chain may have claimed
+    // `first` through a dictionary match: test-and-set, and on failure pick from the own slice instead.
+    unsigned old = 0;
+    if (lane == 0) old = atomicOr(a.claimed + (first >> 5), 1u << (first & 31));
+    old = __shfl_sync(FULL, old, 0);
+    if ((old >> (first & 31)) & 1u) {
+      state = ST_NEWREAD;
+    } else {
+      if (lane < kNumDict) {
+        const uint32_t sidx = __ldg(a.dict[lane].slot_of_read + first);
+        if (sidx != 0xFFFFFFFFu) atomicSub(&a.dict[lane].slots[sidx].live, 1u);
+      }
+      c_unmatched++;
+      stage_read(first);
+      new_contig(first);
+    }
   }
   unsigned long long cy_search = 0, cy_wait_a = 0, cy_commit = 0, cy_wait_b = 0;
   long long t_last = clock64();
@@ -889,7 +903,6 @@ void run_reorder(Ctx &c, const uint64_t *reads, const uint16_t *lens, uint32_t n
   uint32_t *off_single = c.pool.dev<uint32_t>("ro.off_single", nslots + 1);
   unsigned long long *sync = c.pool.dev<unsigned long long>("ro.sync", 2 + CTR_N);
   a.barrier = sync; a.active = reinterpret_cast<int *>(sync + 1); a.ctr = sync + 2;
-  a.overflow = reinterpret_cast<int *>(sync + 1) + 1;
   a.chain_dbg = getenv("SPRING_B200_CHAIN_DBG") ? c.pool.dev<unsigned long long>("ro.chain_dbg", 2 * (size_t)nslots + 2) : nullptr;
   if (a.chain_dbg) SB_CUDA(cudaMemsetAsync(a.chain_dbg, 0, (2 * (size_t)nslots + 2) * sizeof(unsigned long long), st));
   a.num_chains = C; a.per = n / C;
@@ -928,7 +941,6 @@ void run_reorder(Ctx &c, const uint64_t *reads, const uint16_t *lens, uint32_t n
   uint32_t *htot = reinterpret_cast<uint32_t *>(h + CTR_N);
   SB_CUDA(cudaMemcpyAsync(htot, off_aligned + nslots, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
   SB_CUDA(cudaMemcpyAsync(htot + 1, off_single + nslots, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-  SB_CUDA(cudaMemcpyAsync(htot + 2, a.overflow, sizeof(int), cudaMemcpyDeviceToHost, st));
   SB_CUDA(cudaStreamSynchronize(st));
   SB_CUDA(cudaGetLastError());
   if (a.chain_dbg) {
@@ -944,7 +956,6 @@ void run_reorder(Ctx &c, const uint64_t *reads, const uint16_t *lens, uint32_t n
             (pct(ends, .5) - t0) / 1e6, (pct(ends, .9) - t0) / 1e6, (pct(ends, .99) - t0) / 1e6, (ends.back() - t0) / 1e6);
   }
   if (h[CTR_ABORT]) throw LimitError("reorder: watchdog hit (round limit) -- chain kernel did not converge");
-  if (htot[2]) throw LimitError("reorder: more than 65535 reads stacked on one consensus column (u16 column counts)");
   out.num = htot[0];
   out.num_singletons = htot[1];
   if (out.num + out.num_singletons != n) throw LimitError("reorder: records do not cover all reads");

@@ -75,15 +75,25 @@ def write_dna_file(path: str, packed: np.ndarray, lengths: np.ndarray) -> None:
     with open(path, "wb") as f:
         if n and (lengths == lengths[0]).all():
             nb = (int(lengths[0]) + 3) // 4
-            rec = np.empty((n, 2 + nb), dtype=np.uint8)
-            rec[:, 0] = lengths[0] & 0xFF
-            rec[:, 1] = lengths[0] >> 8
-            rec[:, 2:] = raw[:, :nb]
-            f.write(rec.tobytes())
-        else:
-            for i in range(n):
-                f.write(struct.pack("<H", int(lengths[i])))
-                f.write(raw[i, : (int(lengths[i]) + 3) // 4].tobytes())
+            step = 1 << 22
+            for lo in range(0, n, step):  # chunked: a 100 M-read file is 4 GB
+                m = min(step, n - lo)
+                rec = np.empty((m, 2 + nb), dtype=np.uint8)
+                rec[:, 0] = lengths[0] & 0xFF
+                rec[:, 1] = lengths[0] >> 8
+                rec[:, 2:] = raw[lo:lo + m, :nb]
+                f.write(rec.tobytes())
+        else:  # variable lengths: records {u16 len; ceil(len/4) B} selected out of a padded matrix, chunk by chunk
+            step = 1 << 20
+            for lo in range(0, n, step):
+                ln = lengths[lo:lo + step].astype(np.int64)
+                nb = (ln + 3) // 4
+                width = 2 + int(nb.max())
+                rec = np.zeros((len(ln), width), dtype=np.uint8)
+                rec[:, 0] = ln & 0xFF
+                rec[:, 1] = ln >> 8
+                rec[:, 2:] = raw[lo:lo + step, : width - 2]
+                f.write(rec[np.arange(width)[None, :] < (2 + nb)[:, None]].tobytes())
 
 
 def read_dna_file(path: str, num_reads: int, max_readlen: int) -> tuple[np.ndarray, np.ndarray]:

@@ -53,6 +53,8 @@ def exchange_by_bucket(reads: torch.Tensor, lens: torch.Tensor, max_readlen: int
         bucket_fn = gpu_bucket_fn(_default_ctx[key], max_readlen)
     bucket = bucket_fn(reads, lens, world)
     # stable sort of one-byte keys (a single radix pass) instead of an int64 argsort: rank order = input order
+    if world > 256:
+        raise ValueError("exchange_by_bucket: one-byte owner keys, world <= 256")
     order = torch.argsort(bucket.to(torch.uint8), stable=True)
     send_counts = torch.bincount(bucket.long(), minlength=world)
     recv_counts = torch.empty_like(send_counts)
@@ -64,9 +66,11 @@ def exchange_by_bucket(reads: torch.Tensor, lens: torch.Tensor, max_readlen: int
     # u32 global id travel as one fused byte record (every backend moves uint8; gloo has no int16 all-to-all)
     fields = [reads, lens] + ([ids] if ids is not None else [])
     n = reads.shape[0]
-    parts = [x[order].contiguous().view(torch.uint8).reshape(n, -1) for x in fields]
     widths = [int(x.element_size() * int(np.prod(x.shape[1:], dtype=np.int64))) for x in fields]
-    rec = torch.cat(parts, dim=1) if n else torch.empty((0, sum(widths)), dtype=torch.uint8, device=reads.device)
+    if n:  # explicit widths: reshape(n, -1) cannot infer a width for n == 0 (a rank without reads must still join the collective)
+        rec = torch.cat([x[order].contiguous().view(torch.uint8).reshape(n, w) for x, w in zip(fields, widths)], dim=1)
+    else:
+        rec = torch.empty((0, sum(widths)), dtype=torch.uint8, device=reads.device)
     got = torch.empty((n_recv, sum(widths)), dtype=torch.uint8, device=reads.device)
     dist.all_to_all_single(got, rec, output_split_sizes=rc, input_split_sizes=sc, group=group)
     out, off = [], 0

@@ -170,3 +170,51 @@ def write_fastq(rs: ReadSet, path1: str, path2: str | None = None, quality: bool
                 f.write(b"@r%d/%d\n" % (i - lo, mate))
                 f.write(s + b"\n+\n")
                 f.write(b"I" * len(s) + b"\n")
+
+
+@dataclass
+class DeviceInput:
+    """The hot path's input with the clean reads resident on the GPU (what spring_b200_pack_reads with
+    keep_on_device leaves), built in chunks so that a 100 M-read set never needs more than its own size."""
+    reads: torch.Tensor         # int64[N_clean, W] (bit pattern of the uint64 rows)
+    lengths: torch.Tensor       # int16[N_clean]
+    n_seqs: list                # reads with N, ASCII
+    order_n: np.ndarray         # uint32 original index of every N read, ascending
+    num_reads: int
+    num_clean: tuple            # cp.num_reads_clean[2]
+    max_readlen: int
+    paired: bool
+
+    @property
+    def n_records(self) -> bytes:
+        return dnaio.write_dnaN_records(self.n_seqs)
+
+
+def to_device_input(rs: ReadSet, chunk: int = 1 << 20) -> DeviceInput:
+    """Same split as to_hotpath_input (preprocess.cpp:293-304, :364-378), on rs.codes' device."""
+    codes, lens = rs.codes, rs.lengths
+    dev, n, L = codes.device, rs.num_reads, codes.shape[1]
+    w = dnaio.words_per_read(rs.max_readlen)
+    ar = torch.arange(L, device=dev)[None, :]
+    has_n = torch.empty((n,), dtype=torch.bool, device=dev)
+    for lo in range(0, n, chunk):
+        hi = min(lo + chunk, n)
+        has_n[lo:hi] = ((codes[lo:hi] == 4) & (ar < lens[lo:hi, None])).any(dim=1)
+    n_clean = int((~has_n).sum())
+    reads = torch.empty((n_clean, w), dtype=torch.int64, device=dev)
+    lengths = torch.empty((n_clean,), dtype=torch.int16, device=dev)
+    at = 0
+    for lo in range(0, n, chunk):
+        hi = min(lo + chunk, n)
+        keep = ~has_n[lo:hi]
+        c, l = codes[lo:hi][keep], lens[lo:hi][keep]
+        m = int(c.shape[0])
+        reads[at:at + m] = pack_reads(c, l, rs.max_readlen)
+        lengths[at:at + m] = l.to(torch.int16)
+        at += m
+    n_idx = torch.nonzero(has_n).squeeze(1)
+    ccpu, lcpu = codes[n_idx].cpu().numpy(), lens[n_idx].cpu().numpy()
+    n_seqs = [dnaio.CODE4CHAR[ccpu[i, : lcpu[i]]].tobytes() for i in range(len(lcpu))]
+    half = n // 2 if rs.paired else n
+    c0 = int((~has_n[:half]).sum())
+    return DeviceInput(reads, lengths, n_seqs, n_idx.cpu().numpy().astype(np.uint32), n, (c0, n_clean - c0), rs.max_readlen, rs.paired)

@@ -9,7 +9,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libspring_b200.so")
-SOURCES = ["dict.cu", "reorder.cu", "encode.cu", "reblock.cu", "decode.cu", "pack.cu", "bucket.cu", "verify.cu", "pipeline.cu"]
+SOURCES = ["dict.cu", "reorder.cu", "chains2.cu", "encode.cu", "reblock.cu", "decode.cu", "pack.cu", "bucket.cu", "verify.cu", "pipeline.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "-Xcompiler", "-Wno-unused-function",
@@ -24,7 +24,7 @@ def _stale(target: str, deps: list[str]) -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    headers = [os.path.join(CSRC, h) for h in ("common.cuh", "kernels.cuh")] + [os.path.join(HERE, "..", "include", "spring_b200.h")]
+    headers = [os.path.join(CSRC, h) for h in ("common.cuh", "kernels.cuh", "chain_common.cuh")] + [os.path.join(HERE, "..", "include", "spring_b200.h")]
     objs, jobs = [], []
     for s in SOURCES:
         src, obj = os.path.join(CSRC, s), os.path.join(CSRC, s.replace(".cu", ".o"))

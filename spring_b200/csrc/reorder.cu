@@ -32,38 +32,13 @@
 // for the life of the kernel (DESIGN.md sections 5, 6).
 #include <algorithm>
 #include <cub/cub.cuh>
-#include "kernels.cuh"
+#include "chain_common.cuh"
 
 namespace sb {
 
+using namespace chain;
+
 namespace {
-
-constexpr unsigned FULL = 0xFFFFFFFFu;
-constexpr const char *kChainCfgDefault = "8x4";  // 32 chains per SM (64 registers, a few spills) beat 24 spill-free ones
-enum { ST_SEARCH = 0, ST_NEWREAD = 1, ST_DONE = 2 };
-enum { CTR_UNMATCHED = 0, CTR_ROUNDS, CTR_LOST, CTR_PROBES_ISSUED, CTR_PROBES_SEQ, CTR_COMPARES, CTR_ABORT,
-       CTR_CYC_SEARCH, CTR_CYC_WAIT_A, CTR_CYC_COMMIT, CTR_CYC_WAIT_B, CTR_SLOT_PROBES, CTR_N };
-
-struct ChainArgs {
-  const uint64_t *reads; const uint16_t *lens; uint32_t N; int L, W, Lp, maxshift;
-  DictView dict[2];
-  uint32_t *claimed;   // bitmap, one bit per read
-  uint32_t *winner;    // [N], kNoWinner until proposed
-  uint32_t *rec_chain; uint32_t *rec_k; int64_t *rec_pos; uint8_t *rec_meta;
-  uint32_t *chain_aligned; uint32_t *chain_single;
-  uint32_t num_chains, per;
-  unsigned long long *barrier; int *active; unsigned long long *ctr;
-  unsigned long long max_rounds;
-  uint32_t G;            // scan_bin: candidates verified per pass = 32 / W
-  unsigned leader_mask;  // scan_bin: lanes g * W, g < G
-  int generic_update;    // debugging aid: always use the per-column update_ref
-  int steal_probes;      // free-running schedule: random slices an idle chain probes for an unclaimed read (0 = off)
-  unsigned long long *chain_dbg;  // [2 * chains]: steps, globaltimer ns at finish (profiling aid)
-};
-
-__device__ __forceinline__ bool is_claimed(const uint32_t *claimed, uint32_t rid) {
-  return (__ldcg(claimed + (rid >> 5)) >> (rid & 31)) & 1u;
-}
 
 // work/wait: SM cycles thread 0 of the block spent between barriers / spinning in this one
 __device__ __forceinline__ void grid_barrier(unsigned long long *ctr, unsigned long long &target, long long &t_last,
@@ -82,18 +57,6 @@ __device__ __forceinline__ void grid_barrier(unsigned long long *ctr, unsigned l
     wait += t_last - t_arr;
   }
   __syncthreads();
-}
-
-// cnt[col] packs the four per-base counts of a column as u16 fields, rows A,C,T,G (reorder.h:120-123);
-// 2-bit read codes are A0 G1 C2 T3 -> field shift 0, 48, 16, 32.  The reference counts in int
-// (reorder.h:383-384); here a column whose field reaches 0xFFFF is halved (all four fields >> 1), which
-// keeps the order of the counts -- and so the majority -- instead of failing: exact up to 65534 reads
-// stacked on one column, an approximation of the vote beyond (the output stays decodable either way).
-__device__ __forceinline__ uint64_t count_add(uint64_t v, int b) {
-  const int sh = (int)((0x20103000u >> (8 * b)) & 0xFFu);
-  v += 1ull << sh;
-  if (((v >> sh) & 0xFFFFull) == 0xFFFFull) v = (v >> 1) & 0x7FFF7FFF7FFF7FFFull;
-  return v;
 }
 
 // Fold the read staged in curw (cur_len bases; rev: use its reverse complement) into the window.
@@ -167,22 +130,6 @@ __device__ __noinline__ void update_ref(uint64_t *ref, uint64_t *revref, const u
   __syncwarp();
 }
 
-// word w of the reverse complement of the len-base sequence a[] (W words, zero beyond len): reverse the
-// 2-bit groups of the whole array, complement, shift the padding out (reorder.h:215-217 by bit tricks)
-__device__ __forceinline__ uint64_t revcomp_word(const uint64_t *a, int W, int len, int w) {
-  const int pad = 64 * W - 2 * len, ws = pad >> 6, bs = pad & 63;
-  uint64_t a0 = 0, a1 = 0;
-  if (w + ws < W) {
-    const uint64_t x = __brevll(a[W - 1 - (w + ws)]);
-    a0 = ~(((x & 0x5555555555555555ull) << 1) | ((x >> 1) & 0x5555555555555555ull));
-  }
-  if (w + ws + 1 < W) {
-    const uint64_t x = __brevll(a[W - 2 - (w + ws)]);
-    a1 = ~(((x & 0x5555555555555555ull) << 1) | ((x >> 1) & 0x5555555555555555ull));
-  }
-  return bs ? (a0 >> bs) | (a1 << (64 - bs)) : a0;
-}
-
 // update_ref for every case but the fold quirk (delta >= 0): same result as the generic version above,
 // with the consensus rebuilt by word operations instead of a majority vote per column.
 //   * counts: one pass over the columns, 32 per step: cnt[i] = cnt[i + delta] (+ the read's base);
@@ -217,11 +164,9 @@ __device__ void update_ref_fast(uint64_t *ref, uint64_t *revref, uint64_t *curw,
         // word, codes 1 and 2 in the upper half of their word
         const int b = base_code(curw, (int)ci);
         const int sh = ((b ^ (b >> 1)) & 1) << 4;
-        uint32_t f;
-        if (b & 1) { v.y += 1u << sh; f = v.y; } else { v.x += 1u << sh; f = v.x; }
-        if (((f >> sh) & 0xFFFFu) == 0xFFFFu) {  // saturated: halve the column (count_add)
-          v.x = (v.x >> 1) & 0x7FFF7FFFu; v.y = (v.y >> 1) & 0x7FFF7FFFu;
-        }
+        const uint32_t f = (b & 1) ? v.y : v.x;
+        const uint32_t inc = ((f >> sh) & 0xFFFFu) != 0xFFFFu ? 1u << sh : 0u;  // counts saturate at 65535 (count_add)
+        if (b & 1) v.y += inc; else v.x += inc;
       }
       reinterpret_cast<uint2 *>(cnt)[i] = v;
     }
@@ -343,14 +288,6 @@ __device__ bool scan_bin(const ChainArgs &a, const DictView &d, uint32_t bs, uin
 // batch b = 0, 1, ...; a chain that finds nothing continues with the next batch in the next round
 // (bounded work per round keeps the lock-step chains balanced; claims only grow, so earlier batches
 // cannot turn productive later -- same result as a full search, see oracle/spring_oracle.c).
-// bits [pos, pos + nbits) of a bitset that is followed by one zero word (ref / revref in shared memory):
-// no bounds checks, pos < 64 W
-__device__ __forceinline__ uint64_t window_key(const uint64_t *a, int pos, int nbits) {
-  const int k = pos >> 6, bs = pos & 63;
-  const uint64_t v = (a[k] >> bs) | ((a[k + 1] << 1) << (63 - bs));
-  return nbits < 64 ? v & ((1ull << nbits) - 1ull) : v;
-}
-
 __device__ bool chain_search(const ChainArgs &a, const uint64_t *ref, const uint64_t *revref, int ref_len, int lane, int grp,
                              int wig, int b, int S, uint32_t &prop_rid, int &prop_shift, int &prop_rev, uint32_t &probes_issued,
                              uint32_t &probes_seq, uint32_t &compares, uint32_t &slot_probes) {
@@ -858,32 +795,49 @@ void run_reorder(Ctx &c, const uint64_t *reads, const uint16_t *lens, uint32_t n
   if (n == 0) return;
 
   const bool lockstep = c.lockstep;
-  // launch configuration: warps per block x minimum blocks per SM.  The deterministic schedule is a
-  // cooperative launch and keeps 8 x 3; the free-running one defaults to kChainCfgDefault
-  // (SPRING_B200_KCFG=8x3|8x4|4x7 overrides it: occupancy experiments).
+  // The deterministic schedule is a cooperative launch of the warp-per-chain kernel below (8 warps x 3 blocks per SM).
+  // The free-running schedule runs chains2.cu: 16-lane chains, two per warp (SPRING_B200_LANES=32: one per warp;
+  // SPRING_B200_CHAINS_V1=1: the round-1 warp-per-chain kernel of this file, kept for A/B measurements, with
+  // SPRING_B200_KCFG=8x3|8x4|8x5|8x6|4x7|4x9 choosing its launch bounds).
   void (*kern)(ChainArgs) = k_chains<true, 8, 3>;
   int kWarpsPerBlock = 8;
-  if (!lockstep) {
-    const char *cfg = getenv("SPRING_B200_KCFG");
-    const std::string want = cfg ? cfg : kChainCfgDefault;
-    if (want == "8x4") { kern = k_chains<false, 8, 4>; kWarpsPerBlock = 8; }
-    else if (want == "8x5") { kern = k_chains<false, 8, 5>; kWarpsPerBlock = 8; }
-    else if (want == "8x6") { kern = k_chains<false, 8, 6>; kWarpsPerBlock = 8; }
-    else if (want == "4x9") { kern = k_chains<false, 4, 9>; kWarpsPerBlock = 4; }
-    else if (want == "4x7") { kern = k_chains<false, 4, 7>; kWarpsPerBlock = 4; }
-    else { kern = k_chains<false, 8, 3>; kWarpsPerBlock = 8; }
+  const bool v1 = lockstep || getenv("SPRING_B200_CHAINS_V1") != nullptr;
+  int lanes = 16;
+  if (const char *e = getenv("SPRING_B200_LANES")) lanes = atoi(e) == 32 ? 32 : 16;
+  uint32_t chains_per_block, max_chains;
+  size_t smem = 0;
+  if (v1) {
+    if (!lockstep) {
+      const char *cfg = getenv("SPRING_B200_KCFG");
+      const std::string want = cfg ? cfg : kChainCfgDefault;
+      if (want == "8x4") { kern = k_chains<false, 8, 4>; kWarpsPerBlock = 8; }
+      else if (want == "8x5") { kern = k_chains<false, 8, 5>; kWarpsPerBlock = 8; }
+      else if (want == "8x6") { kern = k_chains<false, 8, 6>; kWarpsPerBlock = 8; }
+      else if (want == "4x9") { kern = k_chains<false, 4, 9>; kWarpsPerBlock = 4; }
+      else if (want == "4x7") { kern = k_chains<false, 4, 7>; kWarpsPerBlock = 4; }
+      else { kern = k_chains<false, 8, 3>; kWarpsPerBlock = 8; }
+    }
+    smem = kWarpsPerBlock * chain_smem_words(W, Lp) * sizeof(uint64_t);
+    SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    SB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kWarpsPerBlock * 32, smem));
+    if (per_sm < 1) throw CudaError("k_chains does not fit on an SM");
+    chains_per_block = (uint32_t)kWarpsPerBlock;
+    max_chains = (uint32_t)per_sm * c.num_sms * chains_per_block;
+  } else {
+    const Chains2Config cc = chains2_config(W, lanes);
+    if (cc.max_blocks_per_sm < 1) throw CudaError("k_chains2 does not fit on an SM");
+    chains_per_block = (uint32_t)cc.chains_per_block;
+    max_chains = (uint32_t)cc.max_blocks_per_sm * c.num_sms * chains_per_block;
   }
-  const size_t smem = kWarpsPerBlock * chain_smem_words(W, Lp) * sizeof(uint64_t);
-  SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int per_sm = 0;
-  SB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kWarpsPerBlock * 32, smem));
-  if (per_sm < 1) throw CudaError("k_chains does not fit on an SM");
-  const uint32_t max_chains = (uint32_t)per_sm * c.num_sms * kWarpsPerBlock;
   uint32_t C = num_chains;
-  if (C == 0) { C = n / 256; if (C < 1) C = 1; if (C > max_chains) C = max_chains; }  // auto: >= 256 reads per slice
+  if (C == 0) {  // auto: every co-resident chain, as long as a chain's slice keeps >= 256 reads
+    C = n / 256; if (C < 1) C = 1; if (C > max_chains) C = max_chains;
+    if (const char *e = getenv("SPRING_B200_MAX_CHAINS")) { const uint32_t m = (uint32_t)strtoul(e, nullptr, 10); if (m && C > m) C = m; }
+  }
   if (C > max_chains) C = max_chains;
   if (C > n) C = n;
-  const uint32_t grid = (C + kWarpsPerBlock - 1) / kWarpsPerBlock;
+  const uint32_t grid = (C + chains_per_block - 1) / chains_per_block;
   out.num_chains = C;
 
   ChainArgs a{};
@@ -896,7 +850,7 @@ void run_reorder(Ctx &c, const uint64_t *reads, const uint16_t *lens, uint32_t n
   a.rec_k = c.pool.dev<uint32_t>("ro.rec_k", nn);
   a.rec_pos = c.pool.dev<int64_t>("ro.rec_pos", nn);
   a.rec_meta = c.pool.dev<uint8_t>("ro.rec_meta", nn);
-  const uint32_t nslots = grid * kWarpsPerBlock;
+  const uint32_t nslots = grid * chains_per_block;
   a.chain_aligned = c.pool.dev<uint32_t>("ro.chain_aligned", nslots + 1);
   a.chain_single = c.pool.dev<uint32_t>("ro.chain_single", nslots + 1);
   uint32_t *off_aligned = c.pool.dev<uint32_t>("ro.off_aligned", nslots + 1);
@@ -910,6 +864,7 @@ void run_reorder(Ctx &c, const uint64_t *reads, const uint16_t *lens, uint32_t n
   a.leader_mask = 0;
   for (uint32_t g = 0; g < a.G; g++) a.leader_mask |= 1u << (g * W);
   a.generic_update = getenv("SPRING_B200_GENERIC_UPDATE") ? 1 : 0;
+  a.cnt_scratch = v1 ? nullptr : c.pool.dev<uint64_t>("ro.cnt_scratch", (size_t)nslots * 32 * W);
   a.steal_probes = lockstep ? 0 : (getenv("SPRING_B200_STEAL") ? atoi(getenv("SPRING_B200_STEAL")) : 64);
   a.max_rounds = 8ull * n + 4096ull;
   SB_CUDA(cudaMemsetAsync(a.claimed, 0, bm_words * sizeof(uint32_t), st));
@@ -923,7 +878,8 @@ void run_reorder(Ctx &c, const uint64_t *reads, const uint16_t *lens, uint32_t n
   if (!c.ev_k0) { SB_CUDA(cudaEventCreate(&c.ev_k0)); SB_CUDA(cudaEventCreate(&c.ev_k1)); }
   SB_CUDA(cudaEventRecord(c.ev_k0, st));
   if (lockstep) SB_CUDA(cudaLaunchCooperativeKernel((void *)kern, dim3(grid), dim3(kWarpsPerBlock * 32), args, smem, st));
-  else kern<<<grid, kWarpsPerBlock * 32, smem, st>>>(a);
+  else if (v1) kern<<<grid, kWarpsPerBlock * 32, smem, st>>>(a);
+  else chains2_launch(a, lanes, grid, st);
   SB_CUDA(cudaEventRecord(c.ev_k1, st));
   c.launches++;
 

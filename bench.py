@@ -278,20 +278,17 @@ def main() -> None:
     torch.cuda.synchronize()
     stream = torch.cuda.current_stream()
     ctx = capi.Context(local, stream.cuda_stream)
-    # global ids of this rank's clean reads (paired: file-2 mates are numbered total / 2 + pair index)
-    d_ids = None
+    # global ids of this rank's reads (paired: file-2 mates are numbered total / 2 + pair index); they travel with the
+    # clean reads through the exchange, the rank's own N reads keep theirs for the shard finalisation
+    d_ids, n_ids = None, None
     if world > 1:
-        lidx = torch.arange(n_local, device=dev, dtype=torch.int64)
-        if cfg["paired"]:
-            half_l, half_g = n_local // 2, total // 2
-            gid = torch.where(lidx < half_l, rank * half_l + lidx, half_g + rank * half_l + (lidx - half_l))
-        else:
-            gid = rank * n_local + lidx
+        gid = multigpu.global_ids(n_local, rank, world, cfg["paired"], dev)
         isn = torch.zeros(n_local, dtype=torch.bool, device=dev)
         if len(order_n):
             isn[torch.from_numpy(order_n.astype(np.int64)).to(dev)] = True
-        d_ids = gid[~isn].to(torch.int32).contiguous()
-        n_ids = gid[isn].to(torch.int32).contiguous()  # noqa: F841  (global ids of the local N reads: for the merge)
+        d_ids = gid[~isn].contiguous()
+        n_ids = gid[isn].cpu().numpy().astype(np.uint32)
+        multigpu.init_comm(ctx, rank, world, dev)
 
     def barrier():
         if world > 1:
@@ -299,26 +296,25 @@ def main() -> None:
         torch.cuda.synchronize()
 
     # ---- value: inputs already in HBM ---------------------------------------------------------------
-    xe0, xe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     exchange_ms = []
     keep = {}
 
-    def device_step():
+    def device_step(finalize=True):
         if world > 1:
-            xe0.record(stream)
-            r, l, g = multigpu.exchange_by_bucket(d_reads, d_lens, L, world, ids=d_ids)
-            xe1.record(stream)
-            xe1.synchronize()
-            exchange_ms.append(xe0.elapsed_time(xe1))
-            n_own = int(r.shape[0])
+            # the library's exchange: bucket + histogram kernel, stable scatter, one NCCL group of send / recv
+            x = ctx.exchange_reads(d_reads.data_ptr(), d_lens.data_ptr(), d_ids.data_ptr(), n_clean, L)
+            n_own = int(x.num_reads)
             # the rank's own N reads stay where they are, numbered after the clean reads it owns
             on = (n_own + np.arange(len(order_n))).astype(np.uint32)
-            inp = ctx.make_input(r.data_ptr(), l.data_ptr(), n_own, L, n_records, on, n_own + len(on))
-            keep["in"] = (r, l, g)
+            inp = ctx.make_input(x.reads, x.lengths, n_own, L, n_records, on, n_own + len(on))
+            ctx.reorder_encode_raw(inp, args.chains, device=True)
+            if finalize:  # absolute positions over all ranks' consensus shards + global ids (the reference's thread-file merge)
+                keep["layout"] = ctx.finalize_shard(x.ids, n_own, n_ids)
+                exchange_ms.append(ctx.stats()["ms_exchange"])
         else:
             n_own = n_clean
             inp = ctx.make_input(d_reads.data_ptr(), d_lens.data_ptr(), n_clean, L, n_records, order_n, n_local)
-        ctx.reorder_encode_raw(inp, args.chains, device=True)
+            ctx.reorder_encode_raw(inp, args.chains, device=True)
         return n_own
 
     for _ in range(args.warmup):
@@ -337,6 +333,7 @@ def main() -> None:
         e1.record(stream)
         barrier()
     ms_dev = e0.elapsed_time(e1) / args.steps
+    exchange_avg = sum(exchange_ms[-args.steps:]) / args.steps if exchange_ms else None
     if world > 1:
         t = torch.tensor([ms_dev], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -350,6 +347,9 @@ def main() -> None:
             cpd = dnaio.CompressionParams(paired_end=cfg["paired"], preserve_order=False, num_reads=n_local, max_readlen=L)
         else:  # a rank's shard on its own, as a single-end job over the reads it owns (pairs are split across ranks)
             cpd = dnaio.CompressionParams(paired_end=False, preserve_order=False, num_reads=n_owned + len(order_n), max_readlen=L)
+        if world > 1:
+            n_owned = device_step(finalize=False)  # the check compares with the rank's own numbering
+            cpd.num_reads = n_owned + len(order_n)
         t0 = time.perf_counter()
         v = ctx.verify_roundtrip(capi.CP.from_buffer_copy(cpd.pack()))
         verify = {"ok": bool(v["ok"]), "reads_checked": int(v["reads_checked"]), "mismatching_reads": int(v["base_mismatch_reads"] + v["length_mismatch_reads"]),
@@ -368,14 +368,10 @@ def main() -> None:
     torch.cuda.synchronize()
 
     def host_step():
-        if world > 1:  # H2D, then the same exchange + device path, then D2H of the streams
-            r = d_reads.copy_(h_reads, non_blocking=True)
-            l = d_lens.copy_(h_lens, non_blocking=True)
-            r, l, g = multigpu.exchange_by_bucket(r, l, L, world, ids=d_ids)
-            n_own = int(r.shape[0])
-            on = (n_own + np.arange(len(order_n))).astype(np.uint32)
-            inp = ctx.make_input(r.data_ptr(), l.data_ptr(), n_own, L, n_records, on, n_own + len(on))
-            ctx.reorder_encode_raw(inp, args.chains, device=True)
+        if world > 1:  # H2D, then the same exchange + device path + finalisation, then D2H of the streams
+            d_reads.copy_(h_reads, non_blocking=True)
+            d_lens.copy_(h_lens, non_blocking=True)
+            device_step()
             s = ctx.fetch_streams_raw()
         else:
             inp = ctx.make_input(h_reads.data_ptr(), h_lens.data_ptr(), n_clean, L, n_records, order_n, n_local)
@@ -450,8 +446,9 @@ def main() -> None:
             "stages_ms": {k: stats_acc[k] for k in stats_acc if k.startswith("ms_")},
             "chains": stats_acc["num_chains"], "rounds": stats_acc["rounds"], "unmatched": stats_acc["unmatched"],
             "mb_per_s_fastq": value * fastq_bytes_per_read, "verify": verify}
-    if exchange_ms:  # rank 0's bucket kernel + owner sort + gathers + all-to-alls, per step (inside ms_per_step)
-        line["exchange_ms"] = sum(exchange_ms[-args.steps:]) / args.steps
+    if exchange_ms:  # rank 0's bucket + scatter kernels, count all-gather and the NCCL send / recv group, per step (inside ms_per_step)
+        line["exchange_ms"] = exchange_avg
+        line["shard_layout_rank0"] = keep.get("layout")
     if after is not None:
         line["after_encoder"] = after
     if world == 1 and not args.no_cpu_baseline:

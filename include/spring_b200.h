@@ -117,6 +117,9 @@ typedef struct spring_b200_stats {
   uint64_t cyc_search, cyc_wait_a, cyc_commit, cyc_wait_b; /* SM cycles summed over blocks, per phase of a round */
   uint64_t slot_probes;      /* lookups that passed the L2-resident key filter and read the slot table in HBM */
   float ms_reblock;          /* device time of the last spring_b200_reblock_* call (pe_encode + re-blocking kernels) */
+  float ms_exchange;         /* device time of the last spring_b200_exchange_reads (bucket + scatter kernels, NCCL group) */
+  uint32_t singletons_aligned; /* "N singleton reads were aligned" / "N reads with N were aligned" (src/encoder.h:490-492) */
+  uint32_t n_reads_aligned;
 } spring_b200_stats;
 
 /* ---- context ---------------------------------------------------------------------------- */
@@ -129,6 +132,10 @@ int spring_b200_create(int device, void *stream, spring_b200_ctx **out);
  * default stream (what e.g. torch.cuda.current_stream().cuda_stream is unless a side stream is set). */
 int spring_b200_set_stream(spring_b200_ctx *ctx, void *stream);
 void spring_b200_destroy(spring_b200_ctx *ctx);
+/* The process-wide context of a device, created on first use and kept until the process ends: what the reference-side
+ * drop-ins use, so that the stages of one `spring -c` run share CUDA initialisation, buffers and the streams left in
+ * HBM (spring_b200_reblock_files then skips reading the stream files back).  Do not destroy it. */
+int spring_b200_shared_ctx(int device, spring_b200_ctx **out);
 const char *spring_b200_last_error(const spring_b200_ctx *ctx); /* ctx may be NULL: last create() error */
 int spring_b200_get_stats(const spring_b200_ctx *ctx, spring_b200_stats *out);
 /* Chain schedule of the reorder stage.  deterministic = 0 (default): free-running chains that claim
@@ -268,6 +275,63 @@ int spring_b200_pack_reads(spring_b200_ctx *ctx, const uint8_t *bases, const uin
  * SURVEY.md section 2.4); see DESIGN.md "multi-GPU". */
 int spring_b200_bucket_reads(spring_b200_ctx *ctx, const uint64_t *reads, const uint16_t *lengths, uint32_t num_reads,
                              uint32_t max_readlen, uint32_t num_buckets, uint32_t *bucket);
+
+/* ---- multi-GPU: one context (one process or thread) per GPU, ONE exchange, inside the library --------------- */
+/* The reference has no distributed path (single process, OpenMP threads sharing one pool of reads; SURVEY.md
+ * section 2.4).  Its on-disk format is already sharded -- decompress concatenates read_seq.bin.<t> for t < cp.num_thr
+ * and positions are absolute in that concatenation (src/decompress.cpp:106-120, src/encoder.h:473-487) -- so a GPU plays
+ * the role of one reference thread:
+ *   1. every rank holds a block of the clean reads with their global ids (index among the job's reads, file 2 after file 1)
+ *   2. spring_b200_exchange_reads: owner(read) = minimizer bucket mod world; one all-to-all(v) of {row, length, id}
+ *      over NCCL / NVLink (fused bucket + histogram kernel, stable scatter into per-destination regions, one group of
+ *      ncclSend / ncclRecv); the rank's own reads with N stay where they are
+ *   3. spring_b200_reorder_encode_device on the owned reads (N reads numbered after them)
+ *   4. spring_b200_finalize_shard: positions made absolute over all ranks' consensus shards, local indices replaced by
+ *      global ids -- what the reference's merge of its thread files does (src/encoder.h:386-423, :473-487)
+ *   5. the whole job's streams are the ranks' pieces in the order the layout names: all aligned parts in rank order,
+ *      then all unaligned parts (the invariant of src/reorder_compress_streams.cpp:254-270); spring_b200_merge_shards
+ *      concatenates finalized host streams that way for a single consumer.
+ * NCCL is loaded with dlopen when spring_b200_comm_* is first called. */
+#define SPRING_B200_COMM_ID_BYTES 128
+int spring_b200_comm_unique_id(uint8_t id[SPRING_B200_COMM_ID_BYTES]);   /* on one rank; the host passes it to the others */
+int spring_b200_comm_init(spring_b200_ctx *ctx, const uint8_t id[SPRING_B200_COMM_ID_BYTES], int rank, int world);
+int spring_b200_comm_free(spring_b200_ctx *ctx);
+typedef struct spring_b200_exchanged {
+  const uint64_t *reads;     /* DEVICE, [num_reads * W]: the reads this rank owns, sources in rank order, input order inside */
+  const uint16_t *lengths;   /* DEVICE */
+  const uint32_t *ids;       /* DEVICE: their global ids */
+  uint32_t num_reads;
+  uint64_t sent_to_peers, received_from_peers;   /* reads that crossed NVLink */
+} spring_b200_exchanged;
+/* DEVICE pointers in; the outputs stay valid until the next exchange on this context. */
+int spring_b200_exchange_reads(spring_b200_ctx *ctx, const uint64_t *reads, const uint16_t *lengths, const uint32_t *ids,
+                               uint32_t num_reads, uint32_t max_readlen, spring_b200_exchanged *out);
+typedef struct spring_b200_shard_layout {
+  uint32_t rank, world;
+  uint64_t seq_base;                 /* bases of the lower ranks' consensus shards (added to this rank's positions) */
+  uint64_t aligned_before, noise_before, num_noise_before;       /* where this rank's aligned piece starts in each stream */
+  uint64_t unaligned_reads_before, unaligned_bytes_before;       /* ... and its unaligned piece, after ALL aligned pieces */
+  uint64_t total_seq_len, total_aligned, total_reads, total_noise_bytes, total_num_noise, total_unaligned_bytes, total_unaligned_len;
+} spring_b200_shard_layout;
+/* After spring_b200_reorder_encode_device on the exchanged reads.  ids: DEVICE, the exchanged ids (num_owned of them);
+ * n_ids: HOST, global ids of this rank's reads with N (numbered num_owned, num_owned + 1, ... in the call).  Rewrites
+ * the resident streams' pos / order in place (fetch them afterwards) and tells where the shard's pieces go. */
+int spring_b200_finalize_shard(spring_b200_ctx *ctx, const uint32_t *ids, uint32_t num_owned, const uint32_t *n_ids, uint32_t num_n,
+                               spring_b200_shard_layout *out);
+/* Host-side concatenation of finalized shards (HOST streams, rank order) into one job: aligned pieces first, then the
+ * unaligned ones.  The consensus stays sharded (one read_seq.bin.<t> per shard, cp.num_thr = num_shards).  The result
+ * owns its memory; release it with spring_b200_free_merged. */
+typedef struct spring_b200_merged {
+  spring_b200_streams streams;       /* seq_packed is NULL: see shard_seq */
+  int num_shards;
+  const uint8_t **shard_seq;         /* [num_shards] packed consensus of each shard (pointers into the inputs) */
+  uint64_t *shard_seq_len;           /* [num_shards] */
+  void *owner;
+} spring_b200_merged;
+int spring_b200_merge_shards(const spring_b200_streams *shards, int num_shards, spring_b200_merged *out);
+void spring_b200_free_merged(spring_b200_merged *m);
+/* read_seq.bin.<t> + .tail per shard and the other stream files of a merged job, as spring_b200_write_streams does */
+int spring_b200_write_merged(const char *temp_dir, const spring_b200_merged *m);
 
 /* ---- file-level drop-in -------------------------------------------------------------------- */
 /* Replaces call_reorder + call_encoder (src/call_template_functions.cpp:9-143) on a temp_dir:

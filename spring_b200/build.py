@@ -9,7 +9,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libspring_b200.so")
-SOURCES = ["dict.cu", "reorder.cu", "chains2.cu", "encode.cu", "reblock.cu", "decode.cu", "pack.cu", "bucket.cu", "verify.cu", "pipeline.cu"]
+SOURCES = ["dict.cu", "reorder.cu", "encode.cu", "reblock.cu", "decode.cu", "pack.cu", "bucket.cu", "exchange.cu", "verify.cu", "pipeline.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "-Xcompiler", "-Wno-unused-function",

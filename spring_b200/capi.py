@@ -22,6 +22,9 @@ EXPORTS = [
     "spring_b200_bucket_reads", "spring_b200_set_schedule", "spring_b200_fetch_reorder", "spring_b200_set_stream",
     "spring_b200_pe_encode", "spring_b200_reblock_streams", "spring_b200_reblock_files", "spring_b200_pack_reads",
     "spring_b200_decode_blocks", "spring_b200_verify_roundtrip",
+    "spring_b200_comm_unique_id", "spring_b200_comm_init", "spring_b200_comm_free", "spring_b200_exchange_reads",
+    "spring_b200_finalize_shard", "spring_b200_merge_shards", "spring_b200_free_merged", "spring_b200_write_merged",
+    "spring_b200_shared_ctx",
 ]
 
 
@@ -80,6 +83,26 @@ class PackedReads(C.Structure):
                 ("num_n", C.c_uint32), ("num_reads", C.c_uint32)]
 
 
+class Exchanged(C.Structure):
+    _fields_ = [("reads", C.c_void_p), ("lengths", C.c_void_p), ("ids", C.c_void_p), ("num_reads", C.c_uint32),
+                ("sent_to_peers", C.c_uint64), ("received_from_peers", C.c_uint64)]
+
+
+class ShardLayout(C.Structure):
+    _fields_ = [("rank", C.c_uint32), ("world", C.c_uint32)] + [(n, C.c_uint64) for n in (
+        "seq_base", "aligned_before", "noise_before", "num_noise_before", "unaligned_reads_before", "unaligned_bytes_before",
+        "total_seq_len", "total_aligned", "total_reads", "total_noise_bytes", "total_num_noise", "total_unaligned_bytes",
+        "total_unaligned_len")]
+
+    def as_dict(self) -> dict:
+        return {f: getattr(self, f) for f, _ in self._fields_}
+
+
+class Merged(C.Structure):
+    _fields_ = [("streams", Streams), ("num_shards", C.c_int), ("shard_seq", C.POINTER(C.c_void_p)),
+                ("shard_seq_len", C.POINTER(C.c_uint64)), ("owner", C.c_void_p)]
+
+
 class Verify(C.Structure):
     _fields_ = [("ok", C.c_int32), ("num_reads", C.c_uint64), ("reads_checked", C.c_uint64), ("base_mismatch_reads", C.c_uint64),
                 ("length_mismatch_reads", C.c_uint64), ("bad_order", C.c_uint64), ("num_blocks", C.c_uint64),
@@ -96,7 +119,8 @@ class Stats(C.Structure):
                 ("ms_chains", C.c_float), ("ms_scatter", C.c_float), ("ms_encode", C.c_float), ("ms_d2h", C.c_float),
                 ("ms_total", C.c_float), ("ms_chain_kernel", C.c_float), ("cyc_search", C.c_uint64),
                 ("cyc_wait_a", C.c_uint64), ("cyc_commit", C.c_uint64), ("cyc_wait_b", C.c_uint64),
-                ("slot_probes", C.c_uint64), ("ms_reblock", C.c_float)]
+                ("slot_probes", C.c_uint64), ("ms_reblock", C.c_float), ("ms_exchange", C.c_float),
+                ("singletons_aligned", C.c_uint32), ("n_reads_aligned", C.c_uint32)]
 
     def as_dict(self) -> dict:
         return {f: getattr(self, f) for f, _ in self._fields_}
@@ -135,6 +159,15 @@ def load():
         lib.spring_b200_pack_reads.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int,
                                                C.POINTER(PackedReads)]
         lib.spring_b200_verify_roundtrip.argtypes = [C.c_void_p, C.POINTER(CP), C.POINTER(Verify)]
+        lib.spring_b200_comm_unique_id.argtypes = [C.c_void_p]
+        lib.spring_b200_comm_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        lib.spring_b200_comm_free.argtypes = [C.c_void_p]
+        lib.spring_b200_exchange_reads.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32,
+                                                   C.POINTER(Exchanged)]
+        lib.spring_b200_finalize_shard.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(ShardLayout)]
+        lib.spring_b200_merge_shards.argtypes = [C.POINTER(Streams), C.c_int, C.POINTER(Merged)]
+        lib.spring_b200_free_merged.argtypes = [C.POINTER(Merged)]
+        lib.spring_b200_write_merged.argtypes = [C.c_char_p, C.POINTER(Merged)]
         _lib = lib
     return _lib
 
@@ -404,6 +437,29 @@ class Context:
         offs = _view(out.offsets, out.num_reads + 1, np.uint64).copy()
         return _view(out.bases, int(offs[-1]) if len(offs) else 0, np.uint8).copy(), offs
 
+    # ---- multi-GPU ------------------------------------------------------------------
+    def comm_init(self, comm_id: bytes, rank: int, world: int) -> None:
+        """Join the job's NCCL communicator (comm_id from capi.comm_unique_id() on one rank)."""
+        buf = (C.c_uint8 * 128).from_buffer_copy(comm_id)
+        self._check(self._lib.spring_b200_comm_init(self._h, buf, rank, world))
+
+    def comm_free(self) -> None:
+        self._check(self._lib.spring_b200_comm_free(self._h))
+
+    def exchange_reads(self, reads_ptr: int, lengths_ptr: int, ids_ptr: int, num_reads: int, max_readlen: int) -> Exchanged:
+        """Device pointers in, device pointers out (owned by the context): the reads this rank owns."""
+        x = Exchanged()
+        self._check(self._lib.spring_b200_exchange_reads(self._h, reads_ptr, lengths_ptr, ids_ptr, num_reads, max_readlen, C.byref(x)))
+        return x
+
+    def finalize_shard(self, ids_ptr: int, num_owned: int, n_ids: np.ndarray | None = None) -> dict:
+        """Absolute positions + global ids for the streams of the last reorder_encode_raw(device=True) call."""
+        n_ids = np.zeros(0, np.uint32) if n_ids is None else np.ascontiguousarray(n_ids, dtype=np.uint32)
+        lay = ShardLayout()
+        self._check(self._lib.spring_b200_finalize_shard(self._h, ids_ptr, num_owned, n_ids.ctypes.data if len(n_ids) else None,
+                                                         len(n_ids), C.byref(lay)))
+        return lay.as_dict()
+
     def verify_roundtrip(self, cp: CP) -> dict:
         """Re-block -> block decode -> exact compare with the input of the last reorder_encode* call, all in HBM."""
         v = Verify()
@@ -416,3 +472,43 @@ class Context:
     # ---- files ---------------------------------------------------------------------------------
     def reorder_encode_files(self, temp_dir: str, cp: CP, num_chains: int = 0) -> None:
         self._check(self._lib.spring_b200_reorder_encode_files(self._h, temp_dir.encode(), C.byref(cp), num_chains))
+
+
+def comm_unique_id() -> bytes:
+    """ncclGetUniqueId through the library (one rank makes it, the host hands it to the others)."""
+    buf = (C.c_uint8 * 128)()
+    rc = load().spring_b200_comm_unique_id(buf)
+    if rc != 0:
+        raise SpringB200Error(rc, load().spring_b200_last_error(None).decode())
+    return bytes(buf)
+
+
+def merge_shards(parts: list) -> tuple["StreamsResult", list]:
+    """spring_b200_merge_shards on finalized host shards (StreamsResult-like objects, rank order): the whole job's
+    streams (aligned pieces of every shard, then the unaligned ones) and the per-shard (packed consensus, length)."""
+    lib = load()
+    n = len(parts)
+    arr = (Streams * n)()
+    keep = []
+    for i, s in enumerate(parts):
+        cols = [np.ascontiguousarray(a, dtype=dt) for a, dt in (
+            (s.seq_packed, np.uint8), (s.pos, np.uint64), (s.noise, np.uint8), (s.noisepos, np.uint16), (s.rc, np.uint8),
+            (s.order, np.uint32), (s.lengths, np.uint16), (s.unaligned, np.uint8))]
+        keep.append(cols)
+        ptr = lambda a: a.ctypes.data if a.size else None
+        t = arr[i]
+        t.seq_packed, t.pos, t.noise, t.noisepos, t.rev, t.order, t.lengths, t.unaligned = (ptr(a) for a in cols)
+        t.seq_len, t.noise_bytes, t.num_noise = int(s.seq_len), len(cols[2]), len(cols[3])
+        t.unaligned_bytes, t.unaligned_len = len(cols[7]), int(s.unaligned_len)
+        t.num_aligned, t.num_reads = int(s.num_aligned), len(cols[5])
+        t.singletons_aligned, t.n_reads_aligned = int(getattr(s, "matched_s", 0)), int(getattr(s, "matched_N", 0))
+    m = Merged()
+    rc = lib.spring_b200_merge_shards(arr, n, C.byref(m))
+    if rc != 0:
+        raise SpringB200Error(rc, lib.spring_b200_last_error(None).decode())
+    try:
+        res = Context._streams_to_result(m.streams)
+        shards = [(keep[i][0], int(m.shard_seq_len[i])) for i in range(n)]
+    finally:
+        lib.spring_b200_free_merged(C.byref(m))
+    return res, shards

@@ -1,5 +1,4 @@
-// chain_common.cuh -- what the two chain kernels share (reorder.cu: round-synchronous and warp-wide chains;
-// chains2.cu: free-running sub-warp chains).
+// chain_common.cuh -- definitions of the chain kernel (reorder.cu) that its helpers share.
 #pragma once
 #include "kernels.cuh"
 
@@ -25,9 +24,9 @@ struct ChainArgs {
   uint32_t G;            // scan_bin: candidates verified per pass = 32 / W
   unsigned leader_mask;  // scan_bin: lanes g * W, g < G
   int generic_update;    // debugging aid: always use the per-column update_ref
+  int prefetch_slots;    // pass 1 of a batch prefetches the slot of every filter positive into L2
   int steal_probes;      // free-running schedule: random slices an idle chain probes for an unclaimed read (0 = off)
   unsigned long long *chain_dbg;  // [2 * chains]: steps, globaltimer ns at finish (profiling aid)
-  uint64_t *cnt_scratch;          // chains2: [chains][32 W] packed counts for the per-column update (fold quirk)
 };
 
 __device__ __forceinline__ bool is_claimed(const uint32_t *claimed, uint32_t rid) {
@@ -38,7 +37,7 @@ __device__ __forceinline__ bool is_claimed(const uint32_t *claimed, uint32_t rid
 // 2-bit read codes are A0 G1 C2 T3 -> field shift 0, 48, 16, 32.  The reference counts in int
 // (reorder.h:383-384); here a count SATURATES at 65535 instead of failing: exact up to 65535 reads of one
 // base stacked on one column, a tie broken by the vote's fixed order beyond (the output stays decodable
-// either way).  The bit-sliced counts of chains2.cu saturate identically.
+// either way).
 __device__ __forceinline__ uint64_t count_add(uint64_t v, int b) {
   const int sh = (int)((0x20103000u >> (8 * b)) & 0xFFu);
   if (((v >> sh) & 0xFFFFull) != 0xFFFFull) v += 1ull << sh;
@@ -69,11 +68,6 @@ __device__ __forceinline__ uint64_t window_key(const uint64_t *a, int pos, int n
   return nbits < 64 ? v & ((1ull << nbits) - 1ull) : v;
 }
 
-
-// entry points of chains2.cu (free-running sub-warp chains)
-struct Chains2Config { int block_threads; int chains_per_block; size_t smem_bytes; int max_blocks_per_sm; };
-Chains2Config chains2_config(int W, int lanes_per_chain);
-void chains2_launch(const ChainArgs &a, int lanes_per_chain, uint32_t grid, cudaStream_t st);
 
 }  // namespace chain
 }  // namespace sb

@@ -40,19 +40,19 @@ int env_int(const char *name, int dflt) {
 
 void call_reorder(const std::string &temp_dir, compression_params &cp) {
   if (cp.max_readlen > 511) throw std::runtime_error("Wrong bitset size.");  // call_template_functions.cpp:61
+  // the process-wide context: CUDA initialisation and buffers are shared with call_encoder and
+  // reorder_compress_streams, and the streams stay in HBM for the re-blocking stage
   spring_b200_ctx *ctx = nullptr;
   const int device = env_int("SPRING_B200_DEVICE", 0);
-  if (spring_b200_create(device, nullptr, &ctx) != SPRING_B200_OK)
+  if (spring_b200_shared_ctx(device, &ctx) != SPRING_B200_OK)
     throw std::runtime_error(std::string("spring_b200: ") + spring_b200_last_error(nullptr));
   spring_b200_cp c;
   std::memcpy(&c, &cp, sizeof(c));
   const int rc = spring_b200_reorder_encode_files(ctx, temp_dir.c_str(), &c, (uint32_t)env_int("SPRING_B200_CHAINS", 0));
-  std::string err = rc == SPRING_B200_OK ? "" : spring_b200_last_error(ctx);
+  if (rc != SPRING_B200_OK) throw std::runtime_error(std::string("spring_b200: ") + spring_b200_last_error(ctx));
   spring_b200_stats st;
-  if (rc == SPRING_B200_OK && spring_b200_get_stats(ctx, &st) == SPRING_B200_OK)
+  if (spring_b200_get_stats(ctx, &st) == SPRING_B200_OK)
     std::printf("Reordering done, %u were unmatched\n", st.unmatched);  // reorder.h:633-635
-  spring_b200_destroy(ctx);
-  if (rc != SPRING_B200_OK) throw std::runtime_error("spring_b200: " + err);
 }
 
 void call_encoder(const std::string &temp_dir, compression_params &cp) {
@@ -65,6 +65,11 @@ void call_encoder(const std::string &temp_dir, compression_params &cp) {
     bsc::BSC_compress(base.c_str(), (base + ".bsc").c_str());
     std::remove(base.c_str());
   }
+  // encoder.h:490-492
+  spring_b200_ctx *ctx = nullptr;
+  spring_b200_stats st;
+  if (spring_b200_shared_ctx(env_int("SPRING_B200_DEVICE", 0), &ctx) == SPRING_B200_OK && spring_b200_get_stats(ctx, &st) == SPRING_B200_OK)
+    std::printf("Encoding done:\n%u singleton reads were aligned\n%u reads with N were aligned\n", st.singletons_aligned, st.n_reads_aligned);
 }
 
 }  // namespace spring

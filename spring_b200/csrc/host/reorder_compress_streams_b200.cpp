@@ -36,14 +36,12 @@ void pe_encode(const std::string &, const compression_params &) {}
 void reorder_compress_streams(const std::string &temp_dir, const compression_params &cp) {
   spring_b200_ctx *ctx = nullptr;
   const char *dev = std::getenv("SPRING_B200_DEVICE");
-  if (spring_b200_create(dev ? std::atoi(dev) : 0, nullptr, &ctx) != SPRING_B200_OK)
+  if (spring_b200_shared_ctx(dev ? std::atoi(dev) : 0, &ctx) != SPRING_B200_OK)  // the streams call_reorder left in HBM are reused
     throw std::runtime_error(std::string("spring_b200: ") + spring_b200_last_error(nullptr));
   spring_b200_cp c;
   std::memcpy(&c, &cp, sizeof(c));
   const int rc = spring_b200_reblock_files(ctx, temp_dir.c_str(), &c);
-  const std::string err = rc == SPRING_B200_OK ? "" : spring_b200_last_error(ctx);
-  spring_b200_destroy(ctx);
-  if (rc != SPRING_B200_OK) throw std::runtime_error("spring_b200: " + err);
+  if (rc != SPRING_B200_OK) throw std::runtime_error(std::string("spring_b200: ") + spring_b200_last_error(ctx));
 
   static const char *const files[] = {"read_flag.txt", "read_pos.bin", "read_noise.txt", "read_noisepos.bin", "read_rev.txt",
                                       "read_unaligned.txt", "read_lengths.bin", "read_pos_pair.bin", "read_rev_pair.txt"};

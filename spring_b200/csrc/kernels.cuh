@@ -13,6 +13,7 @@ struct Ctx {
   std::string err;
   uint64_t launches = 0;  // kernels launched since the last reset (ours + CUB passes)
   cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;  // around the chain kernel
+  cudaEvent_t ev_x0 = nullptr, ev_x1 = nullptr;  // around the multi-GPU exchange
   bool lockstep = false;  // chain schedule: deterministic round-synchronous, or free-running (default)
 };
 
@@ -109,6 +110,31 @@ struct PackDev {
 };
 // d_bases: the reads' sequence lines concatenated, file 1 then file 2; d_offsets[n + 1]: start of read i
 void run_pack_reads(Ctx &c, const uint8_t *d_bases, const unsigned long long *d_offsets, uint32_t n, uint32_t n_file1, PackDev &out);
+
+// ---- exchange.cu : the multi-GPU exchange and the shard finalisation -------------------------------
+struct Comm;  // NCCL communicator of one rank (opaque; NCCL is dlopen'ed on first use)
+void comm_unique_id(uint8_t id[128]);
+Comm *comm_create(const uint8_t id[128], int rank, int world);
+void comm_destroy(Comm *c);
+int comm_rank(const Comm *c);
+int comm_world(const Comm *c);
+struct ExchangeDev {  // the reads this rank owns after the all-to-all (device, owned by the context's pool)
+  const uint64_t *reads = nullptr; const uint16_t *lens = nullptr; const uint32_t *ids = nullptr;
+  uint32_t n = 0;
+  uint64_t sent_to_peers = 0, received_from_peers = 0;
+};
+void run_exchange(Ctx &c, Comm *cm, const uint64_t *reads, const uint16_t *lens, const uint32_t *ids, uint32_t n, int L, ExchangeDev &out);
+float exchange_ms(Ctx &c);
+struct ShardLayout {  // where this rank's pieces sit in the whole job's streams (all ranks' aligned parts first)
+  uint32_t rank = 0, world = 1;
+  uint64_t seq_base = 0, aligned_before = 0, noise_before = 0, num_noise_before = 0, unaligned_reads_before = 0, unaligned_bytes_before = 0;
+  uint64_t total_seq_len = 0, total_aligned = 0, total_reads = 0, total_noise_bytes = 0, total_num_noise = 0, total_unaligned_bytes = 0,
+           total_unaligned_len = 0;
+};
+// pos += sum of the lower ranks' consensus lengths; order[i] = global id (ids: device, the exchanged ids of the owned
+// clean reads; h_n_ids: host, global ids of the rank's own reads with N, which were numbered after the owned reads)
+void run_finalize_shard(Ctx &c, Comm *cm, EncodeDev &e, const uint32_t *ids, uint32_t n_owned, const uint32_t *h_n_ids, uint32_t n_n,
+                        ShardLayout &out);
 
 // ---- bucket.cu : multi-GPU partitioning key --------------------------------------------------
 void bucket_reads(Ctx &c, const uint64_t *reads, const uint16_t *lens, uint32_t n, int L, uint32_t num_buckets, uint32_t *bucket);

@@ -1,11 +1,14 @@
 // pipeline.cu -- context, orchestration and the C ABI (include/spring_b200.h).
 #include <errno.h>
 #include <string.h>
+#include <fcntl.h>
+#include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
 #include <algorithm>
 #include <cstddef>
 #include <fstream>
+#include <thread>
 #include "../../include/spring_b200.h"
 #include "kernels.cuh"
 
@@ -30,6 +33,8 @@ struct spring_b200_ctx {
   // the input of that call, for spring_b200_verify_roundtrip (device pointers; the caller's own for *_device)
   const uint64_t *last_reads = nullptr; const uint16_t *last_lens = nullptr; uint32_t last_num_clean = 0; int last_W = 1;
   NReads last_nr{};
+  Comm *comm = nullptr;  // multi-GPU communicator (spring_b200_comm_init)
+  std::string files_dir;  // temp_dir whose stream files hold exactly the resident streams (spring_b200_reorder_encode_files)
   cudaEvent_t ev[8]{};  // 0-5: the hot path's stages, 6-7: around the re-blocking
 };
 
@@ -200,6 +205,7 @@ void run_all(spring_b200_ctx *ctx, const spring_b200_input *in, uint32_t num_cha
   Ctx &c = ctx->c;
   c.launches = 0;
   ctx->stats = spring_b200_stats{};
+  ctx->files_dir.clear();
   const int L = (int)in->max_readlen, W = words_for(L);
   rec(ctx, 0);
   DevInput d = host_in ? upload_reads(c, in, W) : DevInput{in->reads, in->lengths};
@@ -226,6 +232,7 @@ void run_all(spring_b200_ctx *ctx, const spring_b200_input *in, uint32_t num_cha
   st.ms_h2d = ms(ctx, 0, 1); st.ms_dict = ms(ctx, 1, 2); st.ms_chains = ms(ctx, 2, 3); st.ms_scatter = 0;
   st.ms_encode = ms(ctx, 3, 4); st.ms_d2h = ms(ctx, 4, 5); st.ms_total = ms(ctx, 0, 5);
   st.gpu_launches = c.launches;
+  st.singletons_aligned = ctx->last_enc.singletons_aligned; st.n_reads_aligned = ctx->last_enc.n_reads_aligned;
 }
 
 // ---- files ---------------------------------------------------------------------------------------
@@ -240,28 +247,126 @@ std::vector<uint8_t> slurp(const std::string &p, bool must_exist) {
   return v;
 }
 void spill(const std::string &p, const void *data, size_t n) {
-  std::ofstream f(p, std::ios::binary);
-  if (!f.is_open()) throw IoError("cannot create " + p);
-  if (n) f.write((const char *)data, (std::streamsize)n);
-  if (!f.good()) throw IoError("write failed: " + p);
+  const int fd = open(p.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
+  if (fd < 0) throw IoError("cannot create " + p);
+  const char *c = static_cast<const char *>(data);
+  size_t at = 0;
+  while (at < n) {
+    const ssize_t w = write(fd, c + at, n - at > ((size_t)1 << 30) ? ((size_t)1 << 30) : n - at);
+    if (w < 0) { if (errno == EINTR) continue; close(fd); throw IoError("write failed: " + p); }
+    at += (size_t)w;
+  }
+  if (close(fd) != 0) throw IoError("write failed: " + p);
 }
 
-// readDnaFile (reorder.h:222-244): records {u16 len; ceil(len/4) B} copied into bitset storage
-void parse_dna(const std::vector<uint8_t> &buf, uint32_t num, int W, uint32_t max_readlen, uint64_t *reads, uint16_t *lens,
-               const std::string &name) {
-  size_t off = 0;
-  for (uint32_t i = 0; i < num; i++) {
-    if (off + 2 > buf.size()) throw IoError(name + " truncated");
-    uint16_t len; memcpy(&len, buf.data() + off, 2); off += 2;
-    if (len > max_readlen) throw IoError(name + ": read longer than cp.max_readlen");
-    const size_t nb = ((size_t)len + 3) / 4;
-    if (off + nb > buf.size()) throw IoError(name + " truncated");
-    uint64_t *r = reads + (size_t)i * W;
-    for (int w = 0; w < W; w++) r[w] = 0;
-    memcpy(r, buf.data() + off, nb);
-    off += nb;
-    lens[i] = len;
+// A whole file mapped read-only (the page cache is the only copy; the records go straight into pinned memory).
+struct MappedFile {
+  const uint8_t *p = nullptr; size_t n = 0; int fd = -1;
+  MappedFile(const std::string &path, bool must_exist) {
+    fd = open(path.c_str(), O_RDONLY);
+    if (fd < 0) { if (must_exist) throw IoError("cannot open " + path); return; }
+    struct stat sb;
+    if (fstat(fd, &sb) != 0) { close(fd); fd = -1; throw IoError("cannot stat " + path); }
+    n = (size_t)sb.st_size;
+    if (n) {
+      void *m = mmap(nullptr, n, PROT_READ, MAP_PRIVATE | MAP_POPULATE, fd, 0);
+      if (m == MAP_FAILED) { close(fd); fd = -1; throw IoError("cannot map " + path); }
+      p = static_cast<const uint8_t *>(m);
+    }
   }
+  ~MappedFile() { if (p) munmap(const_cast<uint8_t *>(p), n); if (fd >= 0) close(fd); }
+  MappedFile(const MappedFile &) = delete;
+  MappedFile &operator=(const MappedFile &) = delete;
+};
+
+int host_threads() {
+  static const int n = [] {
+    if (const char *e = getenv("SPRING_B200_HOST_THREADS")) { const int v = atoi(e); if (v > 0) return v; }
+    const unsigned hc = std::thread::hardware_concurrency();
+    return (int)(hc ? (hc > 16 ? 16 : hc) : 4);
+  }();
+  return n;
+}
+template <typename F> void parallel_ranges(size_t n, F &&f) {  // f(lo, hi) on host_threads() slices of [0, n)
+  const int T = n < (1u << 16) ? 1 : host_threads();
+  if (T == 1) { f((size_t)0, n); return; }
+  std::vector<std::thread> th;
+  std::vector<std::string> errs(T);
+  for (int t = 0; t < T; t++)
+    th.emplace_back([&, t] {
+      try { f(n * t / T, n * (t + 1) / T); } catch (const std::exception &e) { errs[t] = e.what(); }
+    });
+  for (auto &x : th) x.join();
+  for (auto &e : errs) if (!e.empty()) throw IoError(e);
+}
+
+// readDnaFile (reorder.h:222-244): records {u16 len; ceil(len/4) B} copied into bitset storage.  Fixed-length files
+// (the usual case: every record has the same size) are cut into slices copied by several host threads; files with
+// mixed lengths need the sequential walk over the 2-byte headers first, then the same parallel copy.
+void parse_dna(const MappedFile &buf, uint32_t num, int W, uint32_t max_readlen, uint64_t *reads, uint16_t *lens,
+               const std::string &name) {
+  if (!num) return;
+  if (buf.n < 2) throw IoError(name + " truncated");
+  uint16_t len0; memcpy(&len0, buf.p, 2);
+  const size_t rec0 = 2 + ((size_t)len0 + 3) / 4;
+  bool fixed = len0 <= max_readlen && buf.n == rec0 * (size_t)num;
+  if (fixed) {  // every header must say the same length; checked inside the copy
+    std::vector<uint8_t> bad(1, 0);
+    parallel_ranges(num, [&](size_t lo, size_t hi) {
+      const size_t nb = rec0 - 2;
+      for (size_t i = lo; i < hi; i++) {
+        const uint8_t *r = buf.p + i * rec0;
+        uint16_t len; memcpy(&len, r, 2);
+        if (len != len0) { bad[0] = 1; return; }
+        uint64_t *d = reads + i * (size_t)W;
+        for (int w = (int)(nb >> 3); w < W; w++) d[w] = 0;  // the words the record does not fill completely
+        memcpy(d, r + 2, nb);
+        lens[i] = len;
+      }
+    });
+    if (!bad[0]) return;
+    fixed = false;  // same total size by coincidence: fall through to the general walk
+  }
+  std::vector<size_t> off((size_t)num + 1);
+  size_t at = 0;
+  for (uint32_t i = 0; i < num; i++) {
+    if (at + 2 > buf.n) throw IoError(name + " truncated");
+    uint16_t len; memcpy(&len, buf.p + at, 2);
+    if (len > max_readlen) throw IoError(name + ": read longer than cp.max_readlen");
+    off[i] = at;
+    at += 2 + ((size_t)len + 3) / 4;
+    if (at > buf.n) throw IoError(name + " truncated");
+  }
+  off[num] = at;
+  parallel_ranges(num, [&](size_t lo, size_t hi) {
+    for (size_t i = lo; i < hi; i++) {
+      const uint8_t *r = buf.p + off[i];
+      uint16_t len; memcpy(&len, r, 2);
+      uint64_t *d = reads + i * (size_t)W;
+      for (int w = 0; w < W; w++) d[w] = 0;
+      memcpy(d, r + 2, ((size_t)len + 3) / 4);
+      lens[i] = len;
+    }
+  });
+}
+
+// the eight stream files next to read_seq.bin.<t>, one host thread per file
+void write_stream_files(const std::string &dir, const spring_b200_streams *s) {
+  struct Job { const char *name; const void *p; size_t n; };
+  const Job jobs[] = {{"/read_pos.bin", s->pos, (size_t)s->num_aligned * 8}, {"/read_noise.txt", s->noise, (size_t)s->noise_bytes},
+                      {"/read_noisepos.bin", s->noisepos, (size_t)s->num_noise * 2}, {"/read_rev.txt", s->rev, (size_t)s->num_aligned},
+                      {"/read_order.bin", s->order, (size_t)s->num_reads * 4}, {"/read_lengths.bin", s->lengths, (size_t)s->num_reads * 2},
+                      {"/read_unaligned.txt", s->unaligned, (size_t)s->unaligned_bytes},
+                      {"/read_unaligned.txt.count", &s->unaligned_len, (size_t)8}};
+  std::vector<std::thread> th;
+  std::vector<std::string> errs(sizeof(jobs) / sizeof(jobs[0]));
+  int k = 0;
+  for (const Job &j : jobs) {
+    const int idx = k++;
+    th.emplace_back([&, j, idx] { try { spill(dir + j.name, j.p, j.n); } catch (const std::exception &e) { errs[idx] = e.what(); } });
+  }
+  for (auto &t : th) t.join();
+  for (auto &e : errs) if (!e.empty()) throw IoError(e);
 }
 
 void write_streams(const std::string &dir, const spring_b200_streams *s, int num_shards) {
@@ -279,14 +384,7 @@ void write_streams(const std::string &dir, const spring_b200_streams *s, int num
       for (uint64_t x = full * 4; x < s->seq_len; x++) tail.push_back(code2char[(s->seq_packed[x / 4] >> (2 * (x & 3))) & 3]);
     spill(base + ".tail", tail.data(), tail.size());
   }
-  spill(dir + "/read_pos.bin", s->pos, s->num_aligned * 8);
-  spill(dir + "/read_noise.txt", s->noise, s->noise_bytes);
-  spill(dir + "/read_noisepos.bin", s->noisepos, s->num_noise * 2);
-  spill(dir + "/read_rev.txt", s->rev, s->num_aligned);
-  spill(dir + "/read_order.bin", s->order, s->num_reads * 4);
-  spill(dir + "/read_lengths.bin", s->lengths, s->num_reads * 2);
-  spill(dir + "/read_unaligned.txt", s->unaligned, s->unaligned_bytes);
-  spill(dir + "/read_unaligned.txt.count", &s->unaligned_len, 8);
+  write_stream_files(dir, s);
 }
 
 // ---- pe_encode / re-blocking -----------------------------------------------------------------
@@ -397,11 +495,26 @@ int spring_b200_create(int device, void *stream, spring_b200_ctx **out) {
   return SPRING_B200_OK;
 }
 
+// Process-wide context of a device for the reference-side drop-ins (call_reorder, call_encoder, reorder_compress_streams
+// are separate calls of one `spring -c` run): created on first use and kept, so that CUDA initialisation, the buffer pool
+// and the streams left in HBM are shared between the stages.  Never destroyed explicitly (process exit releases it).
+int spring_b200_shared_ctx(int device, spring_b200_ctx **out) {
+  static std::map<int, spring_b200_ctx *> shared;
+  if (!out) return SPRING_B200_EINVAL;
+  auto it = shared.find(device);
+  if (it != shared.end()) { *out = it->second; return SPRING_B200_OK; }
+  const int rc = spring_b200_create(device, nullptr, out);
+  if (rc == SPRING_B200_OK) shared[device] = *out;
+  return rc;
+}
+
 void spring_b200_destroy(spring_b200_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->c.device);
   cudaStreamSynchronize(ctx->c.stream);
   ctx->c.pool.release();
+  if (ctx->comm) { try { comm_destroy(ctx->comm); } catch (...) {} ctx->comm = nullptr; }
+  if (ctx->c.ev_x0) { cudaEventDestroy(ctx->c.ev_x0); cudaEventDestroy(ctx->c.ev_x1); }
   if (ctx->c.ev_k0) { cudaEventDestroy(ctx->c.ev_k0); cudaEventDestroy(ctx->c.ev_k1); }
   for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
   if (ctx->c.own_stream) cudaStreamDestroy(ctx->c.stream);
@@ -642,6 +755,28 @@ int spring_b200_reblock_files(spring_b200_ctx *ctx, const char *temp_dir, const 
   return guarded(ctx, [&] {
     if (!temp_dir || !cp) throw ArgError("null argument");
     const std::string dir(temp_dir);
+    static const char *files[SPRING_B200_NUM_BLOCK_STREAMS] = {"read_flag.txt", "read_pos.bin", "read_noise.txt", "read_noisepos.bin",
+        "read_rev.txt", "read_unaligned.txt", "read_lengths.bin", "read_pos_pair.bin", "read_rev_pair.txt"};
+    auto finish = [&](const spring_b200_blocks &b) {
+      for (const char *f : {"read_noise.txt", "read_noisepos.bin", "read_rev.txt", "read_order.bin", "read_lengths.bin",
+                            "read_unaligned.txt", "read_pos.bin", "read_unaligned.txt.count"})
+        unlink((dir + "/" + f).c_str());  // :153, :174-181
+      const int ns = cp->paired_end ? SPRING_B200_NUM_BLOCK_STREAMS : SPRING_B200_NUM_BLOCK_STREAMS - 2;
+      parallel_ranges(b.num_blocks, [&](size_t lo, size_t hi) {
+        for (size_t blk = lo; blk < hi; blk++)
+          for (int st = 0; st < ns; st++)
+            spill(dir + "/" + files[st] + "." + std::to_string(blk), b.data[st] + b.off[st][blk], b.off[st][blk + 1] - b.off[st][blk]);
+      });
+    };
+    // The streams spring_b200_reorder_encode_files wrote into this temp_dir are still resident in HBM (same context,
+    // nothing ran in between): no need to read the files back and upload them.  SPRING_B200_REBLOCK_FROM_FILES=1 forces
+    // the file path.
+    if (ctx->have_enc && ctx->files_dir == dir && ctx->last_enc.num_reads == cp->num_reads && !getenv("SPRING_B200_REBLOCK_FROM_FILES")) {
+      spring_b200_blocks b{};
+      reblock(ctx, nullptr, cp, &b);
+      finish(b);
+      return;
+    }
     // the encoder's stream files (reorder_compress_streams.cpp:91-172)
     std::vector<uint8_t> f_pos = slurp(dir + "/read_pos.bin", true), f_noise = slurp(dir + "/read_noise.txt", true);
     std::vector<uint8_t> f_np = slurp(dir + "/read_noisepos.bin", true), f_rev = slurp(dir + "/read_rev.txt", true);
@@ -658,15 +793,7 @@ int spring_b200_reblock_files(spring_b200_ctx *ctx, const char *temp_dir, const 
     s.num_aligned = f_rev.size(); s.num_reads = cp->num_reads;
     spring_b200_blocks b{};
     reblock(ctx, &s, cp, &b);
-    static const char *files[SPRING_B200_NUM_BLOCK_STREAMS] = {"read_flag.txt", "read_pos.bin", "read_noise.txt", "read_noisepos.bin",
-        "read_rev.txt", "read_unaligned.txt", "read_lengths.bin", "read_pos_pair.bin", "read_rev_pair.txt"};
-    for (const char *f : {"read_noise.txt", "read_noisepos.bin", "read_rev.txt", "read_order.bin", "read_lengths.bin",
-                          "read_unaligned.txt", "read_pos.bin", "read_unaligned.txt.count"})
-      unlink((dir + "/" + f).c_str());  // :153, :174-181
-    const int ns = cp->paired_end ? SPRING_B200_NUM_BLOCK_STREAMS : SPRING_B200_NUM_BLOCK_STREAMS - 2;
-    for (uint32_t blk = 0; blk < b.num_blocks; blk++)
-      for (int st = 0; st < ns; st++)
-        spill(dir + "/" + files[st] + "." + std::to_string(blk), b.data[st] + b.off[st][blk], b.off[st][blk + 1] - b.off[st][blk]);
+    finish(b);
   });
 }
 
@@ -677,6 +804,149 @@ int spring_b200_bucket_reads(spring_b200_ctx *ctx, const uint64_t *reads, const 
     if (num_reads && (!reads || !lengths || !bucket)) throw ArgError("null pointer");
     bucket_reads(ctx->c, reads, lengths, num_reads, (int)max_readlen, num_buckets, bucket);
   });
+}
+
+// ---- multi-GPU ------------------------------------------------------------------------------------------------
+int spring_b200_comm_unique_id(uint8_t *id) {
+  if (!id) return SPRING_B200_EINVAL;
+  try { comm_unique_id(id); return SPRING_B200_OK; }
+  catch (const std::exception &e) { g_create_err = e.what(); return SPRING_B200_ECUDA; }
+}
+
+int spring_b200_comm_init(spring_b200_ctx *ctx, const uint8_t *id, int rank, int world) {
+  return guarded(ctx, [&] {
+    if (!id) throw ArgError("null id");
+    if (ctx->comm) { comm_destroy(ctx->comm); ctx->comm = nullptr; }
+    ctx->comm = comm_create(id, rank, world);
+  });
+}
+
+int spring_b200_comm_free(spring_b200_ctx *ctx) {
+  return guarded(ctx, [&] {
+    if (ctx->comm) { SB_CUDA(cudaStreamSynchronize(ctx->c.stream)); comm_destroy(ctx->comm); ctx->comm = nullptr; }
+  });
+}
+
+int spring_b200_exchange_reads(spring_b200_ctx *ctx, const uint64_t *reads, const uint16_t *lengths, const uint32_t *ids,
+                               uint32_t num_reads, uint32_t max_readlen, spring_b200_exchanged *out) {
+  return guarded(ctx, [&] {
+    if (!out) throw ArgError("null output");
+    if (max_readlen < 1 || max_readlen > (uint32_t)kMaxReadLen) throw ArgError("Wrong bitset size. (max_readlen must be 1..511)");
+    if (num_reads && (!reads || !lengths || !ids)) throw ArgError("null pointer");
+    if (num_reads >= 0x7FFFFFF0u) throw ArgError("too many reads for one GPU shard (>= 2^31)");
+    ExchangeDev x;
+    run_exchange(ctx->c, ctx->comm, reads, lengths, ids, num_reads, (int)max_readlen, x);
+    memset(out, 0, sizeof(*out));
+    out->reads = x.reads; out->lengths = x.lens; out->ids = x.ids; out->num_reads = x.n;
+    out->sent_to_peers = x.sent_to_peers; out->received_from_peers = x.received_from_peers;
+    ctx->stats.ms_exchange = 0;  // read lazily: the exchange is still in flight on the stream
+  });
+}
+
+int spring_b200_finalize_shard(spring_b200_ctx *ctx, const uint32_t *ids, uint32_t num_owned, const uint32_t *n_ids, uint32_t num_n,
+                               spring_b200_shard_layout *out) {
+  return guarded(ctx, [&] {
+    if (!out) throw ArgError("null output");
+    if (!ctx->have_enc) throw ArgError("no streams resident on the device (run spring_b200_reorder_encode_device first)");
+    if ((num_owned && !ids) || (num_n && !n_ids)) throw ArgError("null pointer");
+    ShardLayout l;
+    run_finalize_shard(ctx->c, ctx->comm, ctx->last_enc, ids, num_owned, n_ids, num_n, l);
+    out->rank = l.rank; out->world = l.world; out->seq_base = l.seq_base; out->aligned_before = l.aligned_before;
+    out->noise_before = l.noise_before; out->num_noise_before = l.num_noise_before;
+    out->unaligned_reads_before = l.unaligned_reads_before; out->unaligned_bytes_before = l.unaligned_bytes_before;
+    out->total_seq_len = l.total_seq_len; out->total_aligned = l.total_aligned; out->total_reads = l.total_reads;
+    out->total_noise_bytes = l.total_noise_bytes; out->total_num_noise = l.total_num_noise;
+    out->total_unaligned_bytes = l.total_unaligned_bytes; out->total_unaligned_len = l.total_unaligned_len;
+    ctx->stats.ms_exchange = exchange_ms(ctx->c);
+  });
+}
+
+namespace {
+struct MergedOwner {
+  std::vector<uint64_t> pos; std::vector<uint8_t> noise; std::vector<uint16_t> noisepos; std::vector<uint8_t> rev;
+  std::vector<uint32_t> order; std::vector<uint16_t> lengths; std::vector<uint8_t> unaligned;
+  std::vector<const uint8_t *> shard_seq; std::vector<uint64_t> shard_seq_len;
+};
+}  // namespace
+
+// What the reference's merge of its per-thread files does (src/encoder.h:386-453): every shard's aligned part in shard
+// order, then every shard's unaligned part.  The shards are finalized (absolute positions, global ids), so this is pure
+// concatenation; the big copies run on one host thread per stream.
+int spring_b200_merge_shards(const spring_b200_streams *shards, int n, spring_b200_merged *out) {
+  if (!shards || n < 1 || !out) return SPRING_B200_EINVAL;
+  try {
+    auto *o = new MergedOwner();
+    uint64_t na = 0, nr = 0, nb = 0, nn = 0, ub = 0, ul = 0, sl = 0;
+    for (int i = 0; i < n; i++) {
+      const spring_b200_streams &s = shards[i];
+      if (s.num_aligned > s.num_reads || s.noise_bytes != s.num_noise + s.num_aligned) { delete o; return SPRING_B200_EINVAL; }
+      na += s.num_aligned; nr += s.num_reads; nb += s.noise_bytes; nn += s.num_noise; ub += s.unaligned_bytes; ul += s.unaligned_len;
+      sl += s.seq_len;
+      o->shard_seq.push_back(s.seq_packed); o->shard_seq_len.push_back(s.seq_len);
+    }
+    o->pos.resize(na); o->noise.resize(nb); o->noisepos.resize(nn); o->rev.resize(na); o->order.resize(nr); o->lengths.resize(nr);
+    o->unaligned.resize(ub);
+    std::vector<std::thread> th;
+    auto cat = [&](auto *dst, auto field, auto count) {
+      th.emplace_back([=] {
+        size_t at = 0;
+        for (int i = 0; i < n; i++) {
+          const size_t c = count(shards[i]);
+          if (c) memcpy(dst + at, field(shards[i]), c * sizeof(*dst));
+          at += c;
+        }
+      });
+    };
+    cat(o->pos.data(), [](const spring_b200_streams &s) { return s.pos; }, [](const spring_b200_streams &s) { return (size_t)s.num_aligned; });
+    cat(o->noise.data(), [](const spring_b200_streams &s) { return s.noise; }, [](const spring_b200_streams &s) { return (size_t)s.noise_bytes; });
+    cat(o->noisepos.data(), [](const spring_b200_streams &s) { return s.noisepos; }, [](const spring_b200_streams &s) { return (size_t)s.num_noise; });
+    cat(o->rev.data(), [](const spring_b200_streams &s) { return s.rev; }, [](const spring_b200_streams &s) { return (size_t)s.num_aligned; });
+    cat(o->unaligned.data(), [](const spring_b200_streams &s) { return s.unaligned; }, [](const spring_b200_streams &s) { return (size_t)s.unaligned_bytes; });
+    // order / lengths: aligned parts of all shards, then the unaligned parts
+    th.emplace_back([=] {
+      size_t at = 0;
+      for (int i = 0; i < n; i++) { const size_t c = shards[i].num_aligned; if (c) { memcpy(o->order.data() + at, shards[i].order, c * 4); memcpy(o->lengths.data() + at, shards[i].lengths, c * 2); } at += c; }
+      for (int i = 0; i < n; i++) {
+        const size_t a0 = shards[i].num_aligned, c = shards[i].num_reads - a0;
+        if (c) { memcpy(o->order.data() + at, shards[i].order + a0, c * 4); memcpy(o->lengths.data() + at, shards[i].lengths + a0, c * 2); }
+        at += c;
+      }
+    });
+    for (auto &t : th) t.join();
+    memset(out, 0, sizeof(*out));
+    spring_b200_streams &m = out->streams;
+    m.seq_packed = nullptr; m.seq_len = sl; m.pos = o->pos.data(); m.noise = o->noise.data(); m.noise_bytes = nb;
+    m.noisepos = o->noisepos.data(); m.num_noise = nn; m.rev = o->rev.data(); m.order = o->order.data(); m.lengths = o->lengths.data();
+    m.unaligned = o->unaligned.data(); m.unaligned_bytes = ub; m.unaligned_len = ul; m.num_aligned = na; m.num_reads = nr;
+    for (int i = 0; i < n; i++) { m.singletons_aligned += shards[i].singletons_aligned; m.n_reads_aligned += shards[i].n_reads_aligned; }
+    out->num_shards = n; out->shard_seq = o->shard_seq.data(); out->shard_seq_len = o->shard_seq_len.data(); out->owner = o;
+    return SPRING_B200_OK;
+  } catch (const std::exception &e) { g_create_err = e.what(); return SPRING_B200_ECUDA; }
+}
+
+void spring_b200_free_merged(spring_b200_merged *m) {
+  if (!m || !m->owner) return;
+  delete static_cast<MergedOwner *>(m->owner);
+  memset(m, 0, sizeof(*m));
+}
+
+int spring_b200_write_merged(const char *temp_dir, const spring_b200_merged *m) {
+  if (!temp_dir || !m || m->num_shards < 1) return SPRING_B200_EINVAL;
+  try {
+    const std::string dir(temp_dir);
+    static const char code2char[4] = {'A', 'C', 'G', 'T'};
+    for (int t = 0; t < m->num_shards; t++) {  // one read_seq.bin.<t> per shard, its last len % 4 bases as ASCII in .tail
+      const uint64_t len = m->shard_seq_len[t], full = len / 4;
+      const std::string base = dir + "/read_seq.bin." + std::to_string(t);
+      spill(base, m->shard_seq[t], full);
+      std::string tail;
+      for (uint64_t x = full * 4; x < len; x++) tail.push_back(code2char[(m->shard_seq[t][x / 4] >> (2 * (x & 3))) & 3]);
+      spill(base + ".tail", tail.data(), tail.size());
+    }
+    write_stream_files(dir, &m->streams);
+    return SPRING_B200_OK;
+  } catch (const IoError &e) { g_create_err = e.what(); return SPRING_B200_EIO;
+  } catch (const std::exception &e) { g_create_err = e.what(); return SPRING_B200_ECUDA; }
 }
 
 int spring_b200_write_streams(spring_b200_ctx *ctx, const char *temp_dir, const spring_b200_streams *s, int num_shards) {
@@ -700,8 +970,8 @@ int spring_b200_reorder_encode_files(spring_b200_ctx *ctx, const char *temp_dir,
     uint16_t *h_lens = c.pool.pin<uint16_t>("file.lens", n ? n : 1);
     const std::string f1 = dir + "/input_clean_1.dna", f2 = dir + "/input_clean_2.dna";
     const std::string fn = dir + "/input_N.dna", fo = dir + "/read_order_N.bin";
-    { auto b = slurp(f1, true); parse_dna(b, n0, W, L, h_reads, h_lens, "input_clean_1.dna"); }
-    if (cp->paired_end) { auto b = slurp(f2, true); parse_dna(b, n1, W, L, h_reads + (size_t)n0 * W, h_lens + n0, "input_clean_2.dna"); }
+    { MappedFile b(f1, true); parse_dna(b, n0, W, L, h_reads, h_lens, "input_clean_1.dna"); }
+    if (cp->paired_end) { MappedFile b(f2, true); parse_dna(b, n1, W, L, h_reads + (size_t)n0 * W, h_lens + n0, "input_clean_2.dna"); }
     std::vector<uint8_t> nrec = slurp(fn, false), nord = slurp(fo, false);
     spring_b200_input in{};
     in.reads = h_reads; in.lengths = h_lens; in.num_clean = n; in.max_readlen = L;
@@ -713,6 +983,7 @@ int spring_b200_reorder_encode_files(spring_b200_ctx *ctx, const char *temp_dir,
     // inputs are consumed, as in the reference (reorder.h:232,241; encoder.h:606; encoder.cpp:218)
     unlink(f1.c_str()); unlink(f2.c_str()); unlink(fn.c_str()); unlink(fo.c_str());
     write_streams(dir, &s, cp->num_thr > 0 ? cp->num_thr : 1);
+    ctx->files_dir = dir;
   });
 }
 

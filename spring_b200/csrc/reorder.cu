@@ -311,8 +311,11 @@ __device__ bool chain_search(const ChainArgs &a, const uint64_t *ref, const uint
       const int s = S + sub + 8 * j;
       if (s >= s_lo && s < s_hi) {
         okm |= 1u << j;
-        const uint64_t key = window_key(src, kbase + kstep * s, d.key_bits);
-        if (filter_test_hint(d.filter, d.filter_mask, mix64(key), pol_keep)) cand |= 1u << j;
+        const uint64_t hk = mix64(window_key(src, kbase + kstep * s, d.key_bits));
+        if (filter_test_hint(d.filter, d.filter_mask, hk, pol_keep)) {
+          cand |= 1u << j;
+          if (a.prefetch_slots) asm volatile("prefetch.global.L2 [%0];" ::"l"(d.slots + ((uint32_t)hk & d.slot_mask)));
+        }
       }
     }
     probes_issued += (unsigned)__popc(okm);  // per-lane partial sum, reduced when the chain ends
@@ -795,41 +798,28 @@ void run_reorder(Ctx &c, const uint64_t *reads, const uint16_t *lens, uint32_t n
   if (n == 0) return;
 
   const bool lockstep = c.lockstep;
-  // The deterministic schedule is a cooperative launch of the warp-per-chain kernel below (8 warps x 3 blocks per SM).
-  // The free-running schedule runs chains2.cu: 16-lane chains, two per warp (SPRING_B200_LANES=32: one per warp;
-  // SPRING_B200_CHAINS_V1=1: the round-1 warp-per-chain kernel of this file, kept for A/B measurements, with
-  // SPRING_B200_KCFG=8x3|8x4|8x5|8x6|4x7|4x9 choosing its launch bounds).
+  // launch configuration: warps per block x minimum blocks per SM.  The deterministic schedule is a cooperative launch
+  // and keeps 8 x 3; the free-running one defaults to kChainCfgDefault (SPRING_B200_KCFG=8x3|8x4|8x5|8x6|4x7|4x9
+  // overrides it: occupancy experiments).
   void (*kern)(ChainArgs) = k_chains<true, 8, 3>;
   int kWarpsPerBlock = 8;
-  const bool v1 = lockstep || getenv("SPRING_B200_CHAINS_V1") != nullptr;
-  int lanes = 16;
-  if (const char *e = getenv("SPRING_B200_LANES")) lanes = atoi(e) == 32 ? 32 : 16;
-  uint32_t chains_per_block, max_chains;
-  size_t smem = 0;
-  if (v1) {
-    if (!lockstep) {
-      const char *cfg = getenv("SPRING_B200_KCFG");
-      const std::string want = cfg ? cfg : kChainCfgDefault;
-      if (want == "8x4") { kern = k_chains<false, 8, 4>; kWarpsPerBlock = 8; }
-      else if (want == "8x5") { kern = k_chains<false, 8, 5>; kWarpsPerBlock = 8; }
-      else if (want == "8x6") { kern = k_chains<false, 8, 6>; kWarpsPerBlock = 8; }
-      else if (want == "4x9") { kern = k_chains<false, 4, 9>; kWarpsPerBlock = 4; }
-      else if (want == "4x7") { kern = k_chains<false, 4, 7>; kWarpsPerBlock = 4; }
-      else { kern = k_chains<false, 8, 3>; kWarpsPerBlock = 8; }
-    }
-    smem = kWarpsPerBlock * chain_smem_words(W, Lp) * sizeof(uint64_t);
-    SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 0;
-    SB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kWarpsPerBlock * 32, smem));
-    if (per_sm < 1) throw CudaError("k_chains does not fit on an SM");
-    chains_per_block = (uint32_t)kWarpsPerBlock;
-    max_chains = (uint32_t)per_sm * c.num_sms * chains_per_block;
-  } else {
-    const Chains2Config cc = chains2_config(W, lanes);
-    if (cc.max_blocks_per_sm < 1) throw CudaError("k_chains2 does not fit on an SM");
-    chains_per_block = (uint32_t)cc.chains_per_block;
-    max_chains = (uint32_t)cc.max_blocks_per_sm * c.num_sms * chains_per_block;
+  if (!lockstep) {
+    const char *cfg = getenv("SPRING_B200_KCFG");
+    const std::string want = cfg ? cfg : kChainCfgDefault;
+    if (want == "8x4") { kern = k_chains<false, 8, 4>; kWarpsPerBlock = 8; }
+    else if (want == "8x5") { kern = k_chains<false, 8, 5>; kWarpsPerBlock = 8; }
+    else if (want == "8x6") { kern = k_chains<false, 8, 6>; kWarpsPerBlock = 8; }
+    else if (want == "4x9") { kern = k_chains<false, 4, 9>; kWarpsPerBlock = 4; }
+    else if (want == "4x7") { kern = k_chains<false, 4, 7>; kWarpsPerBlock = 4; }
+    else { kern = k_chains<false, 8, 3>; kWarpsPerBlock = 8; }
   }
+  const size_t smem = kWarpsPerBlock * chain_smem_words(W, Lp) * sizeof(uint64_t);
+  SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  SB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kWarpsPerBlock * 32, smem));
+  if (per_sm < 1) throw CudaError("k_chains does not fit on an SM");
+  const uint32_t chains_per_block = (uint32_t)kWarpsPerBlock;
+  const uint32_t max_chains = (uint32_t)per_sm * c.num_sms * chains_per_block;
   uint32_t C = num_chains;
   if (C == 0) {  // auto: every co-resident chain, as long as a chain's slice keeps >= 256 reads
     C = n / 256; if (C < 1) C = 1; if (C > max_chains) C = max_chains;
@@ -864,7 +854,7 @@ void run_reorder(Ctx &c, const uint64_t *reads, const uint16_t *lens, uint32_t n
   a.leader_mask = 0;
   for (uint32_t g = 0; g < a.G; g++) a.leader_mask |= 1u << (g * W);
   a.generic_update = getenv("SPRING_B200_GENERIC_UPDATE") ? 1 : 0;
-  a.cnt_scratch = v1 ? nullptr : c.pool.dev<uint64_t>("ro.cnt_scratch", (size_t)nslots * 32 * W);
+  a.prefetch_slots = getenv("SPRING_B200_PREFETCH") ? atoi(getenv("SPRING_B200_PREFETCH")) : 0;
   a.steal_probes = lockstep ? 0 : (getenv("SPRING_B200_STEAL") ? atoi(getenv("SPRING_B200_STEAL")) : 64);
   a.max_rounds = 8ull * n + 4096ull;
   SB_CUDA(cudaMemsetAsync(a.claimed, 0, bm_words * sizeof(uint32_t), st));
@@ -878,8 +868,7 @@ void run_reorder(Ctx &c, const uint64_t *reads, const uint16_t *lens, uint32_t n
   if (!c.ev_k0) { SB_CUDA(cudaEventCreate(&c.ev_k0)); SB_CUDA(cudaEventCreate(&c.ev_k1)); }
   SB_CUDA(cudaEventRecord(c.ev_k0, st));
   if (lockstep) SB_CUDA(cudaLaunchCooperativeKernel((void *)kern, dim3(grid), dim3(kWarpsPerBlock * 32), args, smem, st));
-  else if (v1) kern<<<grid, kWarpsPerBlock * 32, smem, st>>>(a);
-  else chains2_launch(a, lanes, grid, st);
+  else kern<<<grid, kWarpsPerBlock * 32, smem, st>>>(a);
   SB_CUDA(cudaEventRecord(c.ev_k1, st));
   c.launches++;
 

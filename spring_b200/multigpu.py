@@ -119,3 +119,24 @@ def merge_rank_streams(parts: list, id_maps: list) -> MergedStreams:
     return MergedStreams(shards, cat(pos, np.uint64), cat(noise, np.uint8), cat(noisepos, np.uint16), cat(rc, np.uint8),
                          cat(order_a + order_u, np.uint32), cat(len_a + len_u, np.uint16), cat(unal, np.uint8), ul,
                          int(sum(int(s.num_aligned) for s in parts)))
+
+
+def init_comm(ctx, rank: int, world: int, device=None) -> None:
+    """Create the library's NCCL communicator on every rank: rank 0 makes the unique id, torch.distributed (any
+    backend) broadcasts its 128 bytes."""
+    from . import capi
+    buf = torch.zeros(128, dtype=torch.uint8, device=device if device is not None else "cpu")
+    if rank == 0:
+        buf.copy_(torch.frombuffer(bytearray(capi.comm_unique_id()), dtype=torch.uint8))
+    dist.broadcast(buf, src=0)
+    ctx.comm_init(bytes(buf.cpu().numpy().tobytes()), rank, world)
+
+
+def global_ids(n_local: int, rank: int, world: int, paired: bool, device) -> torch.Tensor:
+    """Global index (position in the whole job's FASTQ order, file 2 after file 1) of local read i when every rank holds
+    one block of n_local reads -- for paired input a block of n_local / 2 pairs, file-1 mates first."""
+    i = torch.arange(n_local, device=device, dtype=torch.int64)
+    if not paired:
+        return (rank * n_local + i).to(torch.int32)
+    half_l, half_g = n_local // 2, n_local * world // 2
+    return torch.where(i < half_l, rank * half_l + i, half_g + rank * half_l + (i - half_l)).to(torch.int32)

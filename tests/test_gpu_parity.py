@@ -144,14 +144,17 @@ def test_edge_cases(ctx):
     assert e.value.code == -1 and "Wrong bitset size" in str(e.value)
 
 
-def test_file_level_drop_in(ctx):
+@pytest.mark.parametrize("name", ["pe100_illumina", "pe_var", "se150"])
+def test_file_level_drop_in(ctx, name):
     """spring_b200_reorder_encode_files on a temp_dir laid out by preprocess: same files the
-    reference's call_reorder + call_encoder leave, inputs consumed."""
-    hp = make_input(**CASES["pe100_illumina"])
+    reference's call_reorder + call_encoder leave, inputs consumed (fixed-length records take the
+    sliced multi-threaded copy, mixed lengths the header walk)."""
+    hp = make_input(**CASES[name])
     _, er = po.reorder_encode(hp.packed, hp.lengths, hp.max_readlen, hp.n_records, hp.order_n, hp.num_reads, 1)
     with tempfile.TemporaryDirectory() as d:
         cpy = dnaio.write_hotpath_inputs(d, hp.packed, hp.lengths, max_readlen=hp.max_readlen, n_seqs=hp.n_seqs,
-                                         order_n=hp.order_n, num_reads=hp.num_reads, paired_split=hp.num_clean[0], num_thr=3)
+                                         order_n=hp.order_n, num_reads=hp.num_reads,
+                                         paired_split=hp.num_clean[0] if hp.paired else None, num_thr=3)
         os.remove(os.path.join(d, "cp_in.bin"))
         cp = capi.CP.from_buffer_copy(cpy.pack())
         ctx.reorder_encode_files(d, cp, 1)

@@ -37,33 +37,38 @@ struct LimitError : std::runtime_error {
   } while (0)
 
 // ---- dictionary in HBM ------------------------------------------------------------------------
-// One open-addressing slot per unique key.  16 B so a probe is one aligned uint4 load (one 32 B
-// sector).  Replaces BooPHF + startpos[] + empty_bin[] (bitset_util.h:22-41): the key is stored,
-// so the reference's "verify against the first read of the bin" step (reorder.h:282-285) is folded
-// into the probe, and `live` -- decremented when a read of the bin is claimed -- plays the role of
-// bbhashdict::remove / empty_bin (bitset_util.cpp:37-63): a bin whose reads are all gone is skipped
-// by the probe itself, without touching the bin.
-// 32 B = one sector: the bin's size and its three highest read ids ride along with the key, so a
-// hit on a bin of <= 3 reads (almost all of them) needs no access to bins[] at all.
+// One open-addressing slot per unique key, 32 B = one sector per probe.  Replaces BooPHF + startpos[] + empty_bin[]
+// (bitset_util.h:22-41): the (hashed) key is stored, so the reference's "verify against the first read of the bin"
+// step (reorder.h:282-285) is folded into the probe, and `live` -- decremented when a read of the bin is claimed --
+// plays the role of bbhashdict::remove / empty_bin (bitset_util.cpp:37-63): a bin whose reads are all gone is skipped
+// by the probe itself, without touching the bin.  The bin's size and its three highest read ids ride along, so a hit
+// on a bin of <= 3 reads (almost all of them) needs no access to bins[] at all.
+//
+// Placement is ORDERED linear probing: hk = mix64(key) is a bijection of the 64-bit key, the home slot is its top
+// bits, and the keys are inserted in ascending hk (the order the build's radix sort leaves them in), each at the first
+// free slot at or after its home.  So (a) the build writes the table front to back -- coalesced stores, no atomics --
+// and (b) every key between home(x) and x's slot is smaller than x: a lookup stops at the first larger key or empty
+// slot.  The table has kSlotPad spare slots behind the last home instead of wrapping around.
 struct __align__(32) DictSlot {
-  uint64_t key;
+  uint64_t key;     // hk = mix64(window key)
   uint32_t start1;  // 1 + index of the bin header in bins[]; 0 = empty slot
   uint32_t live;    // reads of the bin not yet claimed
   uint32_t count;   // reads in the bin
   uint32_t rid[3];  // the bin's highest ids, descending (bins[start1 .. start1+2])
 };
+constexpr uint32_t kSlotPad = 4096;
 
 // bins[]: per unique key {count, read ids in DESCENDING order}: the reference scans a bin from its
 // highest id down (reorder.h:287-288), so a scan is a forward walk from the header.
 struct DictView {
-  DictSlot *slots;
-  uint32_t slot_mask;            // capacity - 1 (power of two)
+  DictSlot *slots;               // [capacity + kSlotPad]
+  int slot_shift;                // home slot of hk = hk >> slot_shift (capacity = 2^(64 - slot_shift))
   const uint32_t *bins;
   const uint32_t *slot_of_read;  // [n] slot index holding read i's key, 0xFFFFFFFF if the read is not indexed
   uint32_t *skip;                // [like bins] at a bin's header index: entries before this offset are all claimed
                                  // (monotone hint: a scan of a big bin starts there; plays bbhashdict::remove's compaction)
   const uint32_t *filter;        // blocked Bloom filter over the keys: 2 bits in one 32-bit word, >= 8 bits per key
-  uint32_t filter_mask;          // number of filter words - 1 (power of two)
+  int filter_shift;              // filter word of hk = hk >> filter_shift (top bits: the build sets it front to back too)
   int start, end;                // base window [start, end]
   int key_bits;                  // bits per base * (end - start + 1)
 };
@@ -76,9 +81,11 @@ __host__ __device__ inline uint64_t mix64(uint64_t x) {
   return x;
 }
 
-// key filter (kept L2-resident by the chain kernel): word (hk >> 32) & mask, bits hk[0:5) and hk[5:10)
-__host__ __device__ inline uint32_t filter_word(uint64_t hk, uint32_t wmask) { return (uint32_t)(hk >> 32) & wmask; }
+// key filter (kept L2-resident by the chain kernel as far as it fits): word = top bits of hk, bits hk[0:5) and hk[5:10)
+__host__ __device__ inline uint32_t filter_word(uint64_t hk, int fshift) { return (uint32_t)(hk >> fshift); }
 __host__ __device__ inline uint32_t filter_bits(uint64_t hk) { return (1u << (hk & 31)) | (1u << ((hk >> 5) & 31)); }
+__host__ __device__ inline uint32_t slot_home(uint64_t hk, int sshift) { return (uint32_t)(hk >> sshift); }
+constexpr uint64_t kInvalidKey = ~0ull;  // hk of a read that is not indexed (too short for the window, N inside it)
 
 __host__ __device__ inline int words_for(int max_readlen) { return (2 * max_readlen - 1) / 64 + 1; }
 
@@ -134,9 +141,9 @@ __device__ __forceinline__ uint64_t spread_bits(uint32_t x) {
 }
 __device__ __forceinline__ int base_code(const uint64_t *w, int j) { return (int)((w[j >> 5] >> (2 * (j & 31))) & 3ull); }
 
-__device__ __forceinline__ bool filter_test(const uint32_t *filter, uint32_t wmask, uint64_t hk) {
+__device__ __forceinline__ bool filter_test(const uint32_t *filter, int fshift, uint64_t hk) {
   const uint32_t b = filter_bits(hk);
-  return (__ldg(filter + filter_word(hk, wmask)) & b) == b;
+  return (__ldg(filter + filter_word(hk, fshift)) & b) == b;
 }
 // L2 eviction policies: the key filter should stay in L2, the slot table streams through it
 __device__ __forceinline__ uint64_t l2_policy_evict_last() {
@@ -149,10 +156,10 @@ __device__ __forceinline__ uint64_t l2_policy_evict_first() {
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
   return p;
 }
-__device__ __forceinline__ bool filter_test_hint(const uint32_t *filter, uint32_t wmask, uint64_t hk, uint64_t pol) {
+__device__ __forceinline__ bool filter_test_hint(const uint32_t *filter, int fshift, uint64_t hk, uint64_t pol) {
   const uint32_t b = filter_bits(hk);
   uint32_t w;
-  asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(w) : "l"(filter + filter_word(hk, wmask)), "l"(pol));
+  asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(w) : "l"(filter + filter_word(hk, fshift)), "l"(pol));
   return (w & b) == b;
 }
 // L2 (.cg) load: `live` is updated by other SMs between rounds, L1 must not serve it
@@ -188,14 +195,14 @@ __device__ __forceinline__ DictSlot load_slot_head(const DictSlot *p) {  // key 
   s.count = 0; s.rid[0] = s.rid[1] = s.rid[2] = 0;
   return s;
 }
-// exact lookup in a dictionary nobody is updating: header index of the bin, or -1
-__device__ __forceinline__ long long dict_find(const DictView &d, uint64_t key) {
-  uint32_t h = (uint32_t)mix64(key) & d.slot_mask;
+// exact lookup in a dictionary nobody is updating: header index of the bin, or -1 (hk = mix64(key))
+__device__ __forceinline__ long long dict_find(const DictView &d, uint64_t hk) {
+  uint32_t h = slot_home(hk, d.slot_shift);
   for (;;) {
     DictSlot s = load_slot_head(d.slots + h);
-    if (s.start1 == 0) return -1;
-    if (s.key == key) return (long long)s.start1 - 1;
-    h = (h + 1) & d.slot_mask;
+    if (s.start1 == 0 || s.key > hk) return -1;
+    if (s.key == hk) return (long long)s.start1 - 1;
+    h++;
   }
 }
 #endif

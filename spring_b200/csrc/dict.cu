@@ -1,93 +1,122 @@
 // dict.cu -- dictionary construction in HBM.
 //
-// Replaces constructdictionary<> (reference src/bitset_util.h:74-221): window key per read ->
-// (drop reads shorter than the window) -> sort -> unique keys -> bins with ascending read ids.
-// The reference maps key -> bin through BooPHF and a CSR startpos[]; here the unique keys go into
-// an open-addressing table of 32-byte slots {key, bin start, live count, bin size, three highest ids}
-// (one 32 B sector per probe),
-// and read_id[] is the value array of a stable radix sort of (key, read id) pairs, so ids are
-// ascending inside every bin exactly as bitset_util.h:188-206 leaves them.
+// Replaces constructdictionary<> (reference src/bitset_util.h:74-221): window key per read -> (drop reads shorter
+// than the window) -> sort -> unique keys -> bins with ascending read ids.  The reference maps key -> bin through
+// BooPHF and a CSR startpos[]; here the unique keys go into an open-addressing table of 32-byte slots {hashed key, bin
+// start, live count, bin size, three highest ids} (one 32 B sector per probe), and read_id[] is the value array of a
+// stable radix sort of (hashed key, read id) pairs, so ids are ascending inside every bin exactly as
+// bitset_util.h:188-206 leaves them.
+//
+// The sort key is hk = mix64(key), a bijection of the 64-bit key, and a slot's home is the top bits of hk: sorted order
+// IS table order.  Slot of the k-th unique key = k + max_{j <= k}(home_j - j) -- the first free slot at or after its
+// home when the keys go in ascending -- is one running-max scan; the table, the bins and the key filter (word = top
+// bits of hk as well) are then written front to back with plain coalesced stores, no atomics, no probing.
+//
+// No host synchronisation: reads that are not indexed get hk = ~0 and sort behind everything, the number of unique keys
+// stays on the device (kernels are launched over the upper bound n and read it there), the table is sized from n.
+#include <climits>
 #include <cub/cub.cuh>
 #include "kernels.cuh"
 
 namespace sb {
 
-// key = ((read & mask1) >> 2*start).to_ullong()  (bitset_util.h:93-94).  One thread per read; a warp
-// touches 32 consecutive rows of W words (coalesced across the warp's combined footprint).
+namespace {
+
+struct MaxOp {
+  __device__ int operator()(int a, int b) const { return a > b ? a : b; }
+};
+
+// hk = mix64((read & mask1) >> 2*start) (bitset_util.h:93-94), ~0 for a read that is not indexed.  One thread per
+// read; a warp touches 32 consecutive rows of W words (coalesced across the warp's combined footprint).
 __global__ void k_extract_keys(const uint64_t *__restrict__ reads, const uint16_t *__restrict__ lens,
                                const uint64_t *__restrict__ nflag, uint32_t n, int W, int start, int end,
-                               uint64_t *__restrict__ keys, uint32_t *__restrict__ rids, uint8_t *__restrict__ valid) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const uint64_t *r = reads + (size_t)i * W;
-  int nbits = 2 * (end - start + 1);
-  uint64_t key = extract_bits(r, W, 2 * start, nbits);
-  bool ok = lens[i] > end;  // bitset_util.h:99-105
-  if (ok && nflag) ok = extract_bits(nflag + (size_t)i * W, W, 2 * start, nbits) == 0;
-  keys[i] = key;
-  rids[i] = i;
-  valid[i] = ok ? 1 : 0;
+                               uint64_t *__restrict__ hkeys, uint32_t *__restrict__ rids, uint32_t *__restrict__ num_valid) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  bool ok = false;
+  if (i < n) {
+    const uint64_t *r = reads + (size_t)i * W;
+    const int nbits = 2 * (end - start + 1);
+    uint64_t hk = mix64(extract_bits(r, W, 2 * start, nbits));
+    ok = lens[i] > end;  // bitset_util.h:99-105
+    if (ok && nflag) ok = extract_bits(nflag + (size_t)i * W, W, 2 * start, nbits) == 0;
+    if (hk == kInvalidKey) ok = false;  // one key in 2^64 shares the marker: its reads simply stay unindexed
+    hkeys[i] = ok ? hk : kInvalidKey;
+    rids[i] = i;
+  }
+  const int c = __syncthreads_count(ok);
+  if (threadIdx.x == 0 && c) atomicAdd(num_valid, (uint32_t)c);
 }
 
-__global__ void k_mark_heads(const uint64_t *__restrict__ keys, uint32_t n, uint8_t *__restrict__ head,
-                             uint32_t *__restrict__ head32) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void k_mark_heads(const uint64_t *__restrict__ hkeys, uint32_t n, uint8_t *__restrict__ head, uint32_t *__restrict__ head32) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const uint32_t h = (i == 0 || keys[i] != keys[i - 1]) ? 1 : 0;
+  const uint64_t k = hkeys[i];
+  const uint32_t h = (k != kInvalidKey && (i == 0 || k != hkeys[i - 1])) ? 1 : 0;
   head[i] = (uint8_t)h;
   head32[i] = h;
 }
 
-// bin k (sorted entries [s, e)) gets header index s + k in bins[] and one slot in the table
-__global__ void k_insert_slots(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ bin_start_idx,
-                               uint32_t numkeys, uint32_t n_valid, DictSlot *slots, uint32_t mask, uint32_t *bins,
-                               uint32_t *slot_of_bin) {
-  uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= numkeys) return;
-  uint32_t s = bin_start_idx[k];
-  uint32_t e = (k + 1 < numkeys) ? bin_start_idx[k + 1] : n_valid;
-  uint64_t key = keys[s];
-  uint32_t h = (uint32_t)mix64(key) & mask;
-  bins[s + k] = e - s;
-  for (;;) {
-    if (atomicCAS(&slots[h].start1, 0u, s + k + 1) == 0u) {  // keys are unique: no key compare needed
-      slots[h].key = key;
-      slots[h].live = e - s;
-      slots[h].count = e - s;
-      slot_of_bin[k] = h;
-      return;
-    }
-    h = (h + 1) & mask;
-  }
+// home_k - k for the running max (INT_MIN beyond the last key)
+__global__ void k_home_minus_rank(const uint64_t *__restrict__ hkeys, const uint32_t *__restrict__ bin_start_idx,
+                                  const uint32_t *__restrict__ numkeys, uint32_t n, int slot_shift, int *__restrict__ v) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  v[k] = k < *numkeys ? (int)slot_home(hkeys[bin_start_idx[k]], slot_shift) - (int)k : INT_MIN;
 }
 
-// key filter: 2 bits in one word per key, >= 8 bits per key => ~5 % false positives in half the
-// footprint of a 1-hash bitmap (32 MB for both dictionaries of 10 M reads: fits one L2 partition)
-__global__ void k_set_filter(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ bin_start_idx, uint32_t numkeys,
-                             uint32_t *filter, uint32_t filter_mask) {
-  uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= numkeys) return;
-  const uint64_t hk = mix64(keys[bin_start_idx[k]]);
-  atomicOr(filter + filter_word(hk, filter_mask), filter_bits(hk));
+// bin k (sorted entries [s, e)) gets header index s + k in bins[], slot k + m[k] of the table and its filter bits
+__global__ void k_insert_slots(const uint64_t *__restrict__ hkeys, const uint32_t *__restrict__ rid_sorted,
+                               const uint32_t *__restrict__ bin_start_idx, const uint32_t *__restrict__ numkeys_p,
+                               const uint32_t *__restrict__ num_valid, const int *__restrict__ m, uint32_t n, uint32_t slot_limit,
+                               int filter_shift, DictSlot *slots, uint32_t *bins, uint32_t *slot_of_bin, uint32_t *filter,
+                               uint32_t *dropped) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t numkeys = *numkeys_p;
+  if (k >= n || k >= numkeys) return;
+  const uint32_t s = bin_start_idx[k];
+  const uint32_t e = (k + 1 < numkeys) ? bin_start_idx[k + 1] : *num_valid;
+  const uint64_t hk = hkeys[s];
+  const long long slot = (long long)k + m[k];
+  bins[s + k] = e - s;
+  if (slot >= (long long)slot_limit) {  // a probe chain longer than the spare slots: the bin stays unindexed (ratio only)
+    slot_of_bin[k] = 0xFFFFFFFFu;
+    atomicAdd(dropped, 1u);
+    return;
+  }
+  DictSlot sl;
+  sl.key = hk; sl.start1 = s + k + 1; sl.live = e - s; sl.count = e - s;
+  sl.rid[0] = rid_sorted[e - 1];
+  sl.rid[1] = e - s > 1 ? rid_sorted[e - 2] : 0;
+  sl.rid[2] = e - s > 2 ? rid_sorted[e - 3] : 0;
+  uint4 *dst = reinterpret_cast<uint4 *>(slots + slot);
+  dst[0] = make_uint4((uint32_t)sl.key, (uint32_t)(sl.key >> 32), sl.start1, sl.live);
+  dst[1] = make_uint4(sl.count, sl.rid[0], sl.rid[1], sl.rid[2]);
+  slot_of_bin[k] = (uint32_t)slot;
+  // keys arrive in ascending hk and the filter word is the top bits of hk: neighbouring threads hit neighbouring words
+  atomicOr(filter + filter_word(hk, filter_shift), filter_bits(hk));
 }
 
 // sorted entry i (ascending id inside its bin) -> descending position behind the bin header
-__global__ void k_fill_bins(const uint32_t *__restrict__ rid_sorted, const uint32_t *__restrict__ kidx1,
+__global__ void k_fill_bins(const uint64_t *__restrict__ hkeys, const uint32_t *__restrict__ rid_sorted, const uint32_t *__restrict__ kidx1,
                             const uint32_t *__restrict__ bin_start_idx, const uint32_t *__restrict__ slot_of_bin,
-                            uint32_t numkeys, uint32_t n_valid, uint32_t *bins, uint32_t *slot_of_read, DictSlot *slots) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_valid) return;
+                            const uint32_t *__restrict__ numkeys_p, const uint32_t *__restrict__ num_valid, uint32_t n, uint32_t *bins,
+                            uint32_t *slot_of_read) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t rid = rid_sorted[i];
+  if (hkeys[i] == kInvalidKey) { slot_of_read[rid] = 0xFFFFFFFFu; return; }
+  const uint32_t numkeys = *numkeys_p;
   const uint32_t k = kidx1[i] - 1;
   const uint32_t s = bin_start_idx[k];
-  const uint32_t e = (k + 1 < numkeys) ? bin_start_idx[k + 1] : n_valid;
-  const uint32_t rid = rid_sorted[i];
-  const uint32_t dpos = e - 1 - i, sl = slot_of_bin[k];
-  bins[s + k + 1 + dpos] = rid;
-  slot_of_read[rid] = sl;
-  if (dpos < 3) slots[sl].rid[dpos] = rid;
+  const uint32_t e = (k + 1 < numkeys) ? bin_start_idx[k + 1] : *num_valid;
+  bins[s + k + 1 + (e - 1 - i)] = rid;
+  slot_of_read[rid] = slot_of_bin[k];
 }
 
-static inline uint32_t grid_for(uint64_t n, int block) { return (uint32_t)((n + block - 1) / block); }
+inline uint32_t grid_for(uint64_t n, int block) { return (uint32_t)((n + block - 1) / block); }
+inline int log2_pow2(uint64_t v) { int b = 0; while ((1ull << b) < v) b++; return b; }
+
+}  // namespace
 
 void build_dictionary(Ctx &c, const uint64_t *reads, const uint16_t *lens, const uint64_t *nflag, uint32_t n, int W,
                       int start, int end, const char *tag, DictBuild &out) {
@@ -98,104 +127,77 @@ void build_dictionary(Ctx &c, const uint64_t *reads, const uint16_t *lens, const
   out.view.start = start;
   out.view.end = end;
   out.view.key_bits = 2 * (end - start + 1);
-  uint32_t nn = n ? n : 1;
+  const uint32_t nn = n ? n : 1;
   uint64_t *keys_a = c.pool.dev<uint64_t>(nm(".keys_a").c_str(), nn);
   uint64_t *keys_b = c.pool.dev<uint64_t>(nm(".keys_b").c_str(), nn);
   uint32_t *rid_a = c.pool.dev<uint32_t>(nm(".rid_a").c_str(), nn);
-  uint32_t *rid_b = c.pool.dev<uint32_t>(nm(".rid_b").c_str(), nn);
   uint32_t *rid_c = c.pool.dev<uint32_t>(nm(".rid_c").c_str(), nn);
+  uint32_t *bin_start_idx = c.pool.dev<uint32_t>(nm(".bin_start").c_str(), nn);
   uint8_t *flag = c.pool.dev<uint8_t>(nm(".flag").c_str(), nn);
   uint32_t *head32 = c.pool.dev<uint32_t>(nm(".head32").c_str(), nn);
   uint32_t *kidx1 = c.pool.dev<uint32_t>(nm(".kidx1").c_str(), nn);
+  int *hm = c.pool.dev<int>(nm(".home_minus").c_str(), nn), *hmax = c.pool.dev<int>(nm(".home_max").c_str(), nn);
   uint32_t *slot_of_bin = c.pool.dev<uint32_t>(nm(".slot_of_bin").c_str(), nn);
   uint32_t *slot_of_read = c.pool.dev<uint32_t>(nm(".slot_of_read").c_str(), nn);
   uint32_t *bins = c.pool.dev<uint32_t>(nm(".bins").c_str(), 2 * (size_t)nn);
   uint32_t *skip = c.pool.dev<uint32_t>(nm(".skip").c_str(), 2 * (size_t)nn);
+  uint32_t *d_count = c.pool.dev<uint32_t>(nm(".count").c_str(), 4);  // [0] indexed reads, [1] unique keys, [2] dropped bins
   SB_CUDA(cudaMemsetAsync(skip, 0, 2 * (size_t)nn * sizeof(uint32_t), st));
-  out.view.skip = skip;
-  uint32_t *d_count = c.pool.dev<uint32_t>(nm(".count").c_str(), 4);
-  uint32_t *h_count = c.pool.pin<uint32_t>(nm(".hcount").c_str(), 4);
-  if (n == 0) {
-    uint32_t *filter0 = c.pool.dev<uint32_t>(nm(".filter").c_str(), 2048);
-    SB_CUDA(cudaMemsetAsync(filter0, 0, 2048 * sizeof(uint32_t), st));
-    out.view.filter = filter0; out.view.filter_mask = 2047;
-    out.capacity = 16;
-    DictSlot *slots = c.pool.dev<DictSlot>(nm(".slots").c_str(), out.capacity);
-    SB_CUDA(cudaMemsetAsync(slots, 0, sizeof(DictSlot) * out.capacity, st));
-    out.view.slots = slots; out.view.slot_mask = out.capacity - 1; out.view.bins = bins; out.view.slot_of_read = slot_of_read;
-    out.sorted_keys = keys_b; out.bin_start_idx = rid_a; out.sorted_rids = rid_c;
-    return;
-  }
-  k_extract_keys<<<grid_for(n, 256), 256, 0, st>>>(reads, lens, nflag, n, W, start, end, keys_a, rid_a, flag);
-  c.launches++;
-  // compaction of reads shorter than the window (variable-length input only)
-  size_t tmp_bytes = 0, need = 0;
-  cub::DeviceSelect::Flagged(nullptr, need, keys_a, flag, keys_b, d_count, (int)n, st); tmp_bytes = need;
-  cub::DeviceSelect::Flagged(nullptr, need, rid_a, flag, rid_b, d_count, (int)n, st); if (need > tmp_bytes) tmp_bytes = need;
-  cub::DeviceRadixSort::SortPairs(nullptr, need, keys_b, keys_a, rid_b, rid_c, (int)n, 0, out.view.key_bits, st);
-  if (need > tmp_bytes) tmp_bytes = need;
-  cub::DeviceScan::InclusiveSum(nullptr, need, head32, kidx1, (int)n, st);
-  if (need > tmp_bytes) tmp_bytes = need;
-  {
-    cub::CountingInputIterator<uint32_t> cnt(0);
-    cub::DeviceSelect::Flagged(nullptr, need, cnt, flag, rid_a, d_count, (int)n, st);
-    if (need > tmp_bytes) tmp_bytes = need;
-  }
-  void *tmp = c.pool.device(nm(".cubtmp").c_str(), tmp_bytes);
-  need = tmp_bytes;
-  cub::DeviceSelect::Flagged(tmp, need, keys_a, flag, keys_b, d_count, (int)n, st);
-  need = tmp_bytes;
-  cub::DeviceSelect::Flagged(tmp, need, rid_a, flag, rid_b, d_count + 1, (int)n, st);
-  c.launches += 4;
-  SB_CUDA(cudaMemcpyAsync(h_count, d_count, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-  SB_CUDA(cudaStreamSynchronize(st));
-  uint32_t nv = h_count[0];
-  out.dict_numreads = nv;
-  // stable LSD radix sort: read ids stay ascending inside equal keys
-  if (nv) {
-    need = tmp_bytes;
-    cub::DeviceRadixSort::SortPairs(tmp, need, keys_b, keys_a, rid_b, rid_c, (int)nv, 0, out.view.key_bits, st);
-    c.launches += 2 + (out.view.key_bits + 7) / 8 * 2;
-    k_mark_heads<<<grid_for(nv, 256), 256, 0, st>>>(keys_a, nv, flag, head32);
-    need = tmp_bytes;
-    cub::DeviceScan::InclusiveSum(tmp, need, head32, kidx1, (int)nv, st);
-    c.launches += 2;
-    cub::CountingInputIterator<uint32_t> cnt(0);
-    need = tmp_bytes;
-    cub::DeviceSelect::Flagged(tmp, need, cnt, flag, rid_a, d_count + 2, (int)nv, st);
-    c.launches += 3;
-    SB_CUDA(cudaMemcpyAsync(h_count + 2, d_count + 2, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-    SB_CUDA(cudaStreamSynchronize(st));
-    out.numkeys = h_count[2];
-  }
-  // slot indices are 32 bits: at most 2^30 unique keys per dictionary (capacity 2^31)
-  if (out.numkeys > (1u << 30)) throw LimitError("dictionary: more than 2^30 unique keys in one GPU shard");
-  uint32_t cap = 16;
-  while (cap < 2ull * out.numkeys) cap <<= 1;
-  out.capacity = cap;
-  DictSlot *slots = c.pool.dev<DictSlot>(nm(".slots").c_str(), cap);
-  SB_CUDA(cudaMemsetAsync(slots, 0, sizeof(DictSlot) * (size_t)cap, st));
+  SB_CUDA(cudaMemsetAsync(d_count, 0, 4 * sizeof(uint32_t), st));
+  // sized from the upper bound n: load factor <= 1/2 whatever the number of unique keys turns out to be
+  if (n > (1u << 30)) throw LimitError("dictionary: more than 2^30 reads in one GPU shard");
+  uint64_t cap = 16;
+  while (cap < 2ull * n) cap <<= 1;
+  out.capacity = (uint32_t)cap;
+  out.view.slot_shift = 64 - log2_pow2(cap);
+  DictSlot *slots = c.pool.dev<DictSlot>(nm(".slots").c_str(), (size_t)cap + kSlotPad);
+  SB_CUDA(cudaMemsetAsync(slots, 0, sizeof(DictSlot) * ((size_t)cap + kSlotPad), st));
+  static const unsigned long long kFilterBitsPerKey =
+      getenv("SPRING_B200_FILTER_BITS") ? strtoull(getenv("SPRING_B200_FILTER_BITS"), nullptr, 10) : 8ull;
   uint64_t fbits = 65536;
-  static const unsigned long long kFilterBitsPerKey = getenv("SPRING_B200_FILTER_BITS") ? strtoull(getenv("SPRING_B200_FILTER_BITS"), nullptr, 10) : 8ull;
-  while (fbits < kFilterBitsPerKey * out.numkeys && fbits < (1ull << 36)) fbits <<= 1;
+  while (fbits < kFilterBitsPerKey * n && fbits < (1ull << 36)) fbits <<= 1;
   uint32_t *filter = c.pool.dev<uint32_t>(nm(".filter").c_str(), fbits / 32);
   SB_CUDA(cudaMemsetAsync(filter, 0, fbits / 8, st));
   out.view.filter = filter;
-  out.view.filter_mask = (uint32_t)(fbits / 32 - 1);
-  SB_CUDA(cudaMemsetAsync(slot_of_read, 0xFF, sizeof(uint32_t) * (size_t)n, st));
-  if (out.numkeys) {
-    k_insert_slots<<<grid_for(out.numkeys, 256), 256, 0, st>>>(keys_a, rid_a, out.numkeys, nv, slots, cap - 1, bins, slot_of_bin);
-    k_fill_bins<<<grid_for(nv, 256), 256, 0, st>>>(rid_c, kidx1, rid_a, slot_of_bin, out.numkeys, nv, bins, slot_of_read, slots);
-    k_set_filter<<<grid_for(out.numkeys, 256), 256, 0, st>>>(keys_a, rid_a, out.numkeys, filter, out.view.filter_mask);
-    c.launches += 3;
-  }
+  out.view.filter_shift = 64 - log2_pow2(fbits / 32);
   out.view.slots = slots;
-  out.view.slot_mask = cap - 1;
   out.view.bins = bins;
   out.view.slot_of_read = slot_of_read;
-  out.sorted_keys = keys_a;
-  out.bin_start_idx = rid_a;
+  out.view.skip = skip;
+  out.sorted_keys = keys_b;
+  out.bin_start_idx = bin_start_idx;
   out.sorted_rids = rid_c;
+  out.d_counts = d_count;
+  if (n == 0) return;
+
+  size_t tmp_bytes = 0, need = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, need, keys_a, keys_b, rid_a, rid_c, (int)n, 0, 64, st); tmp_bytes = need;
+  cub::DeviceScan::InclusiveSum(nullptr, need, head32, kidx1, (int)n, st); if (need > tmp_bytes) tmp_bytes = need;
+  cub::DeviceScan::InclusiveScan(nullptr, need, hm, hmax, MaxOp(), (int)n, st); if (need > tmp_bytes) tmp_bytes = need;
+  {
+    cub::CountingInputIterator<uint32_t> cnt(0);
+    cub::DeviceSelect::Flagged(nullptr, need, cnt, flag, bin_start_idx, d_count + 1, (int)n, st);
+    if (need > tmp_bytes) tmp_bytes = need;
+  }
+  void *tmp = c.pool.device(nm(".cubtmp").c_str(), tmp_bytes);
+
+  k_extract_keys<<<grid_for(n, 256), 256, 0, st>>>(reads, lens, nflag, n, W, start, end, keys_a, rid_a, d_count);
+  // stable LSD radix sort: read ids stay ascending inside equal keys; unindexed reads (hk = ~0) end up last
+  need = tmp_bytes;
+  cub::DeviceRadixSort::SortPairs(tmp, need, keys_a, keys_b, rid_a, rid_c, (int)n, 0, 64, st);
+  k_mark_heads<<<grid_for(n, 256), 256, 0, st>>>(keys_b, n, flag, head32);
+  need = tmp_bytes;
+  cub::DeviceScan::InclusiveSum(tmp, need, head32, kidx1, (int)n, st);
+  cub::CountingInputIterator<uint32_t> cnt(0);
+  need = tmp_bytes;
+  cub::DeviceSelect::Flagged(tmp, need, cnt, flag, bin_start_idx, d_count + 1, (int)n, st);
+  k_home_minus_rank<<<grid_for(n, 256), 256, 0, st>>>(keys_b, bin_start_idx, d_count + 1, n, out.view.slot_shift, hm);
+  need = tmp_bytes;
+  cub::DeviceScan::InclusiveScan(tmp, need, hm, hmax, MaxOp(), (int)n, st);
+  k_insert_slots<<<grid_for(n, 256), 256, 0, st>>>(keys_b, rid_c, bin_start_idx, d_count + 1, d_count, hmax, n, (uint32_t)cap + kSlotPad - 1,
+                                                  out.view.filter_shift, slots, bins, slot_of_bin, filter, d_count + 2);
+  k_fill_bins<<<grid_for(n, 256), 256, 0, st>>>(keys_b, rid_c, kidx1, bin_start_idx, slot_of_bin, d_count + 1, d_count, n, bins, slot_of_read);
+  c.launches += 5 + (2 + 16) + 2 + 3 + 2;  // ours + CUB (sort: histogram + 8 x onesweep ..., scans, select)
   SB_CUDA(cudaGetLastError());
 }
 

@@ -322,8 +322,9 @@ __global__ void k_align_singletons(AlignArgs a) {
     uint64_t key;
     if (!rev) key = cons_bits(a.cons2, j + d.start) & kmask;
     else key = ~(rev_groups(cons_bits(a.cons2, j + L - 1 - d.end) & kmask) >> (64 - 2 * nb)) & kmask;
-    if (!filter_test(d.filter, d.filter_mask, mix64(key))) continue;
-    const long long hdr = dict_find(d, key);
+    const uint64_t hk = mix64(key);
+    if (!filter_test(d.filter, d.filter_shift, hk)) continue;
+    const long long hdr = dict_find(d, hk);
     if (hdr < 0) continue;
     const uint32_t bc = d.bins[hdr];
     const unsigned long long prio = (j << 2) | (unsigned long long)(rev << 1) | (unsigned long long)l;

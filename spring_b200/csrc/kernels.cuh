@@ -21,11 +21,11 @@ struct Ctx {
 struct DictBuild {
   DictView view{};
   uint32_t capacity = 0;
-  uint32_t numkeys = 0;
-  uint32_t dict_numreads = 0;
-  const uint64_t *sorted_keys = nullptr;   // [dict_numreads] keys in sorted order (device)
-  const uint32_t *bin_start_idx = nullptr; // [numkeys] index of each bin's first entry (device)
-  const uint32_t *sorted_rids = nullptr;   // [dict_numreads] read ids in (key, id) order (device)
+  // everything below stays on the device (the build never synchronises with the host)
+  const uint32_t *d_counts = nullptr;      // [0] indexed reads, [1] unique keys, [2] bins dropped for lack of spare slots
+  const uint64_t *sorted_keys = nullptr;   // [n] hashed keys hk = mix64(key) in sorted order, unindexed reads (~0) last
+  const uint32_t *bin_start_idx = nullptr; // [unique keys] index of each bin's first entry
+  const uint32_t *sorted_rids = nullptr;   // [n] read ids in (hk, id) order
 };
 // reads: [n][W] 2-bit packed; nflag: optional [n][W] (bit 2j set where base j is N; such reads are
 // left out of the dictionary when the N falls inside the window).  tag names the pool buffers.

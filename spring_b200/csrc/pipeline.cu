@@ -574,19 +574,39 @@ int spring_b200_build_dictionary(spring_b200_ctx *ctx, const spring_b200_input *
     reorder_windows(L, s, e);
     DictBuild db;
     build_dictionary(c, d.reads, d.lens, nullptr, in->num_clean, W, s[which], e[which], "rd.dict0", db);
-    *num_keys = db.numkeys;
-    *dict_numreads = db.dict_numreads;
-    // unique keys = sorted_keys[bin_start_idx[k]]
-    std::vector<uint64_t> sk(db.dict_numreads);
-    std::vector<uint32_t> bsi(db.numkeys);
-    if (db.dict_numreads) {
-      SB_CUDA(cudaMemcpyAsync(sk.data(), db.sorted_keys, sizeof(uint64_t) * db.dict_numreads, cudaMemcpyDeviceToHost, c.stream));
-      SB_CUDA(cudaMemcpyAsync(read_id, db.sorted_rids, sizeof(uint32_t) * db.dict_numreads, cudaMemcpyDeviceToHost, c.stream));
-    }
-    if (db.numkeys) SB_CUDA(cudaMemcpyAsync(bsi.data(), db.bin_start_idx, sizeof(uint32_t) * db.numkeys, cudaMemcpyDeviceToHost, c.stream));
+    // The build keeps its bins in hashed-key order; the reference's CSR is in key order (bitset_util.h:118-131):
+    // recover every bin's key from its first read and sort the bins by it (test entry point: host loop).
+    uint32_t cnts[4];
+    SB_CUDA(cudaMemcpyAsync(cnts, db.d_counts, sizeof(cnts), cudaMemcpyDeviceToHost, c.stream));
     SB_CUDA(cudaStreamSynchronize(c.stream));
-    for (uint32_t k = 0; k < db.numkeys; k++) { keys[k] = sk[bsi[k]]; bin_start[k] = bsi[k]; }
-    bin_start[db.numkeys] = db.dict_numreads;
+    const uint32_t nv = cnts[0], nk = cnts[1];
+    if (cnts[2]) throw LimitError("dictionary: bins dropped (probe chain longer than the spare slots)");
+    std::vector<uint32_t> bsi(nk + 1), rids(nv);
+    if (nv) SB_CUDA(cudaMemcpyAsync(rids.data(), db.sorted_rids, sizeof(uint32_t) * nv, cudaMemcpyDeviceToHost, c.stream));
+    if (nk) SB_CUDA(cudaMemcpyAsync(bsi.data(), db.bin_start_idx, sizeof(uint32_t) * nk, cudaMemcpyDeviceToHost, c.stream));
+    SB_CUDA(cudaStreamSynchronize(c.stream));
+    bsi[nk] = nv;
+    const int kstart = s[which], kend = e[which], nbits = 2 * (kend - kstart + 1);
+    auto key_of = [&](uint32_t rid) {
+      const uint64_t *r = in->reads + (size_t)rid * W;
+      const int pos = 2 * kstart, k = pos >> 6, bs = pos & 63;
+      uint64_t v = r[k] >> bs;
+      if (bs && k + 1 < W) v |= r[k + 1] << (64 - bs);
+      return nbits < 64 ? v & ((1ull << nbits) - 1ull) : v;
+    };
+    std::vector<std::pair<uint64_t, uint32_t>> order(nk);
+    for (uint32_t k = 0; k < nk; k++) order[k] = {key_of(rids[bsi[k]]), k};
+    std::sort(order.begin(), order.end());
+    uint32_t at = 0;
+    for (uint32_t j = 0; j < nk; j++) {
+      const uint32_t k = order[j].second;
+      keys[j] = order[j].first;
+      bin_start[j] = at;
+      for (uint32_t i = bsi[k]; i < bsi[k + 1]; i++) read_id[at++] = rids[i];
+    }
+    bin_start[nk] = at;
+    *num_keys = nk;
+    *dict_numreads = nv;
     ctx->stats = spring_b200_stats{};
     ctx->stats.gpu_launches = c.launches;
   });

@@ -312,9 +312,9 @@ __device__ bool chain_search(const ChainArgs &a, const uint64_t *ref, const uint
       if (s >= s_lo && s < s_hi) {
         okm |= 1u << j;
         const uint64_t hk = mix64(window_key(src, kbase + kstep * s, d.key_bits));
-        if (filter_test_hint(d.filter, d.filter_mask, hk, pol_keep)) {
+        if (filter_test_hint(d.filter, d.filter_shift, hk, pol_keep)) {
           cand |= 1u << j;
-          if (a.prefetch_slots) asm volatile("prefetch.global.L2 [%0];" ::"l"(d.slots + ((uint32_t)hk & d.slot_mask)));
+          if (a.prefetch_slots) asm volatile("prefetch.global.L2 [%0];" ::"l"(d.slots + slot_home(hk, d.slot_shift)));
         }
       }
     }
@@ -327,18 +327,18 @@ __device__ bool chain_search(const ChainArgs &a, const uint64_t *ref, const uint
         const int j = __ffs(cand) - 1;
         cand &= cand - 1;
         const int s = S + sub + 8 * j;
-        const uint64_t key = window_key(src, kbase + kstep * s, d.key_bits);
-        uint32_t h = (uint32_t)mix64(key) & d.slot_mask;
+        const uint64_t hk = mix64(window_key(src, kbase + kstep * s, d.key_bits));
+        uint32_t h = slot_home(hk, d.slot_shift);
         slot_probes++;
-        for (;;) {
+        for (;;) {  // ordered probing: every key between the home slot and hk's own slot is smaller than hk
           const DictSlot sl = load_slot_hint(d.slots + h, pol_stream);
-          if (sl.start1 == 0) break;
-          if (sl.key == key) {
+          if (sl.start1 == 0 || sl.key > hk) break;
+          if (sl.key == hk) {
             // a bin with no live read is an "empty_bin" (reorder.h:277-281): skipped without a visit
             if (sl.live) { cur_j = j; cur_start1 = sl.start1; cur_count = sl.count; cur_r0 = sl.rid[0]; cur_r1 = sl.rid[1]; cur_r2 = sl.rid[2]; }
             break;
           }
-          h = (h + 1) & d.slot_mask;
+          h++;
         }
       }
       const int myp = cur_j >= 0 ? (((S + sub + 8 * cur_j) << 2) | kind) : 0x7FFFFFFF;

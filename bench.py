@@ -19,6 +19,7 @@ the reads it owns.
   e2e   : the same through the C ABI with HOST (pinned) buffers: H2D + kernels + D2H per step
   verify: after the timed region, the streams of the last step are re-blocked, block-decoded and compared with
           the input on the GPU (spring_b200_verify_roundtrip): every read must decode to its original
+  e2e_files : the same through the file-level plugin call (temp_dir on /dev/shm in, stream files out)
   roofline : the chain kernel (k_chains), algorithmic bytes / live CUDA-event duration
   cpu_baseline : the reference's own call_reorder + call_encoder (oracle/_ref) on the host cores, on a
                  bounded sample of the same generator
@@ -235,6 +236,7 @@ def main() -> None:
     ap.add_argument("--ref-budget-s", type=float, default=420.0, help="--impl reference: wall-clock budget for warm-ups + steps")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-verify", action="store_true")
+    ap.add_argument("--no-files-leg", action="store_true")
     args = ap.parse_args()
     cfg_id, cfg = args.config, CONFIGS[args.config]
     if not args.reads:
@@ -416,6 +418,39 @@ def main() -> None:
                  "gpu_ms": sum(rb_dev) / len(rb_dev), "ms_with_d2h_of_blocks": sum(rb_wall) / len(rb_wall),
                  "blocks": int(blk.num_blocks), "d2h_bytes": int(sum(blk.size[i] for i in range(capi.NUM_BLOCK_STREAMS)))}
 
+    # ---- e2e_files: the plugin call itself -- what the reference's own call_reorder / call_encoder boundary is: the
+    # files preprocess leaves in temp_dir in, the encoder's stream files out (spring_b200_reorder_encode_files, persistent
+    # context, temp_dir on /dev/shm like the reference arm) -------------------------------------------------------------
+    e2e_files = None
+    if world == 1 and not args.no_files_leg:
+        base = "/dev/shm" if os.path.isdir("/dev/shm") else None
+        d = tempfile.mkdtemp(prefix="spring_b200_files_", dir=base)
+        try:
+            h_packed = d_reads.cpu().numpy().view(np.uint64)
+            h_lengths = d_lens.cpu().numpy().view(np.uint16)
+            t_files, in_bytes, out_bytes = [], 0, 0
+            for i in range(1 + min(args.steps, 3)):
+                for f in os.listdir(d):
+                    os.remove(os.path.join(d, f))
+                cpy = dnaio.write_hotpath_inputs(d, h_packed, h_lengths, max_readlen=L, n_seqs=di.n_seqs, order_n=order_n,
+                                                 num_reads=n_local, paired_split=di.num_clean[0] if cfg["paired"] else None, num_thr=8)
+                os.remove(os.path.join(d, "cp_in.bin"))
+                in_bytes = sum(os.path.getsize(os.path.join(d, f)) for f in os.listdir(d))
+                t0 = time.perf_counter()
+                ctx.reorder_encode_files(d, capi.CP.from_buffer_copy(cpy.pack()), args.chains)
+                if i:
+                    t_files.append(time.perf_counter() - t0)
+                out_bytes = sum(os.path.getsize(os.path.join(d, f)) for f in os.listdir(d))
+            ms_files = 1e3 * sum(t_files) / len(t_files)
+            e2e_files = {"value": total / (ms_files * 1e-3) / 1e6, "unit": "Mreads/s", "ms_per_step": ms_files, "steps": len(t_files),
+                         "input_file_bytes": int(in_bytes), "output_file_bytes": int(out_bytes),
+                         "what": "spring_b200_reorder_encode_files: input_clean_*.dna / input_N.dna / read_order_N.bin on /dev/shm -> "
+                                 "read_seq.bin.<t>, read_pos.bin, ... on /dev/shm (mmap + threaded record copy, H2D, kernels, D2H, "
+                                 "threaded file writes); the boundary the reference arm crosses"}
+            del h_packed, h_lengths
+        finally:
+            shutil.rmtree(d, ignore_errors=True)
+
     # ---- roofline of the dominant kernel (k_chains) ---------------------------------------------------
     peak, peak_src = measured_peak_gbs()
     ck_ms = sum(chain_ms) / len(chain_ms)
@@ -451,6 +486,8 @@ def main() -> None:
         line["shard_layout_rank0"] = keep.get("layout")
     if after is not None:
         line["after_encoder"] = after
+    if e2e_files is not None:
+        line["e2e_files"] = e2e_files
     if world == 1 and not args.no_cpu_baseline:
         ctx.close()
         del d_reads, d_lens, di

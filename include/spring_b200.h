@@ -319,10 +319,10 @@ typedef struct spring_b200_shard_layout {
 int spring_b200_finalize_shard(spring_b200_ctx *ctx, const uint32_t *ids, uint32_t num_owned, const uint32_t *n_ids, uint32_t num_n,
                                spring_b200_shard_layout *out);
 /* Host-side concatenation of finalized shards (HOST streams, rank order) into one job: aligned pieces first, then the
- * unaligned ones.  The consensus stays sharded (one read_seq.bin.<t> per shard, cp.num_thr = num_shards).  The result
- * owns its memory; release it with spring_b200_free_merged. */
+ * unaligned ones, the consensus shards joined at 2 bits per base -- a merged job looks exactly like a single-GPU one
+ * (write it with spring_b200_write_streams).  The result owns its memory; release it with spring_b200_free_merged. */
 typedef struct spring_b200_merged {
-  spring_b200_streams streams;       /* seq_packed is NULL: see shard_seq */
+  spring_b200_streams streams;       /* seq_packed: all shards' consensus as one 2-bit stream (shards shifted into place) */
   int num_shards;
   const uint8_t **shard_seq;         /* [num_shards] packed consensus of each shard (pointers into the inputs) */
   uint64_t *shard_seq_len;           /* [num_shards] */
@@ -332,6 +332,15 @@ int spring_b200_merge_shards(const spring_b200_streams *shards, int num_shards, 
 void spring_b200_free_merged(spring_b200_merged *m);
 /* read_seq.bin.<t> + .tail per shard and the other stream files of a merged job, as spring_b200_write_streams does */
 int spring_b200_write_merged(const char *temp_dir, const spring_b200_merged *m);
+
+/* One process driving several GPUs (one host thread and one shared context per GPU): the multi-GPU form of
+ * spring_b200_reorder_encode_files below, i.e. of call_reorder + call_encoder (src/call_template_functions.cpp:9-143).
+ * Reads the same files from temp_dir, block-distributes the reads over the GPUs, runs exchange -> reorder + encode ->
+ * finalisation on every GPU, merges the shards (src/encoder.h:386-487) and writes the same output files, the consensus
+ * cut into cp->num_thr pieces as in the single-GPU call -- so cp.bin and every later host stage stay as they are.
+ * device_ids may be NULL (devices 0 .. num_gpus-1).  stats (may be NULL): GPU 0's, with the match counters summed. */
+int spring_b200_reorder_encode_files_multi(const char *temp_dir, const spring_b200_cp *cp, int num_gpus, const int *device_ids,
+                                           uint32_t num_chains, spring_b200_stats *stats, char *err, size_t errlen);
 
 /* ---- file-level drop-in -------------------------------------------------------------------- */
 /* Replaces call_reorder + call_encoder (src/call_template_functions.cpp:9-143) on a temp_dir:

@@ -24,7 +24,7 @@ EXPORTS = [
     "spring_b200_decode_blocks", "spring_b200_verify_roundtrip",
     "spring_b200_comm_unique_id", "spring_b200_comm_init", "spring_b200_comm_free", "spring_b200_exchange_reads",
     "spring_b200_finalize_shard", "spring_b200_merge_shards", "spring_b200_free_merged", "spring_b200_write_merged",
-    "spring_b200_shared_ctx",
+    "spring_b200_shared_ctx", "spring_b200_reorder_encode_files_multi",
 ]
 
 

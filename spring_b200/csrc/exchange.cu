@@ -171,7 +171,28 @@ __global__ void k_finalize_shard(uint64_t *pos, uint64_t num_aligned, uint64_t s
   }
 }
 
+// original FASTQ index of clean read k0 + i: clean reads keep their order, the reads with N (order_n, ascending) sit in
+// between (encoder.cpp:177-222, the same map as corrected_order in encode.cu)
+__global__ void k_original_ids(uint32_t k0, uint32_t n, const uint32_t *__restrict__ order_n, uint32_t nn, uint32_t *ids) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t k = k0 + i;
+  uint32_t lo = 0, hi = nn;
+  while (lo < hi) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (order_n[mid] - mid <= k) lo = mid + 1; else hi = mid;
+  }
+  ids[i] = k + lo;
+}
+
 }  // namespace
+
+void run_original_ids(Ctx &c, uint32_t k0, uint32_t n, const uint32_t *d_order_n, uint32_t nn, uint32_t *ids) {
+  if (!n) return;
+  k_original_ids<<<(n + 255) / 256, 256, 0, c.stream>>>(k0, n, d_order_n, nn, ids);
+  c.launches++;
+  SB_CUDA(cudaGetLastError());
+}
 
 struct Comm {
   ncclComm_t comm = nullptr;

@@ -32,6 +32,7 @@ namespace spring {
 static_assert(sizeof(compression_params) == sizeof(spring_b200_cp), "cp.bin layout mismatch");
 
 namespace {
+spring_b200_stats g_stats{};  // of the call_reorder that just ran (call_encoder prints the encoder's lines from it)
 int env_int(const char *name, int dflt) {
   const char *v = std::getenv(name);
   return v ? std::atoi(v) : dflt;
@@ -48,11 +49,21 @@ void call_reorder(const std::string &temp_dir, compression_params &cp) {
     throw std::runtime_error(std::string("spring_b200: ") + spring_b200_last_error(nullptr));
   spring_b200_cp c;
   std::memcpy(&c, &cp, sizeof(c));
-  const int rc = spring_b200_reorder_encode_files(ctx, temp_dir.c_str(), &c, (uint32_t)env_int("SPRING_B200_CHAINS", 0));
-  if (rc != SPRING_B200_OK) throw std::runtime_error(std::string("spring_b200: ") + spring_b200_last_error(ctx));
   spring_b200_stats st;
-  if (spring_b200_get_stats(ctx, &st) == SPRING_B200_OK)
-    std::printf("Reordering done, %u were unmatched\n", st.unmatched);  // reorder.h:633-635
+  const int gpus = env_int("SPRING_B200_GPUS", 1);
+  if (gpus > 1) {  // SPRING_B200_GPUS=N: devices 0..N-1, one exchange over NVLink, shards merged before the files are written
+    char err[512] = "";
+    if (spring_b200_reorder_encode_files_multi(temp_dir.c_str(), &c, gpus, nullptr, (uint32_t)env_int("SPRING_B200_CHAINS", 0), &st, err,
+                                               sizeof(err)) != SPRING_B200_OK)
+      throw std::runtime_error(std::string("spring_b200: ") + err);
+    g_stats = st;
+  } else {
+    const int rc = spring_b200_reorder_encode_files(ctx, temp_dir.c_str(), &c, (uint32_t)env_int("SPRING_B200_CHAINS", 0));
+    if (rc != SPRING_B200_OK) throw std::runtime_error(std::string("spring_b200: ") + spring_b200_last_error(ctx));
+    spring_b200_get_stats(ctx, &st);
+    g_stats = st;
+  }
+  std::printf("Reordering done, %u were unmatched\n", st.unmatched);  // reorder.h:633-635
 }
 
 void call_encoder(const std::string &temp_dir, compression_params &cp) {
@@ -66,10 +77,8 @@ void call_encoder(const std::string &temp_dir, compression_params &cp) {
     std::remove(base.c_str());
   }
   // encoder.h:490-492
-  spring_b200_ctx *ctx = nullptr;
-  spring_b200_stats st;
-  if (spring_b200_shared_ctx(env_int("SPRING_B200_DEVICE", 0), &ctx) == SPRING_B200_OK && spring_b200_get_stats(ctx, &st) == SPRING_B200_OK)
-    std::printf("Encoding done:\n%u singleton reads were aligned\n%u reads with N were aligned\n", st.singletons_aligned, st.n_reads_aligned);
+  std::printf("Encoding done:\n%u singleton reads were aligned\n%u reads with N were aligned\n", g_stats.singletons_aligned,
+              g_stats.n_reads_aligned);
 }
 
 }  // namespace spring

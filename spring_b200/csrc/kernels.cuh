@@ -131,6 +131,8 @@ struct ShardLayout {  // where this rank's pieces sit in the whole job's streams
   uint64_t total_seq_len = 0, total_aligned = 0, total_reads = 0, total_noise_bytes = 0, total_num_noise = 0, total_unaligned_bytes = 0,
            total_unaligned_len = 0;
 };
+// ids[i] = original FASTQ index of clean read k0 + i (d_order_n: the job's read_order_N.bin on the device)
+void run_original_ids(Ctx &c, uint32_t k0, uint32_t n, const uint32_t *d_order_n, uint32_t nn, uint32_t *ids);
 // pos += sum of the lower ranks' consensus lengths; order[i] = global id (ids: device, the exchanged ids of the owned
 // clean reads; h_n_ids: host, global ids of the rank's own reads with N, which were numbered after the owned reads)
 void run_finalize_shard(Ctx &c, Comm *cm, EncodeDev &e, const uint32_t *ids, uint32_t n_owned, const uint32_t *h_n_ids, uint32_t n_n,

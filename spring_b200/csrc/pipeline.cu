@@ -886,6 +886,7 @@ struct MergedOwner {
   std::vector<uint64_t> pos; std::vector<uint8_t> noise; std::vector<uint16_t> noisepos; std::vector<uint8_t> rev;
   std::vector<uint32_t> order; std::vector<uint16_t> lengths; std::vector<uint8_t> unaligned;
   std::vector<const uint8_t *> shard_seq; std::vector<uint64_t> shard_seq_len;
+  std::vector<uint8_t> seq;  // all shards' consensus as ONE 2-bit stream (a shard need not end on a byte boundary)
 };
 }  // namespace
 
@@ -932,10 +933,33 @@ int spring_b200_merge_shards(const spring_b200_streams *shards, int n, spring_b2
         at += c;
       }
     });
+    // the consensus: shard after shard at 2 bits per base; a shard that starts inside a byte is shifted into place
+    o->seq.assign((size_t)((sl + 3) / 4) + 1, 0);
+    th.emplace_back([=] {
+      uint64_t at = 0;  // bases written
+      for (int i = 0; i < n; i++) {
+        const uint64_t len = shards[i].seq_len, nb = (len + 3) / 4;
+        const uint8_t *src = shards[i].seq_packed;
+        const int sh = 2 * (int)(at & 3);
+        uint8_t *dst = o->seq.data() + at / 4;
+        if (!len) continue;
+        if (sh == 0) memcpy(dst, src, nb);
+        else {
+          for (uint64_t b = 0; b < nb; b++) {
+            uint8_t v = src[b];
+            if (b == nb - 1 && (len & 3)) v &= (uint8_t)((1u << (2 * (len & 3))) - 1u);  // bases beyond the shard's end
+            dst[b] |= (uint8_t)(v << sh);
+            dst[b + 1] |= (uint8_t)(v >> (8 - sh));
+          }
+        }
+        at += len;
+        if (at & 3) o->seq[at / 4] &= (uint8_t)((1u << (2 * (at & 3))) - 1u);
+      }
+    });
     for (auto &t : th) t.join();
     memset(out, 0, sizeof(*out));
     spring_b200_streams &m = out->streams;
-    m.seq_packed = nullptr; m.seq_len = sl; m.pos = o->pos.data(); m.noise = o->noise.data(); m.noise_bytes = nb;
+    m.seq_packed = o->seq.data(); m.seq_len = sl; m.pos = o->pos.data(); m.noise = o->noise.data(); m.noise_bytes = nb;
     m.noisepos = o->noisepos.data(); m.num_noise = nn; m.rev = o->rev.data(); m.order = o->order.data(); m.lengths = o->lengths.data();
     m.unaligned = o->unaligned.data(); m.unaligned_bytes = ub; m.unaligned_len = ul; m.num_aligned = na; m.num_reads = nr;
     for (int i = 0; i < n; i++) { m.singletons_aligned += shards[i].singletons_aligned; m.n_reads_aligned += shards[i].n_reads_aligned; }
@@ -1005,6 +1029,122 @@ int spring_b200_reorder_encode_files(spring_b200_ctx *ctx, const char *temp_dir,
     write_streams(dir, &s, cp->num_thr > 0 ? cp->num_thr : 1);
     ctx->files_dir = dir;
   });
+}
+
+// ---- one process, several GPUs: the reference-facing form of the multi-GPU path (num_gpus / device_ids) ----
+namespace {
+struct NSplit { std::vector<size_t> off; };  // byte offset of every input_N.dna record (+ the end)
+NSplit split_n_records(const uint8_t *rec, size_t bytes, uint32_t nn) {
+  NSplit s;
+  s.off.resize((size_t)nn + 1);
+  size_t at = 0;
+  for (uint32_t i = 0; i < nn; i++) {
+    if (at + 2 > bytes) throw IoError("input_N.dna truncated");
+    uint16_t len; memcpy(&len, rec + at, 2);
+    s.off[i] = at;
+    at += 2 + ((size_t)len + 1) / 2;
+    if (at > bytes) throw IoError("input_N.dna truncated");
+  }
+  s.off[nn] = at;
+  return s;
+}
+}  // namespace
+
+int spring_b200_reorder_encode_files_multi(const char *temp_dir, const spring_b200_cp *cp, int num_gpus, const int *device_ids,
+                                           uint32_t num_chains, spring_b200_stats *stats, char *err, size_t errlen) {
+  auto fail = [&](int code, const std::string &m) {
+    if (err && errlen) { strncpy(err, m.c_str(), errlen - 1); err[errlen - 1] = 0; }
+    return code;
+  };
+  if (!temp_dir || !cp || num_gpus < 1 || num_gpus > 64) return fail(SPRING_B200_EINVAL, "bad argument");
+  if (cp->long_flag) return fail(SPRING_B200_EINVAL, "long mode has no reorder/encode stage (spring.cpp:150)");
+  const uint32_t L = cp->max_readlen;
+  if (L < 1 || L > (uint32_t)kMaxReadLen) return fail(SPRING_B200_EINVAL, "Wrong bitset size.");
+  try {
+    const int G = num_gpus, W = words_for((int)L);
+    std::vector<spring_b200_ctx *> ctx(G, nullptr);
+    for (int g = 0; g < G; g++)
+      if (spring_b200_shared_ctx(device_ids ? device_ids[g] : g, &ctx[g]) != SPRING_B200_OK)
+        return fail(SPRING_B200_ENODEV, std::string("spring_b200: ") + spring_b200_last_error(nullptr));
+    if (G == 1) {
+      const int rc = spring_b200_reorder_encode_files(ctx[0], temp_dir, cp, num_chains);
+      if (rc != SPRING_B200_OK) return fail(rc, spring_b200_last_error(ctx[0]));
+      if (stats) spring_b200_get_stats(ctx[0], stats);
+      return SPRING_B200_OK;
+    }
+    const std::string dir(temp_dir);
+    const uint32_t n0 = cp->num_reads_clean[0], n1 = cp->num_reads_clean[1], n = n0 + n1, nn = cp->num_reads - n;
+    // the job's input, once, in pinned host memory of rank 0's context
+    SB_CUDA(cudaSetDevice(ctx[0]->c.device));
+    uint64_t *h_reads = ctx[0]->c.pool.pin<uint64_t>("file.reads", (size_t)(n ? n : 1) * W);
+    uint16_t *h_lens = ctx[0]->c.pool.pin<uint16_t>("file.lens", n ? n : 1);
+    const std::string f1 = dir + "/input_clean_1.dna", f2 = dir + "/input_clean_2.dna";
+    const std::string fn = dir + "/input_N.dna", fo = dir + "/read_order_N.bin";
+    { MappedFile b(f1, true); parse_dna(b, n0, W, L, h_reads, h_lens, "input_clean_1.dna"); }
+    if (cp->paired_end) { MappedFile b(f2, true); parse_dna(b, n1, W, L, h_reads + (size_t)n0 * W, h_lens + n0, "input_clean_2.dna"); }
+    std::vector<uint8_t> nrec = slurp(fn, false), nord = slurp(fo, false);
+    if (nord.size() != (size_t)nn * 4) throw IoError("read_order_N.bin size does not match cp.num_reads");
+    const uint32_t *order_n = reinterpret_cast<const uint32_t *>(nord.data());
+    const NSplit ns = split_n_records(nrec.data(), nrec.size(), nn);
+    uint8_t id[SPRING_B200_COMM_ID_BYTES];
+    comm_unique_id(id);
+    std::vector<std::string> errs(G);
+    std::vector<spring_b200_streams> shard(G);
+    std::vector<spring_b200_stats> st(G);
+    std::vector<std::thread> th;
+    for (int g = 0; g < G; g++)
+      th.emplace_back([&, g] {
+        try {
+          spring_b200_ctx *x = ctx[g];
+          SB_CUDA(cudaSetDevice(x->c.device));
+          if (spring_b200_comm_init(x, id, g, G) != SPRING_B200_OK) throw CudaError(spring_b200_last_error(x));
+          Ctx &c = x->c;
+          // this rank's block of the clean reads and of the reads with N
+          const uint32_t k0 = (uint32_t)((uint64_t)n * g / G), k1 = (uint32_t)((uint64_t)n * (g + 1) / G), nl = k1 - k0;
+          const uint32_t j0 = (uint32_t)((uint64_t)nn * g / G), j1 = (uint32_t)((uint64_t)nn * (g + 1) / G), njl = j1 - j0;
+          uint64_t *d_reads = c.pool.dev<uint64_t>("mg.reads", (size_t)(nl ? nl : 1) * W);
+          uint16_t *d_lens = c.pool.dev<uint16_t>("mg.lens", nl ? nl : 1);
+          uint32_t *d_ids = c.pool.dev<uint32_t>("mg.ids", nl ? nl : 1);
+          uint32_t *d_on = c.pool.dev<uint32_t>("mg.order_n", (size_t)nn + 1);
+          if (nl) {
+            SB_CUDA(cudaMemcpyAsync(d_reads, h_reads + (size_t)k0 * W, sizeof(uint64_t) * (size_t)nl * W, cudaMemcpyHostToDevice, c.stream));
+            SB_CUDA(cudaMemcpyAsync(d_lens, h_lens + k0, sizeof(uint16_t) * nl, cudaMemcpyHostToDevice, c.stream));
+          }
+          if (nn) SB_CUDA(cudaMemcpyAsync(d_on, order_n, sizeof(uint32_t) * nn, cudaMemcpyHostToDevice, c.stream));
+          run_original_ids(c, k0, nl, d_on, nn, d_ids);
+          spring_b200_exchanged ex{};
+          if (spring_b200_exchange_reads(x, d_reads, d_lens, d_ids, nl, L, &ex) != SPRING_B200_OK) throw CudaError(spring_b200_last_error(x));
+          std::vector<uint32_t> on_local(njl);
+          for (uint32_t j = 0; j < njl; j++) on_local[j] = ex.num_reads + j;  // the rank's N reads are numbered after the reads it owns
+          spring_b200_input in{};
+          in.reads = ex.reads; in.lengths = ex.lengths; in.num_clean = ex.num_reads; in.max_readlen = L;
+          in.n_records = nrec.data() + ns.off[j0]; in.n_record_bytes = ns.off[j1] - ns.off[j0];
+          in.order_n = on_local.data(); in.num_n = njl; in.num_reads = ex.num_reads + njl;
+          spring_b200_streams dev_s{};
+          if (spring_b200_reorder_encode_device(x, &in, num_chains, &dev_s) != SPRING_B200_OK) throw CudaError(spring_b200_last_error(x));
+          spring_b200_get_stats(x, &st[g]);
+          spring_b200_shard_layout lay{};
+          if (spring_b200_finalize_shard(x, ex.ids, ex.num_reads, order_n + j0, njl, &lay) != SPRING_B200_OK) throw CudaError(spring_b200_last_error(x));
+          if (spring_b200_fetch_streams(x, &shard[g]) != SPRING_B200_OK) throw CudaError(spring_b200_last_error(x));
+        } catch (const std::exception &e) { errs[g] = e.what(); }
+      });
+    for (auto &t : th) t.join();
+    for (int g = 0; g < G; g++) if (!errs[g].empty()) return fail(SPRING_B200_ECUDA, "GPU " + std::to_string(g) + ": " + errs[g]);
+    spring_b200_merged m{};
+    if (spring_b200_merge_shards(shard.data(), G, &m) != SPRING_B200_OK) return fail(SPRING_B200_ECUDA, "merge failed");
+    unlink(f1.c_str()); unlink(f2.c_str()); unlink(fn.c_str()); unlink(fo.c_str());
+    try { write_streams(dir, &m.streams, cp->num_thr > 0 ? cp->num_thr : 1); }
+    catch (...) { spring_b200_free_merged(&m); throw; }
+    spring_b200_free_merged(&m);
+    for (int g = 0; g < G; g++) ctx[g]->files_dir.clear();  // a shard's resident streams are not the job's files
+    if (stats) {
+      *stats = st[0];
+      for (int g = 1; g < G; g++) { stats->unmatched += st[g].unmatched; stats->singletons_aligned += st[g].singletons_aligned; stats->n_reads_aligned += st[g].n_reads_aligned; stats->num_chains += st[g].num_chains; }
+    }
+    return SPRING_B200_OK;
+  } catch (const IoError &e) { return fail(SPRING_B200_EIO, e.what());
+  } catch (const LimitError &e) { return fail(SPRING_B200_ELIMIT, e.what());
+  } catch (const std::exception &e) { return fail(SPRING_B200_ECUDA, e.what()); }
 }
 
 }  // extern "C"

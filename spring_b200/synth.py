@@ -89,7 +89,8 @@ def generate(num_reads: int, read_len: int = 150, genome_len: int | None = None,
             out_len[lo:hi] = lens.int()
         else:
             insert = torch.randint(200, 501, (m,), device=dev, generator=g).clamp_(min=L)
-            fstart = (torch.rand((m,), device=dev, generator=g) * (genome_len - 500 - L)).long()
+            # exact integer starts: a float32 uniform has 2^24 distinct values, a 30 bp grid on a 500 Mbp genome
+            fstart = torch.randint(0, max(genome_len - 500 - L, 1), (m,), device=dev, generator=g)
             lens2 = lens if var_len is None else torch.randint(var_len[0], var_len[1] + 1, (m,), device=dev, generator=g)
             # fragment on strand rc: mate 1 reads the fragment start, mate 2 the opposite strand of its end
             s1 = torch.where(rc, fstart + insert - lens, fstart)

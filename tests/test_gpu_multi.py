@@ -142,3 +142,38 @@ def test_merged_multi_gpu_job_decodes_to_the_input(ctx, paired):
         assert sorted(got) == sorted(orig)
     # sharding costs matches but stays in the range of one GPU
     assert merged.num_aligned > 0.85 * N_READS
+
+
+@pytest.mark.parametrize("paired", [False, True])
+def test_spliced_reference_binary_on_two_gpus(paired, tmp_path):
+    """The reference's own `spring -c -r` host pipeline with call_reorder / call_encoder from libspring_b200.so and
+    SPRING_B200_GPUS=2 (one process, two GPUs: spring_b200_reorder_encode_files_multi): the archive must decode with the
+    UNMODIFIED reference to the input, pairs kept together (util/test_script.sh:78-82)."""
+    import subprocess
+    import torch
+    from oracle import pyoracle as po
+    from spring_b200 import synth
+    from test_gpu_parity import _fastq_records
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs at least 2 GPUs")
+    if not (os.path.exists(po.SPLICE_BIN) and po.have_reference()):
+        pytest.skip("oracle/_ref binaries not built")
+    rs = synth.generate(40000, 120, seed=33, paired=paired, n_frac=0.01, var_len=(60, 120), error_model="illumina")
+    f1, f2 = str(tmp_path / "in_1.fastq"), str(tmp_path / "in_2.fastq")
+    synth.write_fastq(rs, f1, f2 if paired else None)
+    arc = str(tmp_path / "out.spring")
+    ins = [f1, f2] if paired else [f1]
+    env = dict(os.environ, SPRING_B200_GPUS="2")
+    r = subprocess.run([po.SPLICE_BIN, "-c", "-r", "-i", *ins, "-o", arc, "-t", "4", "-w", str(tmp_path)], capture_output=True, text=True,
+                       env=env, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "were unmatched" in r.stdout and "singleton reads were aligned" in r.stdout
+    out = str(tmp_path / "dec")
+    r = subprocess.run([po.REF_BIN, "-d", "-i", arc, "-o", out, "-t", "3", "-w", str(tmp_path)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    if not paired:
+        got, want = sorted(_fastq_records(out)), sorted(_fastq_records(f1))
+    else:
+        got = sorted(zip(_fastq_records(out + ".1"), _fastq_records(out + ".2")))
+        want = sorted(zip(_fastq_records(f1), _fastq_records(f2)))
+    assert got == want

@@ -194,7 +194,7 @@ def test_end_to_end_archive_decodes_with_reference(paired, reorder, splice, tmp_
     r = subprocess.run([binary, "-c", *(["-r"] if reorder else []), "-i", *ins, "-o", arc, "-t", "4", "-w", str(tmp_path)],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
-    assert "were unmatched" in r.stdout
+    assert "were unmatched" in r.stdout and "singleton reads were aligned" in r.stdout and "reads with N were aligned" in r.stdout
     out = str(tmp_path / "dec")
     r = subprocess.run([po.REF_BIN, "-d", "-i", arc, "-o", out, "-t", "3", "-w", str(tmp_path)], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr

@@ -35,7 +35,7 @@ class ReadSet:
 def generate(num_reads: int, read_len: int = 150, genome_len: int | None = None, seed: int = 3,
              sub_rate: float = 0.005, error_model: str = "uniform", var_len: tuple[int, int] | None = None,
              paired: bool = False, n_frac: float = 0.0, device: str | torch.device = "cpu",
-             chunk: int = 1 << 20, read_seed: int | None = None) -> ReadSet:
+             chunk: int = 1 << 20, read_seed: int | None = None, repeats: bool = False) -> ReadSet:
     dev = torch.device(device)
     g = torch.Generator(device=dev)
     g.manual_seed(seed)
@@ -43,6 +43,31 @@ def generate(num_reads: int, read_len: int = 150, genome_len: int | None = None,
     if genome_len is None:
         genome_len = max(num_reads * L // 30, 4 * L + 600)       # 30x coverage
     genome = torch.randint(0, 4, (genome_len,), dtype=torch.uint8, device=dev, generator=g)
+    hot = None
+    if repeats:
+        # repeat-rich genome: interspersed copies of 300-3000 bp segments (1 % divergence), tandem arrays of short
+        # units, one low-complexity (poly-A / poly-G) stretch -- and coverage spikes: 5 % of the reads start inside a
+        # few 200 bp hot spots (amplicon-like), so single columns stack tens of thousands of reads
+        n_rep = max(genome_len // 20000, 4)
+        for _ in range(n_rep):
+            ln = int(torch.randint(300, 3001, (1,), generator=g, device=dev))
+            src = int(torch.randint(0, genome_len - ln, (1,), generator=g, device=dev))
+            dst = int(torch.randint(0, genome_len - ln, (1,), generator=g, device=dev))
+            seg = genome[src:src + ln].clone()
+            mut = torch.rand((ln,), device=dev, generator=g) < 0.01
+            seg = torch.where(mut, (seg + 1) & 3, seg)
+            genome[dst:dst + ln] = seg
+        for _ in range(max(genome_len // 200000, 2)):
+            unit = int(torch.randint(2, 40, (1,), generator=g, device=dev))
+            reps = int(torch.randint(10, 200, (1,), generator=g, device=dev))
+            at = int(torch.randint(0, max(genome_len - unit * reps, 1), (1,), generator=g, device=dev))
+            u = torch.randint(0, 4, (unit,), dtype=torch.uint8, device=dev, generator=g)
+            ln = min(unit * reps, genome_len - at)
+            genome[at:at + ln] = u.repeat(reps)[:ln]
+        at = int(torch.randint(0, max(genome_len - 600, 1), (1,), generator=g, device=dev))
+        genome[at:at + 300] = 0
+        genome[at + 300:at + 600] = 1
+        hot = torch.randint(0, max(genome_len - 3000, 1), (4,), device=dev, generator=g)
     if read_seed is not None:  # same genome, different reads (one block of a larger read set)
         g.manual_seed(read_seed)
     n_frag = num_reads // 2 if paired else num_reads
@@ -85,6 +110,10 @@ def generate(num_reads: int, read_len: int = 150, genome_len: int | None = None,
         rc = torch.rand((m,), device=dev, generator=g) < 0.5
         if not paired:
             starts = torch.randint(0, genome_len - L + 1, (m,), device=dev, generator=g)
+            if hot is not None:
+                spike = torch.rand((m,), device=dev, generator=g) < 0.05
+                hs = hot[torch.randint(0, len(hot), (m,), device=dev, generator=g)] + torch.randint(0, 200, (m,), device=dev, generator=g)
+                starts = torch.where(spike, hs.clamp_(max=genome_len - L), starts)
             out_codes[lo:hi] = sample(starts, rc, lens)
             out_len[lo:hi] = lens.int()
         else:

@@ -156,7 +156,7 @@ __global__ void k_abs_pos(const uint32_t *__restrict__ cidx1, const int64_t *__r
 }
 
 // ---- consensus (buildcontig, encoder.cpp:32-74) ---------------------------------------------------
-constexpr int kTile = 256, kStage = 128;
+constexpr int kTile = 256;  // granularity of the tile tables (k_tile_ranges, k_tile_contigs, k_align_singletons)
 
 // Which sorted reads can touch which 256-column tile, without a binary search per tile (46 dependent
 // HBM loads per block used to be most of the consensus kernel's time): sorted_ap is ascending, so
@@ -218,71 +218,124 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_
                ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-// One block = one 256-column tile.  The reads that can cover it are rows [r_lo, r_hi) of the sorted,
-// oriented array: contiguous in HBM, staged kStage rows at a time by ONE bulk async copy (TMA) issued by
-// thread 0 and awaited on an mbarrier, while the other threads fetch the rows' positions and lengths.
-// (8W-byte rows start on 8-byte boundaries: the copy starts at the 16-byte boundary below the first row
-// and s_head remembers the slack.)
-__global__ void __launch_bounds__(kTile) k_consensus(const uint64_t *__restrict__ srt_words, const uint16_t *__restrict__ srt_len,
-                                                     const uint64_t *__restrict__ sorted_ap,
-                                                     const uint32_t *__restrict__ tile_lo, const uint32_t *__restrict__ tile_hi,
-                                                     int W, int L, uint64_t seq_len, uint64_t *cons2) {
-  __shared__ __align__(16) uint64_t s_buf[kStage * kMaxWords + 2];  // staged rows, stride W, behind up to 8 slack bytes
-  __shared__ int s_rel[kStage];                                     // read start relative to the tile's first column
-  __shared__ uint16_t s_len[kStage];
+// Consensus by bit-sliced votes.  One THREAD owns one 64-bit word of the consensus = 32 columns, one block
+// kConsThreads words = 4096 columns.  The reads that can cover the block's columns are rows [r_lo, r_hi) of the sorted,
+// oriented array: contiguous in HBM, staged kConsStage rows at a time by ONE bulk async copy (TMA) issued by thread 0
+// and awaited on an mbarrier, while the other threads fetch the rows' positions and lengths.  (8W-byte rows start on
+// 8-byte boundaries: the copy starts at the 16-byte boundary below the first row and s_head remembers the slack.)
+//
+// A thread never looks at single bases.  For every staged read that overlaps its 32 columns it cuts the 64 bits under
+// them out of the row (one funnel shift), turns them into two masks -- columns where the read says A or G (A in the even
+// bit of the column's pair, G in the odd one), columns where it says C or T -- and adds the masks into per-base counters
+// kept BIT-SLICED in registers: plane k holds bit k of the counts of all 32 columns, an addition is a ripple carry
+// (about two planes deep on average).  The majority of buildcontig (first strict maximum in A, C, G, T order,
+// encoder.cpp:62-71; uncovered -> 'A') is three bit-sliced comparisons over the planes in use, and its result IS the
+// consensus word in the reads' own 2-bit coding.  ~60 instructions per column instead of ~1000 for a loop over the ~30
+// covering reads of every single column; exact up to 65 535 reads of one base on a column (the count then stays there).
+constexpr int kConsThreads = 128, kConsStage = 256, kConsPlanes = 16;
+constexpr int kConsTilesPerBlock = kConsThreads * 32 / kTile;  // blocks are made of 16 of the 256-column tiles of k_tile_ranges
+
+__global__ void __launch_bounds__(kConsThreads) k_consensus(const uint64_t *__restrict__ srt_words, const uint16_t *__restrict__ srt_len,
+                                                            const uint64_t *__restrict__ sorted_ap,
+                                                            const uint32_t *__restrict__ tile_lo, const uint32_t *__restrict__ tile_hi,
+                                                            uint32_t num_tiles, int W, int L, uint64_t seq_len, uint64_t *cons2) {
+  extern __shared__ __align__(16) uint64_t s_buf[];   // kConsStage * W + 2 words: staged rows behind up to 8 slack bytes
+  __shared__ int s_rel[kConsStage];                   // read start relative to the block's first column
+  __shared__ uint16_t s_len[kConsStage];
   __shared__ __align__(8) uint64_t s_bar;
-  const uint64_t x0 = (uint64_t)blockIdx.x * kTile;
-  const uint64_t x = x0 + threadIdx.x;
-  const int xr = (int)threadIdx.x;
-  const uint32_t r_lo = tile_lo[blockIdx.x], r_hi = tile_hi[blockIdx.x + 1];  // reads with ap + L > x0 and ap < x0 + kTile
+  constexpr uint64_t E = 0x5555555555555555ull;
+  const uint64_t x0 = (uint64_t)blockIdx.x * (kConsThreads * 32);
+  const int g0 = (int)threadIdx.x * 32;               // first column of this thread's word, relative to x0
+  const uint32_t t_first = blockIdx.x * kConsTilesPerBlock;
+  const uint32_t t_last = min(t_first + kConsTilesPerBlock, num_tiles);
+  const uint32_t r_lo = tile_lo[t_first], r_hi = tile_hi[t_last];  // reads with ap + L > x0 and ap < x0 + 4096
   if (threadIdx.x == 0) mbar_init(&s_bar, 1);
   __syncthreads();
-  uint32_t cA = 0, cC = 0, cG = 0, cT = 0, phase = 0;
-  for (uint32_t base = r_lo; base < r_hi; base += kStage) {
-    const uint32_t cnt = min((uint32_t)kStage, r_hi - base);
-    const uintptr_t g0 = reinterpret_cast<uintptr_t>(srt_words + (size_t)base * W);
-    const uint32_t head = (uint32_t)(g0 & 15u);  // 0 or 8
+  uint64_t p0[kConsPlanes], p1[kConsPlanes];          // p0: A (even bits) / G (odd bits); p1: C / T
+#pragma unroll
+  for (int k = 0; k < kConsPlanes; k++) { p0[k] = 0ull; p1[k] = 0ull; }
+  uint32_t phase = 0;
+  for (uint32_t base = r_lo; base < r_hi; base += kConsStage) {
+    const uint32_t cnt = min((uint32_t)kConsStage, r_hi - base);
+    const uintptr_t gsrc = reinterpret_cast<uintptr_t>(srt_words + (size_t)base * W);
+    const uint32_t head = (uint32_t)(gsrc & 15u);  // 0 or 8
     if (threadIdx.x == 0) {
       const uint32_t bytes = (head + cnt * (uint32_t)W * 8u + 15u) & ~15u;
       mbar_expect_tx(&s_bar, bytes);
-      tma_bulk_g2s(s_buf, reinterpret_cast<const void *>(g0 - head), bytes, &s_bar);
+      tma_bulk_g2s(s_buf, reinterpret_cast<const void *>(gsrc - head), bytes, &s_bar);
     }
-    if (threadIdx.x < cnt) {
-      const uint32_t r = base + threadIdx.x;
-      s_rel[threadIdx.x] = (int)((long long)sorted_ap[r] - (long long)x0);
-      s_len[threadIdx.x] = srt_len[r];
+    for (uint32_t t = threadIdx.x; t < cnt; t += kConsThreads) {
+      const uint32_t r = base + t;
+      s_rel[t] = (int)((long long)sorted_ap[r] - (long long)x0);
+      s_len[t] = srt_len[r];
     }
     __syncthreads();
     mbar_wait(&s_bar, phase);
     phase ^= 1u;
     const uint64_t *s_words = s_buf + (head >> 3);
-    if (x < seq_len) {
-      // staged reads are sorted by position: only those starting in (x - L, x] can cover column x
-      uint32_t q = 0, qh = cnt;
-      const int first = xr - (L - 1);
-      while (q < qh) { const uint32_t mid = (q + qh) >> 1; if (s_rel[mid] < first) q = mid + 1; else qh = mid; }
-      uint32_t acc = 0;  // four u8 counters {A,G,C,T}; at most kStage (< 256) additions per stage
-      for (; q < cnt && s_rel[q] <= xr; q++) {
-        const unsigned off = (unsigned)(xr - s_rel[q]);
-        if (off < (unsigned)s_len[q]) acc += 1u << (8 * base_code(s_words + q * W, (int)off));
+    // staged reads are sorted by position: only those starting in (g0 - L, g0 + 32) can touch this word
+    uint32_t q = 0, qh = cnt;
+    const int first = g0 - (L - 1);
+    while (q < qh) { const uint32_t mid = (q + qh) >> 1; if (s_rel[mid] < first) q = mid + 1; else qh = mid; }
+    for (; q < cnt && s_rel[q] < g0 + 32; q++) {
+      const int off = g0 - s_rel[q], len = (int)s_len[q];   // base of the read under the word's first column
+      if (off >= len) continue;
+      const uint64_t *row = s_words + (size_t)q * W;
+      uint64_t w, valid;
+      if (off >= 0) {
+        const int k = off >> 5, bs = 2 * (off & 31);
+        const uint64_t lo = row[k], hi = k + 1 < W ? row[k + 1] : 0ull;
+        w = bs ? (lo >> bs) | (hi << (64 - bs)) : lo;
+        const int rem = len - off;                         // bases of the read from the word's first column on
+        valid = rem >= 32 ? ~0ull : (1ull << (2 * rem)) - 1ull;
+      } else {                                             // the read starts inside the word
+        const int sh = 2 * (-off);
+        w = row[0] << sh;
+        const int rem = len - off;                         // = len + |off|: end of the read in word columns
+        valid = (rem >= 32 ? ~0ull : (1ull << (2 * rem)) - 1ull) & (~0ull << sh);
       }
-      cA += acc & 0xFFu; cG += (acc >> 8) & 0xFFu; cC += (acc >> 16) & 0xFFu; cT += acc >> 24;
+      const uint64_t v = valid & E, lo1 = w & E, hi1 = (w >> 1) & E;
+      uint64_t c0 = (v & ~hi1 & ~lo1) | ((v & ~hi1 & lo1) << 1);   // A -> even bit, G -> odd bit
+      uint64_t c1 = (v & hi1 & ~lo1) | ((v & hi1 & lo1) << 1);     // C -> even bit, T -> odd bit
+#pragma unroll
+      for (int k = 0; k < kConsPlanes; k++) {
+        if (!(c0 | c1)) break;
+        const uint64_t t0 = p0[k] & c0, t1 = p1[k] & c1;
+        p0[k] ^= c0; p1[k] ^= c1;
+        c0 = t0; c1 = t1;
+      }
+      if (c0 | c1) {  // a count would pass 65 535: it stays there
+#pragma unroll
+        for (int k = 0; k < kConsPlanes; k++) { p0[k] |= c0; p1[k] |= c1; }
+      }
     }
     __syncthreads();  // every thread is done with the buffer before the next copy lands in it
   }
-  uint32_t code = 0;
-  if (x < seq_len) {  // first strict maximum in A,C,G,T order (encoder.cpp:62-71); uncovered -> 'A'
-    uint32_t mx = 0;
-    if (cA > mx) { mx = cA; code = 0; }
-    if (cC > mx) { mx = cC; code = 2; }
-    if (cG > mx) { mx = cG; code = 1; }
-    if (cT > mx) { mx = cT; code = 3; }
-  }
-  // consensus kept 2 bits/base in the reads' own coding (A0 G1 C2 T3): each warp owns one word
-  const int lane = threadIdx.x & 31;
-  const uint32_t part = code << (2 * (lane & 15));
-  const uint32_t lo = __reduce_or_sync(FULL, lane < 16 ? part : 0u), hi = __reduce_or_sync(FULL, lane < 16 ? 0u : part);
-  if (lane == 0 && x0 + (threadIdx.x & ~31u) < seq_len) cons2[(x0 >> 5) + (threadIdx.x >> 5)] = (uint64_t)lo | ((uint64_t)hi << 32);
+  const uint64_t xw = x0 + (uint64_t)g0;
+  if (xw >= seq_len) return;
+  // first strict maximum in A, C, G, T order, 32 columns at a time: X beats the best so far where X > best, compared
+  // plane by plane from the top (gt / eq masks live in the even bits)
+  uint64_t bestv[kConsPlanes];
+#pragma unroll
+  for (int k = 0; k < kConsPlanes; k++) bestv[k] = p0[k] & E;      // A
+  uint64_t code_lo = 0ull, code_hi = 0ull;                         // 2-bit code of the winner per column (A0 G1 C2 T3)
+  auto challenge = [&](auto plane_of, uint64_t lo_bit, uint64_t hi_bit) {
+    uint64_t gt = 0ull, eq = E;
+#pragma unroll
+    for (int k = kConsPlanes - 1; k >= 0; k--) {
+      const uint64_t x = plane_of(k), y = bestv[k];
+      gt |= eq & x & ~y;
+      eq &= ~(x ^ y);
+    }
+#pragma unroll
+    for (int k = 0; k < kConsPlanes; k++) bestv[k] = (plane_of(k) & gt) | (bestv[k] & ~gt);
+    code_lo = (code_lo & ~gt) | (lo_bit & gt);
+    code_hi = (code_hi & ~gt) | (hi_bit & gt);
+  };
+  challenge([&](int k) { return p1[k] & E; }, 0ull, E);            // C = code 2
+  challenge([&](int k) { return (p0[k] >> 1) & E; }, E, 0ull);     // G = code 1
+  challenge([&](int k) { return (p1[k] >> 1) & E; }, E, E);        // T = code 3
+  cons2[xw >> 5] = code_lo | (code_hi << 1);
 }
 
 // ---- singleton re-alignment (encoder.h:231-352) ---------------------------------------------------
@@ -603,7 +656,10 @@ void run_encode(Ctx &c, const uint64_t *reads, const uint16_t *lens, uint32_t n,
   if (seq_len) {
     k_gather_sorted<<<grid_for((uint64_t)M * W, 256), 256, 0, st>>>(reads, lens, ro.order, ro.rev, perm, M, W, srt_words, srt_len, srt_rid, srt_rev);
     k_tile_ranges<<<grid_for((uint64_t)M + 1, 256), 256, 0, st>>>(sorted_ap, M, L, num_tiles, tile_lo, tile_hi);
-    k_consensus<<<num_tiles, kTile, 0, st>>>(srt_words, srt_len, sorted_ap, tile_lo, tile_hi, W, L, seq_len, cons2);
+    const size_t cons_smem = ((size_t)kConsStage * W + 2) * sizeof(uint64_t);
+    SB_CUDA(cudaFuncSetAttribute(k_consensus, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cons_smem));
+    k_consensus<<<grid_for(seq_len, kConsThreads * 32), kConsThreads, cons_smem, st>>>(srt_words, srt_len, sorted_ap, tile_lo, tile_hi,
+                                                                                       num_tiles, W, L, seq_len, cons2);
     c.launches += 3;
   }
 

@@ -140,15 +140,8 @@ __device__ __noinline__ void update_ref(uint64_t *ref, uint64_t *revref, const u
 //     read's words, and only the columns where read and old consensus DIFFER -- at most THRESH_REORDER
 //     of them, the match passed the Hamming test on exactly these bits -- need the vote.
 // curw is overwritten with the read as oriented in the contig.
-//
-// Order of work: the consensus words come first -- provisionally, with the old base in the columns that still need
-// the vote -- and are published to ref / revref, then warm() runs (the free-running schedule probes the next step's
-// first batch there: filter words on their way to L1, the slots of the positives on their way to L2), THEN the count
-// pass, whose ~250 shared-memory instructions cover those round trips, then the votes; ref / revref are rewritten
-// only when a vote changed a base.
-template <typename Warm>
-__device__ __forceinline__ void update_ref_fast(uint64_t *ref, uint64_t *revref, uint64_t *curw, uint64_t *cnt, int W, int lane,
-                                                int old_len, int delta, int cs, int cur_len, bool rev, int new_len, Warm &&warm) {
+__device__ void update_ref_fast(uint64_t *ref, uint64_t *revref, uint64_t *curw, uint64_t *cnt, int W, int lane, int old_len,
+                                int delta, int cs, int cur_len, bool rev, int new_len) {
   if (rev) {
     uint64_t o = 0;
     if (lane < W) o = revcomp_word(curw, W, cur_len, lane);
@@ -156,22 +149,6 @@ __device__ __forceinline__ void update_ref_fast(uint64_t *ref, uint64_t *revref,
     if (lane < W) curw[lane] = o;
     __syncwarp();
   }
-  uint64_t nw = 0, mm = 0;
-  if (lane < W) {
-    const uint64_t MA = range_mask(lane, 0, 2 * (old_len - delta));        // columns that have a source column
-    const uint64_t MB = range_mask(lane, 2 * cs, 2 * (cs + cur_len));      // columns the read covers
-    const uint64_t A = shr_word(ref, W, lane, 2 * delta) & MA;
-    const uint64_t B = shl_word(curw, W, lane, 2 * cs) & MB;
-    nw = A | (B & ~MA);
-    const uint64_t X = (A ^ B) & MA & MB;
-    mm = (X | (X >> 1)) & 0x5555555555555555ull;  // bit 2t: column 32*lane + t needs the vote
-  }
-  __syncwarp();  // old ref read by every lane
-  if (lane < W) ref[lane] = nw;
-  __syncwarp();
-  if (lane < W) revref[lane] = revcomp_word(ref, W, new_len, lane);
-  __syncwarp();
-  warm();
   const int nchunks = (new_len + 31) >> 5;
   for (int cc = 0; cc < nchunks; cc++) {  // ascending is safe: delta >= 0, sources lie at or above the column
     const int i = (cc << 5) + lane;
@@ -194,8 +171,17 @@ __device__ __forceinline__ void update_ref_fast(uint64_t *ref, uint64_t *revref,
       reinterpret_cast<uint2 *>(cnt)[i] = v;
     }
   }
-  __syncwarp();  // counts written
-  bool changed = false;
+  uint64_t nw = 0, mm = 0;
+  if (lane < W) {
+    const uint64_t MA = range_mask(lane, 0, 2 * (old_len - delta));        // columns that have a source column
+    const uint64_t MB = range_mask(lane, 2 * cs, 2 * (cs + cur_len));      // columns the read covers
+    const uint64_t A = shr_word(ref, W, lane, 2 * delta) & MA;
+    const uint64_t B = shl_word(curw, W, lane, 2 * cs) & MB;
+    nw = A | (B & ~MA);
+    const uint64_t X = (A ^ B) & MA & MB;
+    mm = (X | (X >> 1)) & 0x5555555555555555ull;  // bit 2t: column 32*lane + t needs the vote
+  }
+  __syncwarp();  // counts written, old ref read
   while (mm) {
     const int bp = __ffsll((long long)mm) - 1;
     mm &= mm - 1;
@@ -206,14 +192,12 @@ __device__ __forceinline__ void update_ref_fast(uint64_t *ref, uint64_t *revref,
     if (f1 > mx) { mx = f1; code = 2; }
     if (f2 > mx) { mx = f2; code = 3; }
     if (f3 > mx) { mx = f3; code = 1; }
-    if (((nw >> bp) & 3ull) != (uint64_t)code) { nw = (nw & ~(3ull << bp)) | ((uint64_t)code << bp); changed = true; }
+    nw = (nw & ~(3ull << bp)) | ((uint64_t)code << bp);
   }
-  if (__any_sync(FULL, changed)) {  // a vote overturned the old base somewhere: publish the final words
-    if (lane < W) ref[lane] = nw;
-    __syncwarp();
-    if (lane < W) revref[lane] = revcomp_word(ref, W, new_len, lane);
-    __syncwarp();
-  }
+  if (lane < W) ref[lane] = nw;
+  __syncwarp();
+  if (lane < W) revref[lane] = revcomp_word(ref, W, new_len, lane);
+  __syncwarp();
 }
 
 // Verify the live reads of one bin, highest id first, at most MAX_SEARCH of them (reorder.h:287-311).
@@ -470,24 +454,9 @@ __global__ void __launch_bounds__(WPB * 32, MINB) k_chains(ChainArgs a) {
   };
   // fold the read staged in curw into the window: word-parallel fast path, or the per-column generic
   // version for the reference's in-place "fold" quirk (and on request, as a cross-check)
-  // The next step's first batch (shifts 0..7, all four kinds), probed on the provisional consensus while the count pass
-  // is still to come: the filter word lands in L1 for the real search, the slot of a positive is prefetched into L2.
-  // State-free (nothing is kept): a vote that changes the consensus only wastes the prefetch.
-  auto warm = [&](int new_len) {
-    if (LOCKSTEP || a.prefetch_slots < 2) return;
-    const int kind = lane & 3, rev = kind >> 1, s = lane >> 2;
-    const DictView &d = a.dict[kind & 1];
-    const int s_lo = rev ? d.end - new_len + 1 : 0;
-    const int s_hi = min(a.maxshift, rev ? d.start : new_len - d.end);
-    if (s >= s_lo && s < s_hi) {
-      const uint64_t hk = mix64(window_key(rev ? revref : ref, 2 * d.start + (rev ? -2 : 2) * s, d.key_bits));
-      if (filter_test_hint(d.filter, d.filter_shift, hk, l2_policy_evict_last()))
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(d.slots + slot_home(hk, d.slot_shift)));
-    }
-  };
   auto upd = [&](int old_len, int delta, int cs, int cur_len, bool rev, int new_len, int fold) {
     if (fold > 0 || a.generic_update) update_ref(ref, revref, curw, cnt, W, lane, old_len, delta, cs, cur_len, rev, new_len, fold);
-    else update_ref_fast(ref, revref, curw, cnt, W, lane, old_len, delta, cs, cur_len, rev, new_len, [&] { warm(new_len); });
+    else update_ref_fast(ref, revref, curw, cnt, W, lane, old_len, delta, cs, cur_len, rev, new_len);
   };
   // the read must already be staged in curw
   auto new_contig = [&](uint32_t rid) {  // updaterefcount(..., resetcount = true, rev = false) + reorder.h:426-430,:601-612
@@ -885,9 +854,7 @@ void run_reorder(Ctx &c, const uint64_t *reads, const uint16_t *lens, uint32_t n
   a.leader_mask = 0;
   for (uint32_t g = 0; g < a.G; g++) a.leader_mask |= 1u << (g * W);
   a.generic_update = getenv("SPRING_B200_GENERIC_UPDATE") ? 1 : 0;
-  // 1: pass 1 of a batch prefetches the slots of its filter positives (-1 to -2 % on configs 2 and 3); 2: and every update
-  // probes the next step's first batch ahead of its count pass (update_ref_fast)
-  a.prefetch_slots = getenv("SPRING_B200_PREFETCH") ? atoi(getenv("SPRING_B200_PREFETCH")) : 2;
+  a.prefetch_slots = getenv("SPRING_B200_PREFETCH") ? atoi(getenv("SPRING_B200_PREFETCH")) : 1;  // -1 to -2 % on configs 2 and 3
   a.steal_probes = lockstep ? 0 : (getenv("SPRING_B200_STEAL") ? atoi(getenv("SPRING_B200_STEAL")) : 64);
   a.max_rounds = 8ull * n + 4096ull;
   SB_CUDA(cudaMemsetAsync(a.claimed, 0, bm_words * sizeof(uint32_t), st));

@@ -365,7 +365,11 @@ __global__ void k_align_singletons(AlignArgs a) {
   while (lo + 1 < a.num_contigs && a.cstart[lo + 1] <= j) lo++;
   if (j + (uint64_t)a.L > a.cstart[lo + 1]) return;  // window leaves the contig (or contig shorter than max_readlen)
   const int L = a.L, W = a.W;
-#pragma unroll 1
+  // the four probes of a window (2 strands x 2 dictionaries, encoder.h:242-351) are independent: all four keys are cut
+  // out and hashed and all four filter words requested before the first one is looked at
+  uint64_t hk[4];
+  uint32_t fw[4];
+#pragma unroll
   for (int kind = 0; kind < 4; kind++) {
     const int rev = kind >> 1, l = kind & 1;
     const DictView &d = a.dict[l];
@@ -375,9 +379,16 @@ __global__ void k_align_singletons(AlignArgs a) {
     uint64_t key;
     if (!rev) key = cons_bits(a.cons2, j + d.start) & kmask;
     else key = ~(rev_groups(cons_bits(a.cons2, j + L - 1 - d.end) & kmask) >> (64 - 2 * nb)) & kmask;
-    const uint64_t hk = mix64(key);
-    if (!filter_test(d.filter, d.filter_shift, hk)) continue;
-    const long long hdr = dict_find(d, hk);
+    hk[kind] = mix64(key);
+    fw[kind] = __ldg(d.filter + filter_word(hk[kind], d.filter_shift));
+  }
+#pragma unroll
+  for (int kind = 0; kind < 4; kind++) {
+    const uint32_t fb = filter_bits(hk[kind]);
+    if ((fw[kind] & fb) != fb) continue;
+    const int rev = kind >> 1, l = kind & 1;
+    const DictView &d = a.dict[l];
+    const long long hdr = dict_find(d, hk[kind]);
     if (hdr < 0) continue;
     const uint32_t bc = d.bins[hdr];
     const unsigned long long prio = (j << 2) | (unsigned long long)(rev << 1) | (unsigned long long)l;

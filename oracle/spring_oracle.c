@@ -23,7 +23,7 @@
  * claim state of the round start and *proposes* one read; the lowest chain id wins a
  * contested read, losers retry next round.  For C == 1 this is exactly the reference's
  * single-thread execution (no lock is ever contended), which is how the oracle is pinned:
- * tests/test_oracle_vs_reference.py compares every output stream byte for byte with
+ * tests/test_oracle.py compares every output stream byte for byte with
  * oracle/_ref/spring_ref --hotpath -t 1.  For C > 1 it is one legal interleaving of the
  * reference's threads, except that chain c seeds new contigs only from its own slice
  * [c*(N/C), (c+1)*(N/C)) instead of from the global top (keeps chains independent).

@@ -6,6 +6,7 @@
 #include <sys/stat.h>
 #include <unistd.h>
 #include <algorithm>
+#include <atomic>
 #include <cstddef>
 #include <fstream>
 #include <thread>
@@ -269,7 +270,7 @@ struct MappedFile {
     if (fstat(fd, &sb) != 0) { close(fd); fd = -1; throw IoError("cannot stat " + path); }
     n = (size_t)sb.st_size;
     if (n) {
-      void *m = mmap(nullptr, n, PROT_READ, MAP_PRIVATE | MAP_POPULATE, fd, 0);
+      void *m = mmap(nullptr, n, PROT_READ, MAP_PRIVATE, fd, 0);  // pages are faulted in by the copy threads, in parallel
       if (m == MAP_FAILED) { close(fd); fd = -1; throw IoError("cannot map " + path); }
       p = static_cast<const uint8_t *>(m);
     }
@@ -350,23 +351,46 @@ void parse_dna(const MappedFile &buf, uint32_t num, int W, uint32_t max_readlen,
   });
 }
 
-// the eight stream files next to read_seq.bin.<t>, one host thread per file
+// the eight stream files next to read_seq.bin.<t>: every file is created at its final size and filled by pwrite() in
+// 64 MiB pieces, the pieces of all files spread over the host threads (read_pos.bin alone is 800 MB at 100 M reads)
 void write_stream_files(const std::string &dir, const spring_b200_streams *s) {
-  struct Job { const char *name; const void *p; size_t n; };
-  const Job jobs[] = {{"/read_pos.bin", s->pos, (size_t)s->num_aligned * 8}, {"/read_noise.txt", s->noise, (size_t)s->noise_bytes},
-                      {"/read_noisepos.bin", s->noisepos, (size_t)s->num_noise * 2}, {"/read_rev.txt", s->rev, (size_t)s->num_aligned},
-                      {"/read_order.bin", s->order, (size_t)s->num_reads * 4}, {"/read_lengths.bin", s->lengths, (size_t)s->num_reads * 2},
-                      {"/read_unaligned.txt", s->unaligned, (size_t)s->unaligned_bytes},
-                      {"/read_unaligned.txt.count", &s->unaligned_len, (size_t)8}};
-  std::vector<std::thread> th;
-  std::vector<std::string> errs(sizeof(jobs) / sizeof(jobs[0]));
-  int k = 0;
-  for (const Job &j : jobs) {
-    const int idx = k++;
-    th.emplace_back([&, j, idx] { try { spill(dir + j.name, j.p, j.n); } catch (const std::exception &e) { errs[idx] = e.what(); } });
+  struct Job { const char *name; const void *p; size_t n; int fd; };
+  std::vector<Job> jobs = {{"/read_pos.bin", s->pos, (size_t)s->num_aligned * 8, -1}, {"/read_noise.txt", s->noise, (size_t)s->noise_bytes, -1},
+                           {"/read_noisepos.bin", s->noisepos, (size_t)s->num_noise * 2, -1}, {"/read_rev.txt", s->rev, (size_t)s->num_aligned, -1},
+                           {"/read_order.bin", s->order, (size_t)s->num_reads * 4, -1}, {"/read_lengths.bin", s->lengths, (size_t)s->num_reads * 2, -1},
+                           {"/read_unaligned.txt", s->unaligned, (size_t)s->unaligned_bytes, -1},
+                           {"/read_unaligned.txt.count", &s->unaligned_len, (size_t)8, -1}};
+  constexpr size_t kPiece = (size_t)64 << 20;
+  struct Piece { int job; size_t off, n; };
+  std::vector<Piece> pieces;
+  auto close_all = [&] { for (auto &j : jobs) if (j.fd >= 0) { close(j.fd); j.fd = -1; } };
+  for (size_t k = 0; k < jobs.size(); k++) {
+    Job &j = jobs[k];
+    j.fd = open((dir + j.name).c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
+    if (j.fd < 0) { close_all(); throw IoError("cannot create " + dir + j.name); }
+    for (size_t off = 0; off < j.n; off += kPiece) pieces.push_back({(int)k, off, std::min(kPiece, j.n - off)});
   }
+  std::atomic<size_t> next{0};
+  std::atomic<int> failed{0};
+  const int T = (int)std::min<size_t>((size_t)host_threads(), pieces.size() ? pieces.size() : 1);
+  std::vector<std::thread> th;
+  for (int t = 0; t < T; t++)
+    th.emplace_back([&] {
+      for (size_t i = next++; i < pieces.size(); i = next++) {
+        const Piece &pc = pieces[i];
+        const char *src = static_cast<const char *>(jobs[pc.job].p) + pc.off;
+        size_t at = 0;
+        while (at < pc.n) {
+          const ssize_t w = pwrite(jobs[pc.job].fd, src + at, pc.n - at, (off_t)(pc.off + at));
+          if (w < 0) { if (errno == EINTR) continue; failed = 1; return; }
+          at += (size_t)w;
+        }
+      }
+    });
   for (auto &t : th) t.join();
-  for (auto &e : errs) if (!e.empty()) throw IoError(e);
+  bool bad = failed.load() != 0;
+  for (auto &j : jobs) if (j.fd >= 0) { if (close(j.fd) != 0) bad = true; j.fd = -1; }
+  if (bad) throw IoError("write failed in " + dir);
 }
 
 void write_streams(const std::string &dir, const spring_b200_streams *s, int num_shards) {

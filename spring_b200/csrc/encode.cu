@@ -220,7 +220,7 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_
 
 // Consensus by bit-sliced votes.  One THREAD owns one 64-bit word of the consensus = 32 columns, one block
 // kConsThreads words = 4096 columns.  The reads that can cover the block's columns are rows [r_lo, r_hi) of the sorted,
-// oriented array: contiguous in HBM, staged kConsStage rows at a time by ONE bulk async copy (TMA) issued by thread 0
+// oriented array: contiguous in HBM, staged up to 1024 rows at a time by ONE bulk async copy (TMA) issued by thread 0
 // and awaited on an mbarrier, while the other threads fetch the rows' positions and lengths.  (8W-byte rows start on
 // 8-byte boundaries: the copy starts at the 16-byte boundary below the first row and s_head remembers the slack.)
 //
@@ -232,16 +232,17 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_
 // encoder.cpp:62-71; uncovered -> 'A') is three bit-sliced comparisons over the planes in use, and its result IS the
 // consensus word in the reads' own 2-bit coding.  ~60 instructions per column instead of ~1000 for a loop over the ~30
 // covering reads of every single column; exact up to 65 535 reads of one base on a column (the count then stays there).
-constexpr int kConsThreads = 128, kConsStage = 256, kConsPlanes = 16;
+constexpr int kConsThreads = 128, kConsStageMax = 1024, kConsPlanes = 16;  // rows per stage: as many as fit 40 KB, at most 1024
 constexpr int kConsTilesPerBlock = kConsThreads * 32 / kTile;  // blocks are made of 16 of the 256-column tiles of k_tile_ranges
 
 __global__ void __launch_bounds__(kConsThreads) k_consensus(const uint64_t *__restrict__ srt_words, const uint16_t *__restrict__ srt_len,
                                                             const uint64_t *__restrict__ sorted_ap,
                                                             const uint32_t *__restrict__ tile_lo, const uint32_t *__restrict__ tile_hi,
-                                                            uint32_t num_tiles, int W, int L, uint64_t seq_len, uint64_t *cons2) {
-  extern __shared__ __align__(16) uint64_t s_buf[];   // kConsStage * W + 2 words: staged rows behind up to 8 slack bytes
-  __shared__ int s_rel[kConsStage];                   // read start relative to the block's first column
-  __shared__ uint16_t s_len[kConsStage];
+                                                            uint32_t num_tiles, int W, int L, uint64_t seq_len, int stage_rows,
+                                                            uint64_t *cons2) {
+  extern __shared__ __align__(16) uint64_t s_buf[];   // stage_rows * W + 2 words: staged rows behind up to 8 slack bytes
+  __shared__ int s_rel[kConsStageMax];                // read start relative to the block's first column
+  __shared__ uint16_t s_len[kConsStageMax];
   __shared__ __align__(8) uint64_t s_bar;
   constexpr uint64_t E = 0x5555555555555555ull;
   const uint64_t x0 = (uint64_t)blockIdx.x * (kConsThreads * 32);
@@ -255,8 +256,8 @@ __global__ void __launch_bounds__(kConsThreads) k_consensus(const uint64_t *__re
 #pragma unroll
   for (int k = 0; k < kConsPlanes; k++) { p0[k] = 0ull; p1[k] = 0ull; }
   uint32_t phase = 0;
-  for (uint32_t base = r_lo; base < r_hi; base += kConsStage) {
-    const uint32_t cnt = min((uint32_t)kConsStage, r_hi - base);
+  for (uint32_t base = r_lo; base < r_hi; base += (uint32_t)stage_rows) {
+    const uint32_t cnt = min((uint32_t)stage_rows, r_hi - base);
     const uintptr_t gsrc = reinterpret_cast<uintptr_t>(srt_words + (size_t)base * W);
     const uint32_t head = (uint32_t)(gsrc & 15u);  // 0 or 8
     if (threadIdx.x == 0) {
@@ -667,10 +668,12 @@ void run_encode(Ctx &c, const uint64_t *reads, const uint16_t *lens, uint32_t n,
   if (seq_len) {
     k_gather_sorted<<<grid_for((uint64_t)M * W, 256), 256, 0, st>>>(reads, lens, ro.order, ro.rev, perm, M, W, srt_words, srt_len, srt_rid, srt_rev);
     k_tile_ranges<<<grid_for((uint64_t)M + 1, 256), 256, 0, st>>>(sorted_ap, M, L, num_tiles, tile_lo, tile_hi);
-    const size_t cons_smem = ((size_t)kConsStage * W + 2) * sizeof(uint64_t);
+    // one stage usually holds every row of a block (4096 columns at 30x and 150 bp: ~850 rows): one bulk copy, one wait
+    const int stage_rows = std::max(64, std::min(kConsStageMax, (40 * 1024) / (8 * W)));
+    const size_t cons_smem = ((size_t)stage_rows * W + 2) * sizeof(uint64_t);
     SB_CUDA(cudaFuncSetAttribute(k_consensus, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cons_smem));
     k_consensus<<<grid_for(seq_len, kConsThreads * 32), kConsThreads, cons_smem, st>>>(srt_words, srt_len, sorted_ap, tile_lo, tile_hi,
-                                                                                       num_tiles, W, L, seq_len, cons2);
+                                                                                       num_tiles, W, L, seq_len, stage_rows, cons2);
     c.launches += 3;
   }
 

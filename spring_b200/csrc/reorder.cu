@@ -208,13 +208,15 @@ __device__ void update_ref_fast(uint64_t *ref, uint64_t *revref, uint64_t *curw,
 // XOR / mask / popcount per lane, a W-lane segmented sum.  (A lane per candidate would spend W times the
 // instructions on the one or two candidates a typical bin holds.)  The shifted reference word is the
 // same for every candidate of the scan and is computed once.
-__device__ bool scan_bin(const ChainArgs &a, const DictView &d, uint32_t bs, uint32_t bc, uint32_t r0, uint32_t r1, uint32_t r2,
+template <int WT>
+__device__ __forceinline__ bool scan_bin(const ChainArgs &a, const DictView &d, uint32_t bs, uint32_t bc, uint32_t r0, uint32_t r1, uint32_t r2,
                          const uint64_t *refsm, bool rev, int s, int ref_len, int lane, int grp, int wig, uint32_t &rid_out,
                          uint32_t &compares) {
-  const int W = a.W;
-  const uint32_t G = a.G;
+  const int W = WT ? WT : a.W;  // WT > 0: words per read known at compile time (index arithmetic folds)
+  const uint32_t G = WT ? 32u / (uint32_t)(WT ? WT : 1) : a.G;
   const bool act = (uint32_t)grp < G;
-  const unsigned leaders = a.leader_mask;                  // lanes with wig == 0 of the G groups
+  unsigned leaders = a.leader_mask;                        // lanes with wig == 0 of the G groups
+  if (WT) { leaders = 0; for (uint32_t q = 0; q < G; q++) leaders |= 1u << (q * (uint32_t)W); }  // a constant when W is
   const unsigned below = leaders & ((1u << (lane - wig)) - 1u);  // leaders of the groups before mine
   const uint64_t rw = rev ? shl_word(refsm, W, wig, 2 * s) : shr_word(refsm, W, wig, 2 * s);
   int live_before = 0;
@@ -288,10 +290,11 @@ __device__ bool scan_bin(const ChainArgs &a, const DictView &d, uint32_t bs, uin
 // batch b = 0, 1, ...; a chain that finds nothing continues with the next batch in the next round
 // (bounded work per round keeps the lock-step chains balanced; claims only grow, so earlier batches
 // cannot turn productive later -- same result as a full search, see oracle/spring_oracle.c).
-__device__ bool chain_search(const ChainArgs &a, const uint64_t *ref, const uint64_t *revref, int ref_len, int lane, int grp,
+template <int WT>
+__device__ __forceinline__ bool chain_search(const ChainArgs &a, const uint64_t *ref, const uint64_t *revref, int ref_len, int lane, int grp,
                              int wig, int b, int S, uint32_t &prop_rid, int &prop_shift, int &prop_rev, uint32_t &probes_issued,
                              uint32_t &probes_seq, uint32_t &compares, uint32_t &slot_probes) {
-  const int W = a.W;
+  const int W = WT ? WT : a.W;
   const int kind = lane & 3, rev = kind >> 1, sub = lane >> 2;
   const DictView &d = a.dict[kind & 1];
   const uint64_t *src = rev ? revref : ref;
@@ -351,7 +354,7 @@ __device__ bool chain_search(const ChainArgs &a, const uint64_t *ref, const uint
       const uint32_t r0 = __shfl_sync(FULL, cur_r0, owner), r1 = __shfl_sync(FULL, cur_r1, owner), r2 = __shfl_sync(FULL, cur_r2, owner);
       const DictView &pd = a.dict[pk & 1];
       uint32_t rid;
-      if (scan_bin(a, pd, mb, mc, r0, r1, r2, (pk >> 1) ? revref : ref, pk >> 1, ps, ref_len, lane, grp, wig, rid, compares)) {
+      if (scan_bin<WT>(a, pd, mb, mc, r0, r1, r2, (pk >> 1) ? revref : ref, pk >> 1, ps, ref_len, lane, grp, wig, rid, compares)) {
         prop_rid = rid; prop_shift = ps; prop_rev = pk >> 1; found_p = p;
         break;
       }
@@ -404,13 +407,15 @@ __host__ __device__ inline size_t chain_smem_words(int W, int Lp) { return 3 * (
 
 // WPB warps (= chains) per block, at least MINB blocks per SM: the register budget is the knob that
 // decides how many chains co-reside (run_reorder picks the configuration)
-template <bool LOCKSTEP, int WPB, int MINB>
+// WT > 0: specialised for reads of WT words (W = 5: up to 160 bases, W = 8: up to 256) -- every row address, lane / W
+// split, per-chain shared-memory offset and loop bound becomes a constant; WT = 0: any length, from the arguments
+template <bool LOCKSTEP, int WPB, int MINB, int WT>
 __global__ void __launch_bounds__(WPB * 32, MINB) k_chains(ChainArgs a) {
   constexpr int kWarpsPerBlock = WPB;
   extern __shared__ __align__(16) uint64_t smem[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const uint32_t cid = blockIdx.x * kWarpsPerBlock + wib;
-  const int W = a.W, Lp = a.Lp;
+  const int W = WT ? WT : a.W, Lp = WT ? 32 * WT : a.Lp;  // Lp = 32 W for every L (words_for)
   const int grp = lane / W, wig = lane - grp * W;  // scan_bin's lane layout
   const size_t per_chain = chain_smem_words(W, Lp);
   uint64_t *ref = smem + wib * per_chain, *revref = ref + W + 1, *curw = revref + W + 1;
@@ -516,7 +521,7 @@ __global__ void __launch_bounds__(WPB * 32, MINB) k_chains(ChainArgs a) {
         if (!stop_searching) {
           int b = 0, S = 0;
           while (S < a.maxshift) {
-            if (chain_search(a, ref, revref, ref_len, lane, grp, wig, b, S, k, shift, prev_rev, c_issued, c_seq, c_cmp, c_slot)) {
+            if (chain_search<WT>(a, ref, revref, ref_len, lane, grp, wig, b, S, k, shift, prev_rev, c_issued, c_seq, c_cmp, c_slot)) {
               // the claim's round trip overlaps the loads the update will need (row, length, slot indices)
               unsigned old = 0;
               if (lane == 0) old = atomicOr(a.claimed + (k >> 5), 1u << (k & 31));
@@ -645,7 +650,7 @@ __global__ void __launch_bounds__(WPB * 32, MINB) k_chains(ChainArgs a) {
         iter_started = 1;
       }
       if (!stop_searching) {
-        has_prop = chain_search(a, ref, revref, ref_len, lane, grp, wig, batch, batch_S, prop_rid, prop_shift, prop_rev, c_issued,
+        has_prop = chain_search<WT>(a, ref, revref, ref_len, lane, grp, wig, batch, batch_S, prop_rid, prop_shift, prop_rev, c_issued,
                                 c_seq, c_cmp, c_slot);
         if (!has_prop) {
           const int nshift = 8 * (batch < 4 ? 1 << batch : 16);
@@ -801,17 +806,24 @@ void run_reorder(Ctx &c, const uint64_t *reads, const uint16_t *lens, uint32_t n
   // launch configuration: warps per block x minimum blocks per SM.  The deterministic schedule is a cooperative launch
   // and keeps 8 x 3; the free-running one defaults to kChainCfgDefault (SPRING_B200_KCFG=8x3|8x4|8x5|8x6|4x7|4x9
   // overrides it: occupancy experiments).
-  void (*kern)(ChainArgs) = k_chains<true, 8, 3>;
+  void (*kern)(ChainArgs) = k_chains<true, 8, 3, 0>;
   int kWarpsPerBlock = 8;
   if (!lockstep) {
     const char *cfg = getenv("SPRING_B200_KCFG");
     const std::string want = cfg ? cfg : kChainCfgDefault;
-    if (want == "8x4") { kern = k_chains<false, 8, 4>; kWarpsPerBlock = 8; }
-    else if (want == "8x5") { kern = k_chains<false, 8, 5>; kWarpsPerBlock = 8; }
-    else if (want == "8x6") { kern = k_chains<false, 8, 6>; kWarpsPerBlock = 8; }
-    else if (want == "4x9") { kern = k_chains<false, 4, 9>; kWarpsPerBlock = 4; }
-    else if (want == "4x7") { kern = k_chains<false, 4, 7>; kWarpsPerBlock = 4; }
-    else { kern = k_chains<false, 8, 3>; kWarpsPerBlock = 8; }
+    const bool generic_w = getenv("SPRING_B200_GENERIC_W") != nullptr;  // A/B: the any-length instantiation
+    if (want == "8x4") {
+      kWarpsPerBlock = 8;
+      if (W == 5 && !generic_w) kern = k_chains<false, 8, 4, 5>;       // 129..160 bases (150 bp reads)
+      else if (W == 8 && !generic_w) kern = k_chains<false, 8, 4, 8>;  // 225..256 bases (250 bp reads)
+      else if (W == 4 && !generic_w) kern = k_chains<false, 8, 4, 4>;  // 97..128 bases (100 / 125 bp reads)
+      else kern = k_chains<false, 8, 4, 0>;
+    }
+    else if (want == "8x5") { kern = k_chains<false, 8, 5, 0>; kWarpsPerBlock = 8; }
+    else if (want == "8x6") { kern = k_chains<false, 8, 6, 0>; kWarpsPerBlock = 8; }
+    else if (want == "4x9") { kern = k_chains<false, 4, 9, 0>; kWarpsPerBlock = 4; }
+    else if (want == "4x7") { kern = k_chains<false, 4, 7, 0>; kWarpsPerBlock = 4; }
+    else { kern = k_chains<false, 8, 3, 0>; kWarpsPerBlock = 8; }
   }
   const size_t smem = kWarpsPerBlock * chain_smem_words(W, Lp) * sizeof(uint64_t);
   SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -10,7 +10,7 @@ for ln in txt.splitlines():
     m = re.search(r"Function : (\S+)", ln)
     if m:
         cur = m.group(1); funcs[cur] = []; continue
-    if cur and re.search(r"/\*[0-9a-f]{4}\*/", ln):
+    if cur and re.search(r"/\*[0-9a-f]{4,}\*/", ln):
         ins = re.sub(r"/\*[0-9a-f]+\*/", "", ln).strip().rstrip(";").strip()
         if ins:
             funcs[cur].append(ins)

@@ -10,30 +10,11 @@
 
 namespace sb {
 namespace {
-constexpr int kK = 16;  // k-mer length (32-bit k-mers)
-
 __global__ void k_bucket(const uint64_t *__restrict__ reads, const uint16_t *__restrict__ lens, uint32_t n, int W,
                          uint32_t num_buckets, uint32_t *__restrict__ bucket) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const uint64_t *r = reads + (size_t)i * W;
-  const int len = lens[i];
-  uint64_t best = ~0ull;
-  uint32_t fwd = 0, rc = 0;
-  uint64_t w = 0;
-  for (int j = 0; j < len; j++) {
-    if ((j & 31) == 0) w = r[j >> 5];
-    const uint32_t c = (uint32_t)(w & 3ull);
-    w >>= 2;
-    fwd = (fwd << 2) | c;                      // kK = 16 bases fill the 32-bit word exactly
-    rc = (rc >> 2) | ((3u - c) << (2 * (kK - 1)));
-    if (j >= kK - 1) {
-      const uint64_t h = mix64((uint64_t)(fwd < rc ? fwd : rc));
-      best = h < best ? h : best;
-    }
-  }
-  if (len < kK) best = mix64((uint64_t)len);
-  bucket[i] = (uint32_t)((best >> 16) % num_buckets);
+  bucket[i] = minimizer_bucket(reads + (size_t)i * W, lens[i], num_buckets);  // common.cuh: the same function the exchange uses
 }
 }  // namespace
 

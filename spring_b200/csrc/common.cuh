@@ -89,6 +89,34 @@ constexpr uint64_t kInvalidKey = ~0ull;  // hk of a read that is not indexed (to
 
 __host__ __device__ inline int words_for(int max_readlen) { return (2 * max_readlen - 1) / 64 + 1; }
 
+// ---- multi-GPU owner of a read: strand-canonical 16-mer minimizer bucket (bucket.cu, exchange.cu) -----------------
+// One pass over the read: forward and reverse-complement 16-mer in two 32-bit registers, per position a 32-bit
+// multiply-xorshift hash of the smaller one (a handful of integer instructions: the pass is ALU work, 150 positions per
+// read), minimum over the positions; the minimum is spread by mix64 once per read.  A read, its reverse complement and
+// its shifted neighbours mostly agree on the minimizer.
+constexpr int kMinimizerK = 16;
+__host__ __device__ inline uint32_t kmer_hash32(uint32_t x) {
+  x *= 0x9E3779B1u;
+  return x ^ (x >> 15);
+}
+__host__ __device__ inline uint32_t minimizer_bucket(const uint64_t *r, int len, uint32_t num_buckets) {
+  uint32_t best = 0xFFFFFFFFu, fwd = 0, rc = 0;
+  uint64_t w = 0;
+  for (int j = 0; j < len; j++) {
+    if ((j & 31) == 0) w = r[j >> 5];
+    const uint32_t c = (uint32_t)(w & 3ull);
+    w >>= 2;
+    fwd = (fwd << 2) | c;                      // 16 bases fill the 32-bit word exactly
+    rc = (rc >> 2) | ((3u - c) << (2 * (kMinimizerK - 1)));
+    if (j >= kMinimizerK - 1) {
+      const uint32_t h = kmer_hash32(fwd < rc ? fwd : rc);
+      best = h < best ? h : best;
+    }
+  }
+  if (len < kMinimizerK) best = kmer_hash32((uint32_t)len);
+  return (uint32_t)((mix64((uint64_t)best) >> 16) % num_buckets);
+}
+
 // reorder dictionary windows (reorder.h:752-759)
 inline void reorder_windows(int L, int start[2], int end[2]) {
   start[0] = L > 100 ? L / 2 - 32 : L / 2 - L * 32 / 100;

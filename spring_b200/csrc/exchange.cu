@@ -74,28 +74,8 @@ NcclApi &nccl() {
     if (_r != ncclSuccess) throw sb::CudaError(std::string(#expr) + ": " + nccl().GetErrorString(_r));                   \
   } while (0)
 
-constexpr int kK = 16;        // k-mer length of the minimizer (bucket.cu)
 constexpr int kBlock = 256;   // reads per block of the histogram / scatter passes
 constexpr int kMaxWorld = 256;
-
-__device__ __forceinline__ uint32_t minimizer_bucket(const uint64_t *r, int len, uint32_t num_buckets) {
-  uint64_t best = ~0ull;
-  uint32_t fwd = 0, rc = 0;
-  uint64_t w = 0;
-  for (int j = 0; j < len; j++) {
-    if ((j & 31) == 0) w = r[j >> 5];
-    const uint32_t c = (uint32_t)(w & 3ull);
-    w >>= 2;
-    fwd = (fwd << 2) | c;                      // kK = 16 bases fill the 32-bit word exactly
-    rc = (rc >> 2) | ((3u - c) << (2 * (kK - 1)));
-    if (j >= kK - 1) {
-      const uint64_t h = mix64((uint64_t)(fwd < rc ? fwd : rc));
-      best = h < best ? h : best;
-    }
-  }
-  if (len < kK) best = mix64((uint64_t)len);
-  return (uint32_t)((best >> 16) % num_buckets);
-}
 
 // owner of every read (one byte) + histogram of the owners per block of 256 reads
 __global__ void __launch_bounds__(kBlock) k_bucket_hist(const uint64_t *__restrict__ reads, const uint16_t *__restrict__ lens, uint32_t n,

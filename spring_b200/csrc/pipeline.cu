@@ -71,7 +71,8 @@ void check_input(const spring_b200_input *in) {
   if ((uint64_t)in->num_clean + in->num_n != in->num_reads) throw ArgError("num_clean + num_n != num_reads");
   if (in->num_clean && (!in->reads || !in->lengths)) throw ArgError("null reads/lengths");
   if (in->num_n && (!in->n_records || !in->order_n)) throw ArgError("null n_records/order_n");
-  if (in->num_reads >= 0x7FFFFFF0u) throw ArgError("too many reads for one GPU shard (>= 2^31)");
+  // 32-bit slot indices and bins[] offsets (up to 2 n): at most 2^30 reads per GPU shard; bigger jobs are sharded over GPUs
+  if (in->num_reads > (1u << 30)) throw ArgError("too many reads for one GPU shard (> 2^30)");
 }
 
 // input_N.dna records (util.cpp:322-374) -> 2-bit codes (N as 00) + N bit-plane, uploaded

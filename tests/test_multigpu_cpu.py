@@ -28,24 +28,29 @@ def mix64(x: np.ndarray) -> np.ndarray:
 
 
 def bucket_numpy(packed: np.ndarray, lengths: np.ndarray, num_buckets: int) -> np.ndarray:
-    """numpy mirror of k_bucket (spring_b200/csrc/bucket.cu): canonical 16-mer minimizer bucket."""
+    """numpy mirror of minimizer_bucket (spring_b200/csrc/common.cuh): canonical 16-mer minimizer bucket."""
     n = len(lengths)
     lmax = int(lengths.max()) if n else 0
     codes = dnaio.unpack_codes(packed, max(lmax, 1)).astype(np.uint64)
-    best = np.full(n, M64, dtype=np.uint64)
+    M32 = np.uint64(0xFFFFFFFF)
+
+    def h32(x):
+        x = (x * np.uint64(0x9E3779B1)) & M32
+        return x ^ (x >> np.uint64(15))
+    best = np.full(n, 0xFFFFFFFF, dtype=np.uint64)
     fwd = np.zeros(n, np.uint64); rc = np.zeros(n, np.uint64)
     with np.errstate(over="ignore"):
         for j in range(lmax):
             c = codes[:, j]
-            fwd = ((fwd << np.uint64(2)) | c) & np.uint64(0xFFFFFFFF)
+            fwd = ((fwd << np.uint64(2)) | c) & M32
             rc = (rc >> np.uint64(2)) | ((np.uint64(3) - c) << np.uint64(30))
             if j >= 15:
-                h = mix64(np.minimum(fwd, rc))
+                h = h32(np.minimum(fwd, rc))
                 upd = (j < lengths) & (h < best)
                 best = np.where(upd, h, best)
         short = lengths < 16
-        best = np.where(short, mix64(lengths.astype(np.uint64)), best)
-    return ((best >> np.uint64(16)) % np.uint64(num_buckets)).astype(np.int32)
+        best = np.where(short, h32(lengths.astype(np.uint64)), best)
+        return ((mix64(best) >> np.uint64(16)) % np.uint64(num_buckets)).astype(np.int32)
 
 
 def _free_port():

@@ -7,7 +7,7 @@ import numpy as np
 from helpers import CASES, make_input
 from spring_b200 import capi, dnaio
 ctx = capi.Context(0)
-for name in ("se100_n", "var64_noisy", "long511", "heavy_bins", "pe100_illumina"):
+for name in (sys.argv[1:] or ("se100_n", "var64_noisy", "long511", "heavy_bins", "pe100_illumina")):
     kw = dict(CASES[name]); kw["num_reads"] = min(kw["num_reads"], 3000)
     hp = make_input(**kw)
     for det in (False, True):
@@ -22,6 +22,11 @@ for name in ("se100_n", "var64_noisy", "long511", "heavy_bins", "pe100_illumina"
         b1 = ctx.reblock_streams(cp, None)      # streams resident in HBM
         b2 = ctx.reblock_streams(cp, s)         # host streams
         assert all(b1.data[k].tobytes() == b2.data[k].tobytes() for k in b1.data)
+    # round trip in HBM (verify.cu: re-block -> decode.cu -> compare) on the resident streams of the last call
+    ctx.reorder_encode(hp.packed, hp.lengths, hp.max_readlen, hp.n_records, hp.order_n, hp.num_reads, 16)
+    v = ctx.verify_roundtrip(capi.CP.from_buffer_copy(dnaio.CompressionParams(paired_end=paired, preserve_order=False, num_reads=hp.num_reads,
+                                                                               max_readlen=hp.max_readlen, num_reads_per_block=700).pack()))
+    assert v["ok"] == 1, v
     seqs = dnaio.packed_to_seqs(hp.packed, hp.lengths) + list(hp.n_seqs)
     offs = np.zeros(len(seqs) + 1, np.uint64); offs[1:] = np.cumsum([len(x) for x in seqs])
     pk = ctx.pack_reads(np.frombuffer(b"".join(seqs), np.uint8), offs)

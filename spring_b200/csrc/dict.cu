@@ -12,6 +12,12 @@
 // home when the keys go in ascending -- is one running-max scan; the table, the bins and the key filter (word = top
 // bits of hk as well) are then written front to back with plain coalesced stores, no atomics, no probing.
 //
+// The radix sort runs on the TOP 32 bits of hk only (4 passes instead of 8), with (low 32 bits of hk, read id) as its
+// 64-bit value.  Two different keys share their top 32 bits about once per 2^32 / n keys (1 % of the keys at 100 M); such a
+// run comes out of the stable sort ordered by read id with the keys interleaved, and one thread re-orders it by the
+// low 32 bits (stable insertion sort; k_fix_runs) before the bins are cut.  The value 0xFFFFFFFF of the top bits is
+// reserved for reads that are not indexed.
+//
 // No host synchronisation: reads that are not indexed get hk = ~0 and sort behind everything, the number of unique keys
 // stays on the device (kernels are launched over the upper bound n and read it there), the table is sized from n.
 #include <climits>
@@ -26,32 +32,66 @@ struct MaxOp {
   __device__ int operator()(int a, int b) const { return a > b ? a : b; }
 };
 
-// hk = mix64((read & mask1) >> 2*start) (bitset_util.h:93-94), ~0 for a read that is not indexed.  One thread per
-// read; a warp touches 32 consecutive rows of W words (coalesced across the warp's combined footprint).
+// hk = mix64((read & mask1) >> 2*start) (bitset_util.h:93-94) as sort key k32 = hk >> 32 and value (hk << 32) | read id;
+// k32 = 0xFFFFFFFF marks a read that is not indexed (too short for the window, N inside it -- or, once per 2^32 keys, a
+// real key whose top bits are all ones: its reads simply stay unindexed).  One thread per read; a warp touches 32
+// consecutive rows of W words (coalesced across the warp's combined footprint).
 __global__ void k_extract_keys(const uint64_t *__restrict__ reads, const uint16_t *__restrict__ lens,
                                const uint64_t *__restrict__ nflag, uint32_t n, int W, int start, int end,
-                               uint64_t *__restrict__ hkeys, uint32_t *__restrict__ rids, uint32_t *__restrict__ num_valid) {
+                               uint32_t *__restrict__ k32, uint64_t *__restrict__ val, uint32_t *__restrict__ num_valid) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   bool ok = false;
   if (i < n) {
     const uint64_t *r = reads + (size_t)i * W;
     const int nbits = 2 * (end - start + 1);
-    uint64_t hk = mix64(extract_bits(r, W, 2 * start, nbits));
+    const uint64_t hk = mix64(extract_bits(r, W, 2 * start, nbits));
     ok = lens[i] > end;  // bitset_util.h:99-105
     if (ok && nflag) ok = extract_bits(nflag + (size_t)i * W, W, 2 * start, nbits) == 0;
-    if (hk == kInvalidKey) ok = false;  // one key in 2^64 shares the marker: its reads simply stay unindexed
-    hkeys[i] = ok ? hk : kInvalidKey;
-    rids[i] = i;
+    if ((uint32_t)(hk >> 32) == 0xFFFFFFFFu) ok = false;
+    k32[i] = ok ? (uint32_t)(hk >> 32) : 0xFFFFFFFFu;
+    val[i] = (ok ? hk << 32 : 0xFFFFFFFF00000000ull) | i;
   }
   const int c = __syncthreads_count(ok);
   if (threadIdx.x == 0 && c) atomicAdd(num_valid, (uint32_t)c);
 }
 
-__global__ void k_mark_heads(const uint64_t *__restrict__ hkeys, uint32_t n, uint8_t *__restrict__ head, uint32_t *__restrict__ head32) {
+// Runs of equal k32 that hold more than one key: thread i sits on a place where the low key bits change inside a run;
+// the first such thread of a run to take the run's lock (at the run's head) re-orders the whole run by the low bits,
+// stably, so read ids stay ascending inside every key.  Runs with one key -- all but ~n / 2^32 of them -- cost two loads.
+__global__ void k_fix_runs(const uint32_t *__restrict__ k32, uint64_t *val, uint32_t n, uint8_t *lock) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0 || i >= n) return;
+  const uint32_t k = k32[i];
+  if (k == 0xFFFFFFFFu || k != k32[i - 1] || (uint32_t)(val[i] >> 32) == (uint32_t)(val[i - 1] >> 32)) return;
+  uint32_t h = i - 1;
+  while (h > 0 && k32[h - 1] == k) h--;
+  // one byte per entry, four entries per word: set the byte of the run's head
+  unsigned int *w = reinterpret_cast<unsigned int *>(lock + (h & ~3u));
+  const unsigned int bit = 1u << (8 * (h & 3u));
+  if (atomicOr(w, bit) & bit) return;  // another thread of this run has it
+  uint32_t e = i + 1;
+  while (e < n && k32[e] == k) e++;
+  for (uint32_t a = h + 1; a < e; a++) {  // stable insertion sort of val[h, e) by its high half
+    const uint64_t x = val[a];
+    uint32_t b = a;
+    while (b > h && (uint32_t)(val[b - 1] >> 32) > (uint32_t)(x >> 32)) { val[b] = val[b - 1]; b--; }
+    val[b] = x;
+  }
+}
+
+// sorted (k32, value) -> hashed keys hk (unindexed: ~0), read ids, and the heads of the runs of equal hk = the bins
+__global__ void k_unpack_heads(const uint32_t *__restrict__ k32, const uint64_t *__restrict__ val, uint32_t n,
+                               uint64_t *__restrict__ hkeys, uint32_t *__restrict__ rids, uint8_t *__restrict__ head,
+                               uint32_t *__restrict__ head32) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const uint64_t k = hkeys[i];
-  const uint32_t h = (k != kInvalidKey && (i == 0 || k != hkeys[i - 1])) ? 1 : 0;
+  const uint32_t k = k32[i];
+  const uint64_t v = val[i];
+  const uint64_t hk = k == 0xFFFFFFFFu ? kInvalidKey : ((uint64_t)k << 32) | (v >> 32);
+  uint32_t h = 0;
+  if (k != 0xFFFFFFFFu) h = (i == 0 || k != k32[i - 1] || (uint32_t)(v >> 32) != (uint32_t)(val[i - 1] >> 32)) ? 1u : 0u;
+  hkeys[i] = hk;
+  rids[i] = (uint32_t)v;
   head[i] = (uint8_t)h;
   head32[i] = h;
 }
@@ -128,12 +168,12 @@ void build_dictionary(Ctx &c, const uint64_t *reads, const uint16_t *lens, const
   out.view.end = end;
   out.view.key_bits = 2 * (end - start + 1);
   const uint32_t nn = n ? n : 1;
-  uint64_t *keys_a = c.pool.dev<uint64_t>(nm(".keys_a").c_str(), nn);
-  uint64_t *keys_b = c.pool.dev<uint64_t>(nm(".keys_b").c_str(), nn);
-  uint32_t *rid_a = c.pool.dev<uint32_t>(nm(".rid_a").c_str(), nn);
-  uint32_t *rid_c = c.pool.dev<uint32_t>(nm(".rid_c").c_str(), nn);
+  uint64_t *val_a = c.pool.dev<uint64_t>(nm(".val_a").c_str(), nn), *val_b = c.pool.dev<uint64_t>(nm(".val_b").c_str(), nn);
+  uint32_t *k32_a = c.pool.dev<uint32_t>(nm(".k32_a").c_str(), nn), *k32_b = c.pool.dev<uint32_t>(nm(".k32_b").c_str(), nn);
+  uint64_t *keys_b = val_a;   // the sort's input buffers are free again when the sorted pairs are unpacked
+  uint32_t *rid_c = k32_a;
   uint32_t *bin_start_idx = c.pool.dev<uint32_t>(nm(".bin_start").c_str(), nn);
-  uint8_t *flag = c.pool.dev<uint8_t>(nm(".flag").c_str(), nn);
+  uint8_t *flag = c.pool.dev<uint8_t>(nm(".flag").c_str(), (size_t)nn + 4);
   uint32_t *head32 = c.pool.dev<uint32_t>(nm(".head32").c_str(), nn);
   uint32_t *kidx1 = c.pool.dev<uint32_t>(nm(".kidx1").c_str(), nn);
   int *hm = c.pool.dev<int>(nm(".home_minus").c_str(), nn), *hmax = c.pool.dev<int>(nm(".home_max").c_str(), nn);
@@ -171,7 +211,7 @@ void build_dictionary(Ctx &c, const uint64_t *reads, const uint16_t *lens, const
   if (n == 0) return;
 
   size_t tmp_bytes = 0, need = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, need, keys_a, keys_b, rid_a, rid_c, (int)n, 0, 64, st); tmp_bytes = need;
+  cub::DeviceRadixSort::SortPairs(nullptr, need, k32_a, k32_b, val_a, val_b, (int)n, 0, 32, st); tmp_bytes = need;
   cub::DeviceScan::InclusiveSum(nullptr, need, head32, kidx1, (int)n, st); if (need > tmp_bytes) tmp_bytes = need;
   cub::DeviceScan::InclusiveScan(nullptr, need, hm, hmax, MaxOp(), (int)n, st); if (need > tmp_bytes) tmp_bytes = need;
   {
@@ -181,11 +221,13 @@ void build_dictionary(Ctx &c, const uint64_t *reads, const uint16_t *lens, const
   }
   void *tmp = c.pool.device(nm(".cubtmp").c_str(), tmp_bytes);
 
-  k_extract_keys<<<grid_for(n, 256), 256, 0, st>>>(reads, lens, nflag, n, W, start, end, keys_a, rid_a, d_count);
-  // stable LSD radix sort: read ids stay ascending inside equal keys; unindexed reads (hk = ~0) end up last
+  k_extract_keys<<<grid_for(n, 256), 256, 0, st>>>(reads, lens, nflag, n, W, start, end, k32_a, val_a, d_count);
+  // stable LSD radix sort on the top 32 bits: read ids stay ascending inside equal keys; unindexed reads end up last
   need = tmp_bytes;
-  cub::DeviceRadixSort::SortPairs(tmp, need, keys_a, keys_b, rid_a, rid_c, (int)n, 0, 64, st);
-  k_mark_heads<<<grid_for(n, 256), 256, 0, st>>>(keys_b, n, flag, head32);
+  cub::DeviceRadixSort::SortPairs(tmp, need, k32_a, k32_b, val_a, val_b, (int)n, 0, 32, st);
+  SB_CUDA(cudaMemsetAsync(flag, 0, ((size_t)nn + 3) & ~(size_t)3, st));  // run locks of k_fix_runs
+  k_fix_runs<<<grid_for(n, 256), 256, 0, st>>>(k32_b, val_b, n, flag);
+  k_unpack_heads<<<grid_for(n, 256), 256, 0, st>>>(k32_b, val_b, n, keys_b, rid_c, flag, head32);
   need = tmp_bytes;
   cub::DeviceScan::InclusiveSum(tmp, need, head32, kidx1, (int)n, st);
   cub::CountingInputIterator<uint32_t> cnt(0);
@@ -197,7 +239,7 @@ void build_dictionary(Ctx &c, const uint64_t *reads, const uint16_t *lens, const
   k_insert_slots<<<grid_for(n, 256), 256, 0, st>>>(keys_b, rid_c, bin_start_idx, d_count + 1, d_count, hmax, n, (uint32_t)cap + kSlotPad - 1,
                                                   out.view.filter_shift, slots, bins, slot_of_bin, filter, d_count + 2);
   k_fill_bins<<<grid_for(n, 256), 256, 0, st>>>(keys_b, rid_c, kidx1, bin_start_idx, slot_of_bin, d_count + 1, d_count, n, bins, slot_of_read);
-  c.launches += 5 + (2 + 16) + 2 + 3 + 2;  // ours + CUB (sort: histogram + 8 x onesweep ..., scans, select)
+  c.launches += 6 + (2 + 4) + 2 + 3 + 2;  // ours + CUB (sort: histogram + 4 x onesweep, scans, select)
   SB_CUDA(cudaGetLastError());
 }
 

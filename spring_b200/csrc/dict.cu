@@ -55,27 +55,32 @@ __global__ void k_extract_keys(const uint64_t *__restrict__ reads, const uint16_
   if (threadIdx.x == 0 && c) atomicAdd(num_valid, (uint32_t)c);
 }
 
-// Runs of equal k32 that hold more than one key: thread i sits on a place where the low key bits change inside a run;
-// the first such thread of a run to take the run's lock (at the run's head) re-orders the whole run by the low bits,
-// stably, so read ids stay ascending inside every key.  Runs with one key -- all but ~n / 2^32 of them -- cost two loads.
-__global__ void k_fix_runs(const uint32_t *__restrict__ k32, uint64_t *val, uint32_t n, uint8_t *lock) {
+// The sort looked at the top `32 - rshift` bits only (rshift = 0 unless SPRING_B200_DICT_SORT_BITS says otherwise: a
+// test knob that makes multi-key runs common at any input size).  A run of entries equal in those bits is in read-id
+// order; if it holds several keys out of order -- thread i sits on such an inversion -- the first thread to take the
+// run's lock (at the run's head) re-orders the whole run by the full key, stably, so read ids stay ascending inside
+// every key.  Runs that are already in order -- all but ~n / 2^32 of them at 32 bits -- cost two loads per entry.
+__device__ __forceinline__ uint64_t full_key(uint32_t k, uint64_t v) { return ((uint64_t)k << 32) | (v >> 32); }
+__global__ void k_fix_runs(uint32_t *k32, uint64_t *val, uint32_t n, int rshift, uint8_t *lock) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i == 0 || i >= n) return;
-  const uint32_t k = k32[i];
-  if (k == 0xFFFFFFFFu || k != k32[i - 1] || (uint32_t)(val[i] >> 32) == (uint32_t)(val[i - 1] >> 32)) return;
+  const uint32_t k = k32[i], run = k >> rshift;
+  if (rshift == 0 && k == 0xFFFFFFFFu) return;  // the unindexed reads: one homogeneous run, possibly huge
+  if (run != (k32[i - 1] >> rshift) || full_key(k, val[i]) >= full_key(k32[i - 1], val[i - 1])) return;
   uint32_t h = i - 1;
-  while (h > 0 && k32[h - 1] == k) h--;
+  while (h > 0 && (k32[h - 1] >> rshift) == run) h--;
   // one byte per entry, four entries per word: set the byte of the run's head
   unsigned int *w = reinterpret_cast<unsigned int *>(lock + (h & ~3u));
   const unsigned int bit = 1u << (8 * (h & 3u));
   if (atomicOr(w, bit) & bit) return;  // another thread of this run has it
   uint32_t e = i + 1;
-  while (e < n && k32[e] == k) e++;
-  for (uint32_t a = h + 1; a < e; a++) {  // stable insertion sort of val[h, e) by its high half
-    const uint64_t x = val[a];
+  while (e < n && (k32[e] >> rshift) == run) e++;
+  for (uint32_t a = h + 1; a < e; a++) {  // stable insertion sort of the pairs [h, e) by their full key
+    const uint32_t xk = k32[a];
+    const uint64_t xv = val[a], x = full_key(xk, xv);
     uint32_t b = a;
-    while (b > h && (uint32_t)(val[b - 1] >> 32) > (uint32_t)(x >> 32)) { val[b] = val[b - 1]; b--; }
-    val[b] = x;
+    while (b > h && full_key(k32[b - 1], val[b - 1]) > x) { k32[b] = k32[b - 1]; val[b] = val[b - 1]; b--; }
+    k32[b] = xk; val[b] = xv;
   }
 }
 
@@ -224,9 +229,14 @@ void build_dictionary(Ctx &c, const uint64_t *reads, const uint16_t *lens, const
   k_extract_keys<<<grid_for(n, 256), 256, 0, st>>>(reads, lens, nflag, n, W, start, end, k32_a, val_a, d_count);
   // stable LSD radix sort on the top 32 bits: read ids stay ascending inside equal keys; unindexed reads end up last
   need = tmp_bytes;
-  cub::DeviceRadixSort::SortPairs(tmp, need, k32_a, k32_b, val_a, val_b, (int)n, 0, 32, st);
+  static const int kSortBits = [] {
+    const char *e = getenv("SPRING_B200_DICT_SORT_BITS");
+    const int b = e ? atoi(e) : 32;
+    return b < 1 ? 1 : (b > 32 ? 32 : b);
+  }();
+  cub::DeviceRadixSort::SortPairs(tmp, need, k32_a, k32_b, val_a, val_b, (int)n, 32 - kSortBits, 32, st);
   SB_CUDA(cudaMemsetAsync(flag, 0, ((size_t)nn + 3) & ~(size_t)3, st));  // run locks of k_fix_runs
-  k_fix_runs<<<grid_for(n, 256), 256, 0, st>>>(k32_b, val_b, n, flag);
+  k_fix_runs<<<grid_for(n, 256), 256, 0, st>>>(k32_b, val_b, n, 32 - kSortBits, flag);
   k_unpack_heads<<<grid_for(n, 256), 256, 0, st>>>(k32_b, val_b, n, keys_b, rid_c, flag, head32);
   need = tmp_bytes;
   cub::DeviceScan::InclusiveSum(tmp, need, head32, kidx1, (int)n, st);

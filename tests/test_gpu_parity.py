@@ -32,6 +32,44 @@ def test_dictionary_matches_oracle(ctx, name):
         assert (k == ok).all() and (b == ob).all() and (r == orr).all()
 
 
+def test_dictionary_3M_reads_matches_oracle(ctx):
+    """At 3 M keys about a thousand pairs of different keys share their top 32 hash bits: the sort's fix-up of
+    multi-key runs (dict.cu:k_fix_runs) is exercised on real collisions; keys, bins and ids must still be the oracle's."""
+    from spring_b200 import synth
+    hp = synth.to_hotpath_input(synth.generate(3_000_000, 100, genome_len=10_000_000, seed=19, sub_rate=0.005, device="cuda"))
+    for which in (0, 1):
+        k, b, r = ctx.build_dictionary(hp.packed, hp.lengths, hp.max_readlen, which)
+        ok, ob, orr = po.reorder_dict(hp.packed, hp.lengths, hp.max_readlen, which)
+        assert (k == ok).all() and (b == ob).all() and (r == orr).all()
+
+
+def test_multi_key_runs_everywhere(tmp_path):
+    """SPRING_B200_DICT_SORT_BITS=6: the radix sort looks at 6 hash bits only, so EVERY run holds many keys and the
+    fix-up does the real sorting -- dictionaries and streams must not change.  (The knob is read once per process.)"""
+    import subprocess, sys, textwrap
+    code = textwrap.dedent("""
+        import sys
+        sys.path.insert(0, %r); sys.path.insert(0, %r)
+        from helpers import CASES, assert_streams_equal, make_input
+        from oracle import pyoracle as po
+        from spring_b200 import capi
+        ctx = capi.Context(0)
+        for name in ("se150", "var250", "heavy_bins", "pe100_illumina"):
+            hp = make_input(**CASES[name])
+            for which in (0, 1):
+                k, b, r = ctx.build_dictionary(hp.packed, hp.lengths, hp.max_readlen, which)
+                ok, ob, orr = po.reorder_dict(hp.packed, hp.lengths, hp.max_readlen, which)
+                assert (k == ok).all() and (b == ob).all() and (r == orr).all(), name
+            got = ctx.reorder_encode(hp.packed, hp.lengths, hp.max_readlen, hp.n_records, hp.order_n, hp.num_reads, 1)
+            _, er = po.reorder_encode(hp.packed, hp.lengths, hp.max_readlen, hp.n_records, hp.order_n, hp.num_reads, 1)
+            assert_streams_equal(got, er, name)
+        print("ok")
+    """) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300,
+                       env=dict(os.environ, SPRING_B200_DICT_SORT_BITS="6"))
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
+
+
 @pytest.mark.parametrize("name", sorted(CASES))
 def test_reorder_stream_matches_oracle(det, name):
     """reorder<>(), deterministic schedule: order / flag / pos / rev / singleton lists bit-exact

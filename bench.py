@@ -459,8 +459,8 @@ def main() -> None:
     traffic = None
     tp = os.path.join(ROOT, "profiles", "r02_chain_kernel_traffic.json")
     if os.path.exists(tp):
-        tj = json.load(open(tp))
-        if tj.get("reads") == n_local and tj.get("config_id") == cfg_id and world == 1:
+        tj = json.load(open(tp)).get(str(cfg_id), {})  # one ncu capture per config: dram__bytes_read.sum + dram__bytes_write.sum
+        if tj.get("reads") == n_local and world == 1:
             traffic = tj.get("dram_bytes_per_launch")
     roofline = {"kernel": "k_chains", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src, "kernel_ms": ck_ms,

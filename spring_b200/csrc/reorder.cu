@@ -833,8 +833,18 @@ void run_reorder(Ctx &c, const uint64_t *reads, const uint16_t *lens, uint32_t n
   const uint32_t chains_per_block = (uint32_t)kWarpsPerBlock;
   const uint32_t max_chains = (uint32_t)per_sm * c.num_sms * chains_per_block;
   uint32_t C = num_chains;
-  if (C == 0) {  // auto: every co-resident chain, as long as a chain's slice keeps >= 256 reads
-    C = n / 256; if (C < 1) C = 1; if (C > max_chains) C = max_chains;
+  if (C == 0) {
+    // auto: every co-resident chain, as long as a chain's slice keeps >= 2048 reads.  Every chain costs contig starts:
+    // measured (tests/tools/ratio_check.py) the `Reads:` stream grows by about 64 * chains / reads against the reference
+    // (+7.6 % at 4 M reads with 4736 chains), so 2048 reads per chain bound the cost at ~3 % for small inputs, where the
+    // kernel's speed does not matter, and change nothing from 10 M reads up (4736 chains: 3 % at 10 M, 0.3 % at 100 M).
+    // SPRING_B200_READS_PER_CHAIN=6400 keeps it under 1 % at any size; 256 is the round-1 policy.
+    static const uint32_t kReadsPerChain = [] {
+      const char *e = getenv("SPRING_B200_READS_PER_CHAIN");
+      const long v = e ? atol(e) : 2048;
+      return (uint32_t)(v < 1 ? 1 : v);
+    }();
+    C = n / kReadsPerChain; if (C < 1) C = 1; if (C > max_chains) C = max_chains;
     if (const char *e = getenv("SPRING_B200_MAX_CHAINS")) { const uint32_t m = (uint32_t)strtoul(e, nullptr, 10); if (m && C > m) C = m; }
   }
   if (C > max_chains) C = max_chains;

@@ -286,7 +286,7 @@ def test_config2_scale_roundtrip(ctx):
     from spring_b200 import synth
     rs = synth.generate(2_000_000, 150, genome_len=10_000_000, seed=3, sub_rate=0.005, device="cuda")
     got, st = _full_size_roundtrip(ctx, rs)
-    assert got.num_aligned > 0.95 * 2_000_000 and st["num_chains"] > 1000
+    assert got.num_aligned > 0.95 * 2_000_000 and st["num_chains"] > 900
 
 
 def test_config3_like_roundtrip(ctx):

@@ -15,6 +15,9 @@ runs = [("reference", po.REF_BIN, {}), ("b200 auto chains", po.SPLICE_BIN, {}), 
         ("b200 1 chain", po.SPLICE_BIN, {"SPRING_B200_CHAINS": "1"})]
 if "--quick" in sys.argv:
     runs = runs[:3]
+if "--policy" in sys.argv:  # chain-count policies: reads per chain of the auto rule (reorder.cu:run_reorder)
+    runs = [("reference", po.REF_BIN, {})] + [(f"b200 {r} reads/chain", po.SPLICE2_BIN, {"SPRING_B200_READS_PER_CHAIN": str(r)})
+                                              for r in (256, 2048, 6400)]
 for name, binary, env in runs:
     out = os.path.join(d, name.replace(" ", "_") + ".spring")
     t0 = time.time()

@@ -68,7 +68,8 @@ struct DictView {
   uint32_t *skip;                // [like bins] at a bin's header index: entries before this offset are all claimed
                                  // (monotone hint: a scan of a big bin starts there; plays bbhashdict::remove's compaction)
   const uint32_t *filter;        // blocked Bloom filter over the keys: 2 bits in one 32-bit word, >= 8 bits per key
-  int filter_shift;              // filter word of hk = hk >> filter_shift (top bits: the build sets it front to back too)
+  uint32_t filter_words;         // filter word of hk = (top 32 bits of hk) * filter_words >> 32: any size, monotone in hk
+                                 // (the build sets it front to back too)
   int start, end;                // base window [start, end]
   int key_bits;                  // bits per base * (end - start + 1)
 };
@@ -81,8 +82,9 @@ __host__ __device__ inline uint64_t mix64(uint64_t x) {
   return x;
 }
 
-// key filter (kept L2-resident by the chain kernel as far as it fits): word = top bits of hk, bits hk[0:5) and hk[5:10)
-__host__ __device__ inline uint32_t filter_word(uint64_t hk, int fshift) { return (uint32_t)(hk >> fshift); }
+// key filter (kept L2-resident by the chain kernel as far as it fits): word = top bits of hk scaled to the filter's
+// size (no power-of-two rounding: at 100 M keys that rounding alone was 128 MB instead of 100), bits hk[0:5) and hk[5:10)
+__host__ __device__ inline uint32_t filter_word(uint64_t hk, uint32_t nwords) { return (uint32_t)(((hk >> 32) * (uint64_t)nwords) >> 32); }
 __host__ __device__ inline uint32_t filter_bits(uint64_t hk) { return (1u << (hk & 31)) | (1u << ((hk >> 5) & 31)); }
 __host__ __device__ inline uint32_t slot_home(uint64_t hk, int sshift) { return (uint32_t)(hk >> sshift); }
 constexpr uint64_t kInvalidKey = ~0ull;  // hk of a read that is not indexed (too short for the window, N inside it)
@@ -169,9 +171,9 @@ __device__ __forceinline__ uint64_t spread_bits(uint32_t x) {
 }
 __device__ __forceinline__ int base_code(const uint64_t *w, int j) { return (int)((w[j >> 5] >> (2 * (j & 31))) & 3ull); }
 
-__device__ __forceinline__ bool filter_test(const uint32_t *filter, int fshift, uint64_t hk) {
+__device__ __forceinline__ bool filter_test(const uint32_t *filter, uint32_t nwords, uint64_t hk) {
   const uint32_t b = filter_bits(hk);
-  return (__ldg(filter + filter_word(hk, fshift)) & b) == b;
+  return (__ldg(filter + filter_word(hk, nwords)) & b) == b;
 }
 // L2 eviction policies: the key filter should stay in L2, the slot table streams through it
 __device__ __forceinline__ uint64_t l2_policy_evict_last() {
@@ -184,10 +186,10 @@ __device__ __forceinline__ uint64_t l2_policy_evict_first() {
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
   return p;
 }
-__device__ __forceinline__ bool filter_test_hint(const uint32_t *filter, int fshift, uint64_t hk, uint64_t pol) {
+__device__ __forceinline__ bool filter_test_hint(const uint32_t *filter, uint32_t nwords, uint64_t hk, uint64_t pol) {
   const uint32_t b = filter_bits(hk);
   uint32_t w;
-  asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(w) : "l"(filter + filter_word(hk, fshift)), "l"(pol));
+  asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(w) : "l"(filter + filter_word(hk, nwords)), "l"(pol));
   return (w & b) == b;
 }
 // L2 (.cg) load: `live` is updated by other SMs between rounds, L1 must not serve it

@@ -113,7 +113,7 @@ __global__ void k_home_minus_rank(const uint64_t *__restrict__ hkeys, const uint
 __global__ void k_insert_slots(const uint64_t *__restrict__ hkeys, const uint32_t *__restrict__ rid_sorted,
                                const uint32_t *__restrict__ bin_start_idx, const uint32_t *__restrict__ numkeys_p,
                                const uint32_t *__restrict__ num_valid, const int *__restrict__ m, uint32_t n, uint32_t slot_limit,
-                               int filter_shift, DictSlot *slots, uint32_t *bins, uint32_t *slot_of_bin, uint32_t *filter,
+                               uint32_t filter_words, DictSlot *slots, uint32_t *bins, uint32_t *slot_of_bin, uint32_t *filter,
                                uint32_t *dropped) {
   const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t numkeys = *numkeys_p;
@@ -138,7 +138,7 @@ __global__ void k_insert_slots(const uint64_t *__restrict__ hkeys, const uint32_
   dst[1] = make_uint4(sl.count, sl.rid[0], sl.rid[1], sl.rid[2]);
   slot_of_bin[k] = (uint32_t)slot;
   // keys arrive in ascending hk and the filter word is the top bits of hk: neighbouring threads hit neighbouring words
-  atomicOr(filter + filter_word(hk, filter_shift), filter_bits(hk));
+  atomicOr(filter + filter_word(hk, filter_words), filter_bits(hk));
 }
 
 // sorted entry i (ascending id inside its bin) -> descending position behind the bin header
@@ -197,14 +197,16 @@ void build_dictionary(Ctx &c, const uint64_t *reads, const uint16_t *lens, const
   out.view.slot_shift = 64 - log2_pow2(cap);
   DictSlot *slots = c.pool.dev<DictSlot>(nm(".slots").c_str(), (size_t)cap + kSlotPad);
   SB_CUDA(cudaMemsetAsync(slots, 0, sizeof(DictSlot) * ((size_t)cap + kSlotPad), st));
-  static const unsigned long long kFilterBitsPerKey =
-      getenv("SPRING_B200_FILTER_BITS") ? strtoull(getenv("SPRING_B200_FILTER_BITS"), nullptr, 10) : 8ull;
-  uint64_t fbits = 65536;
-  while (fbits < kFilterBitsPerKey * n && fbits < (1ull << 36)) fbits <<= 1;
-  uint32_t *filter = c.pool.dev<uint32_t>(nm(".filter").c_str(), fbits / 32);
-  SB_CUDA(cudaMemsetAsync(filter, 0, fbits / 8, st));
+  // 32-bit words, 2 bits set per key; SPRING_B200_FILTER_BITS bits per read (default 8: ~5 % false positives).  The size is
+  // not rounded to a power of two: two filters of 100 M keys are 200 MB then, not 256 -- every MB counts against a 126 MB L2.
+  static const double kFilterBitsPerKey = getenv("SPRING_B200_FILTER_BITS") ? atof(getenv("SPRING_B200_FILTER_BITS")) : 8.0;
+  uint64_t fwords = (uint64_t)(kFilterBitsPerKey * (double)n / 32.0) + 1;
+  if (fwords < 2048) fwords = 2048;
+  if (fwords > 0x7FFFFFFFull) fwords = 0x7FFFFFFFull;
+  uint32_t *filter = c.pool.dev<uint32_t>(nm(".filter").c_str(), fwords);
+  SB_CUDA(cudaMemsetAsync(filter, 0, fwords * sizeof(uint32_t), st));
   out.view.filter = filter;
-  out.view.filter_shift = 64 - log2_pow2(fbits / 32);
+  out.view.filter_words = (uint32_t)fwords;
   out.view.slots = slots;
   out.view.bins = bins;
   out.view.slot_of_read = slot_of_read;
@@ -247,7 +249,7 @@ void build_dictionary(Ctx &c, const uint64_t *reads, const uint16_t *lens, const
   need = tmp_bytes;
   cub::DeviceScan::InclusiveScan(tmp, need, hm, hmax, MaxOp(), (int)n, st);
   k_insert_slots<<<grid_for(n, 256), 256, 0, st>>>(keys_b, rid_c, bin_start_idx, d_count + 1, d_count, hmax, n, (uint32_t)cap + kSlotPad - 1,
-                                                  out.view.filter_shift, slots, bins, slot_of_bin, filter, d_count + 2);
+                                                  out.view.filter_words, slots, bins, slot_of_bin, filter, d_count + 2);
   k_fill_bins<<<grid_for(n, 256), 256, 0, st>>>(keys_b, rid_c, kidx1, bin_start_idx, slot_of_bin, d_count + 1, d_count, n, bins, slot_of_read);
   c.launches += 6 + (2 + 4) + 2 + 3 + 2;  // ours + CUB (sort: histogram + 4 x onesweep, scans, select)
   SB_CUDA(cudaGetLastError());

@@ -381,7 +381,7 @@ __global__ void k_align_singletons(AlignArgs a) {
     if (!rev) key = cons_bits(a.cons2, j + d.start) & kmask;
     else key = ~(rev_groups(cons_bits(a.cons2, j + L - 1 - d.end) & kmask) >> (64 - 2 * nb)) & kmask;
     hk[kind] = mix64(key);
-    fw[kind] = __ldg(d.filter + filter_word(hk[kind], d.filter_shift));
+    fw[kind] = __ldg(d.filter + filter_word(hk[kind], d.filter_words));
   }
 #pragma unroll
   for (int kind = 0; kind < 4; kind++) {

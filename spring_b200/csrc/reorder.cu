@@ -315,7 +315,7 @@ __device__ __forceinline__ bool chain_search(const ChainArgs &a, const uint64_t 
       if (s >= s_lo && s < s_hi) {
         okm |= 1u << j;
         const uint64_t hk = mix64(window_key(src, kbase + kstep * s, d.key_bits));
-        if (filter_test_hint(d.filter, d.filter_shift, hk, pol_keep)) {
+        if (filter_test_hint(d.filter, d.filter_words, hk, pol_keep)) {
           cand |= 1u << j;
           if (a.prefetch_slots) asm volatile("prefetch.global.L2 [%0];" ::"l"(d.slots + slot_home(hk, d.slot_shift)));
         }

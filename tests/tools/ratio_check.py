@@ -19,7 +19,7 @@ if "--policy" in sys.argv:  # chain-count policies: reads per chain of the auto 
     runs = [("reference", po.REF_BIN, {})] + [(f"b200 {r} reads/chain", po.SPLICE2_BIN, {"SPRING_B200_READS_PER_CHAIN": str(r)})
                                               for r in (256, 2048, 6400)]
 for name, binary, env in runs:
-    out = os.path.join(d, name.replace(" ", "_") + ".spring")
+    out = os.path.join(d, name.replace(" ", "_").replace("/", "_per_") + ".spring")
     t0 = time.time()
     r = subprocess.run([binary, "-c", "-r", "--no-quality", "-i", fq, "-o", out, "-t", str(threads), "-w", d], capture_output=True, text=True, env={**os.environ, **env})
     wall = time.time() - t0

@@ -233,7 +233,7 @@ def main() -> None:
     ap.add_argument("--chains", type=int, default=0, help="0 = as many chains as co-reside")
     ap.add_argument("--cpu-sample", type=int, default=10_000_000, help="reads of the cpu_baseline sample")
     ap.add_argument("--ref-reads", type=int, default=0, help="--impl reference: reads to time (default: the whole N = 1 workload)")
-    ap.add_argument("--ref-budget-s", type=float, default=420.0, help="--impl reference: wall-clock budget for warm-ups + steps")
+    ap.add_argument("--ref-budget-s", type=float, default=300.0, help="--impl reference: wall-clock budget for warm-ups + steps")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-verify", action="store_true")
     ap.add_argument("--no-files-leg", action="store_true")

@@ -315,7 +315,7 @@ __device__ __forceinline__ bool chain_search(const ChainArgs &a, const uint64_t 
       if (s >= s_lo && s < s_hi) {
         okm |= 1u << j;
         const uint64_t hk = mix64(window_key(src, kbase + kstep * s, d.key_bits));
-        if (filter_test_hint(d.filter, d.filter_words, hk, pol_keep)) {
+        if (a.filter_hint ? filter_test_hint(d.filter, d.filter_words, hk, pol_keep) : filter_test(d.filter, d.filter_words, hk)) {
           cand |= 1u << j;
           if (a.prefetch_slots) asm volatile("prefetch.global.L2 [%0];" ::"l"(d.slots + slot_home(hk, d.slot_shift)));
         }
@@ -876,7 +876,8 @@ void run_reorder(Ctx &c, const uint64_t *reads, const uint16_t *lens, uint32_t n
   a.leader_mask = 0;
   for (uint32_t g = 0; g < a.G; g++) a.leader_mask |= 1u << (g * W);
   a.generic_update = getenv("SPRING_B200_GENERIC_UPDATE") ? 1 : 0;
-  a.prefetch_slots = getenv("SPRING_B200_PREFETCH") ? atoi(getenv("SPRING_B200_PREFETCH")) : 1;  // -1 to -2 % on configs 2 and 3
+  a.prefetch_slots = getenv("SPRING_B200_PREFETCH") ? atoi(getenv("SPRING_B200_PREFETCH")) : 1;
+  a.filter_hint = getenv("SPRING_B200_FILTER_HINT") ? atoi(getenv("SPRING_B200_FILTER_HINT")) : 1;  // L2 evict_last on the filter words  // -1 to -2 % on configs 2 and 3
   a.steal_probes = lockstep ? 0 : (getenv("SPRING_B200_STEAL") ? atoi(getenv("SPRING_B200_STEAL")) : 64);
   a.max_rounds = 8ull * n + 4096ull;
   SB_CUDA(cudaMemsetAsync(a.claimed, 0, bm_words * sizeof(uint32_t), st));

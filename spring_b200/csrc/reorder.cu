@@ -290,7 +290,7 @@ __device__ __forceinline__ bool scan_bin(const ChainArgs &a, const DictView &d, 
 // batch b = 0, 1, ...; a chain that finds nothing continues with the next batch in the next round
 // (bounded work per round keeps the lock-step chains balanced; claims only grow, so earlier batches
 // cannot turn productive later -- same result as a full search, see oracle/spring_oracle.c).
-template <int WT>
+template <int WT, bool FAST_TAIL>
 __device__ __forceinline__ bool chain_search(const ChainArgs &a, const uint64_t *ref, const uint64_t *revref, int ref_len, int lane, int grp,
                              int wig, int b, int S, uint32_t &prop_rid, int &prop_shift, int &prop_rev, uint32_t &probes_issued,
                              uint32_t &probes_seq, uint32_t &compares, uint32_t &slot_probes) {
@@ -306,7 +306,10 @@ __device__ __forceinline__ bool chain_search(const ChainArgs &a, const uint64_t 
   // bit position of the window key in src at shift s: kbase + ksign * 2s
   const int kbase = 2 * d.start, kstep = rev ? -2 : 2;
   {
-    const int n = b < 4 ? 1 << b : 16;  // 8, 16, 32, 64, then 128 shifts per batch
+    // probes per lane: the deterministic schedule keeps the oracle's rounds of 8, 16, 32, 64, then 128 shifts; a free-running
+    // chain goes 8, 16, then everything that is left (up to 128 shifts): 99 % of the matches sit below shift 24, so the
+    // third batch is almost always the last one of a dead end -- three round trips per dead end instead of four or five
+    const int n = FAST_TAIL ? (b < 2 ? 1 << b : 16) : (b < 4 ? 1 << b : 16);
     // ---- pass 1: bounds + filter bit for this lane's n probes (independent 4-byte loads) ----
     unsigned okm = 0, cand = 0;
 #pragma unroll 4
@@ -521,7 +524,7 @@ __global__ void __launch_bounds__(WPB * 32, MINB) k_chains(ChainArgs a) {
         if (!stop_searching) {
           int b = 0, S = 0;
           while (S < a.maxshift) {
-            if (chain_search<WT>(a, ref, revref, ref_len, lane, grp, wig, b, S, k, shift, prev_rev, c_issued, c_seq, c_cmp, c_slot)) {
+            if (chain_search<WT, true>(a, ref, revref, ref_len, lane, grp, wig, b, S, k, shift, prev_rev, c_issued, c_seq, c_cmp, c_slot)) {
               // the claim's round trip overlaps the loads the update will need (row, length, slot indices)
               unsigned old = 0;
               if (lane == 0) old = atomicOr(a.claimed + (k >> 5), 1u << (k & 31));
@@ -533,7 +536,7 @@ __global__ void __launch_bounds__(WPB * 32, MINB) k_chains(ChainArgs a) {
               c_lost++;  // another chain took it between the check and the claim: search this batch again
               continue;
             }
-            S += 8 * (b < 4 ? 1 << b : 16);
+            S += 8 * (b < 2 ? 1 << b : 16);
             b++;
           }
         }
@@ -650,7 +653,7 @@ __global__ void __launch_bounds__(WPB * 32, MINB) k_chains(ChainArgs a) {
         iter_started = 1;
       }
       if (!stop_searching) {
-        has_prop = chain_search<WT>(a, ref, revref, ref_len, lane, grp, wig, batch, batch_S, prop_rid, prop_shift, prop_rev, c_issued,
+        has_prop = chain_search<WT, false>(a, ref, revref, ref_len, lane, grp, wig, batch, batch_S, prop_rid, prop_shift, prop_rev, c_issued,
                                 c_seq, c_cmp, c_slot);
         if (!has_prop) {
           const int nshift = 8 * (batch < 4 ? 1 << batch : 16);

@@ -309,7 +309,8 @@ __device__ __forceinline__ bool chain_search(const ChainArgs &a, const uint64_t 
     // probes per lane: the deterministic schedule keeps the oracle's rounds of 8, 16, 32, 64, then 128 shifts; a free-running
     // chain goes 8, 16, then everything that is left (up to 128 shifts): 99 % of the matches sit below shift 24, so the
     // third batch is almost always the last one of a dead end -- three round trips per dead end instead of four or five
-    const int n = FAST_TAIL ? (b < 2 ? 1 << b : 16) : (b < 4 ? 1 << b : 16);
+    // (SPRING_B200_FAST_TAIL=1; off by default: measured slower together with the contig-start preload, visit 13)
+    const int n = (FAST_TAIL && a.fast_tail) ? (b < 2 ? 1 << b : 16) : (b < 4 ? 1 << b : 16);
     // ---- pass 1: bounds + filter bit for this lane's n probes (independent 4-byte loads) ----
     unsigned okm = 0, cand = 0;
 #pragma unroll 4
@@ -540,7 +541,7 @@ __global__ void __launch_bounds__(WPB * 32, MINB) k_chains(ChainArgs a) {
               c_lost++;  // another chain took it between the check and the claim: search this batch again
               continue;
             }
-            S += 8 * (b < 2 ? 1 << b : 16);
+            S += 8 * (a.fast_tail ? (b < 2 ? 1 << b : 16) : (b < 4 ? 1 << b : 16));
             b++;
           }
         }
@@ -894,6 +895,7 @@ void run_reorder(Ctx &c, const uint64_t *reads, const uint16_t *lens, uint32_t n
   for (uint32_t g = 0; g < a.G; g++) a.leader_mask |= 1u << (g * W);
   a.generic_update = getenv("SPRING_B200_GENERIC_UPDATE") ? 1 : 0;
   a.prefetch_slots = getenv("SPRING_B200_PREFETCH") ? atoi(getenv("SPRING_B200_PREFETCH")) : 1;
+  a.fast_tail = getenv("SPRING_B200_FAST_TAIL") ? atoi(getenv("SPRING_B200_FAST_TAIL")) : 0;
   a.filter_hint = getenv("SPRING_B200_FILTER_HINT") ? atoi(getenv("SPRING_B200_FILTER_HINT")) : 1;  // L2 evict_last on the filter words  // -1 to -2 % on configs 2 and 3
   a.steal_probes = lockstep ? 0 : (getenv("SPRING_B200_STEAL") ? atoi(getenv("SPRING_B200_STEAL")) : 64);
   a.max_rounds = 8ull * n + 4096ull;

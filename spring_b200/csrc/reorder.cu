@@ -406,9 +406,8 @@ __device__ bool find_unclaimed(const uint32_t *claimed, long long lo, long long 
 }
 
 // shared memory of one chain, in uint64 words: ref and revref (W words + one zero word each, so that
-// window_key may read one word past the bitset), the staged read, the contig's first read (for the left search),
-// Lp packed count columns
-__host__ __device__ inline size_t chain_smem_words(int W, int Lp) { return 4 * (size_t)W + 2 + (size_t)Lp; }
+// window_key may read one word past the bitset), the staged read, Lp packed count columns
+__host__ __device__ inline size_t chain_smem_words(int W, int Lp) { return 3 * (size_t)W + 2 + (size_t)Lp; }
 
 // WPB warps (= chains) per block, at least MINB blocks per SM: the register budget is the knob that
 // decides how many chains co-reside (run_reorder picks the configuration)
@@ -424,8 +423,7 @@ __global__ void __launch_bounds__(WPB * 32, MINB) k_chains(ChainArgs a) {
   const int grp = lane / W, wig = lane - grp * W;  // scan_bin's lane layout
   const size_t per_chain = chain_smem_words(W, Lp);
   uint64_t *ref = smem + wib * per_chain, *revref = ref + W + 1, *curw = revref + W + 1;
-  uint64_t *firstw = curw + W;   // the current contig's first read as stored (reorder.h:562-571 restarts from it)
-  uint64_t *cnt = firstw + W;    // one word per column: four u16 counts {A,C,T,G}
+  uint64_t *cnt = curw + W;  // one word per column: four u16 counts {A,C,T,G}
   if (lane == 0) { ref[W] = 0ull; revref[W] = 0ull; }
   __syncwarp();
 
@@ -433,7 +431,6 @@ __global__ void __launch_bounds__(WPB * 32, MINB) k_chains(ChainArgs a) {
   int ref_len = 0, prev_unmatched = 0, left_search = 0, iter_started = 0, stop_searching = 0, batch = 0, batch_S = 0;
   long long ref_pos = 0, cur_read_pos = 0;
   int cursor = -1, slice_lo = 0;  // read ids fit 31 bits (check_input)
-  int first_len = 0;
   uint32_t first_rid = 0, prev = 0, num_reads_thr = 0, num_unmatched_1m = 0, n_aligned = 0, n_single = 0;
   // statistics: c_issued / c_seq / c_slot are per-lane partial sums, c_cmp / c_unmatched / c_lost are
   // warp-uniform; 32-bit in registers, flushed to the 64-bit totals before they can wrap
@@ -471,15 +468,14 @@ __global__ void __launch_bounds__(WPB * 32, MINB) k_chains(ChainArgs a) {
     else update_ref_fast(ref, revref, curw, cnt, W, lane, old_len, delta, cs, cur_len, rev, new_len);
   };
   // the read must already be staged in curw
-  auto new_contig_len = [&](uint32_t rid, int len) {  // updaterefcount(..., resetcount = true, rev = false) + reorder.h:426-430,:601-612
-    if (lane < W) firstw[lane] = curw[lane];
+  auto new_contig = [&](uint32_t rid) {  // updaterefcount(..., resetcount = true, rev = false) + reorder.h:426-430,:601-612
+    const int len = __ldg(a.lens + rid);
     upd(0, 0, 0, len, false, len, 0);
-    ref_len = len; ref_pos = 0; cur_read_pos = 0; first_len = len;
+    ref_len = len; ref_pos = 0; cur_read_pos = 0;
     prev_unmatched = 1; first_rid = rid; prev = rid; left_search = 0;
     state = ST_SEARCH; iter_started = 0; batch = 0; batch_S = 0;
     flush_counters(false);
   };
-  auto new_contig = [&](uint32_t rid) { new_contig_len(rid, __ldg(a.lens + rid)); };
 
   if (state == ST_SEARCH) {  // reorder.h:405-431
     const uint32_t first = cid * a.per;
@@ -577,9 +573,8 @@ __global__ void __launch_bounds__(WPB * 32, MINB) k_chains(ChainArgs a) {
           num_unmatched_1m++;
           if (!left_search) {
             left_search = 1;
-            if (lane < W) curw[lane] = firstw[lane];  // the contig's first read, kept since new_contig: no reload
-            __syncwarp();
-            const int len = first_len;
+            stage_read(first_rid);
+            const int len = __ldg(a.lens + first_rid);
             upd(0, 0, 0, len, true, len, 0);
             ref_len = len; ref_pos = 0; cur_read_pos = 0;
             iter_started = 0;
@@ -589,20 +584,14 @@ __global__ void __launch_bounds__(WPB * 32, MINB) k_chains(ChainArgs a) {
           }
         }
       } else {  // ST_NEWREAD, reorder.h:576-612
-        uint32_t j = 0, nsidx = 0xFFFFFFFFu;
-        uint64_t nword = 0;
-        int nlen = 0;
-        bool got = false, preloaded = false;
+        uint32_t j = 0;
+        bool got = false;
         while (find_unclaimed(a.claimed, slice_lo, cursor, lane, j)) {
-          // the claim's round trip overlaps the loads the new contig needs (row, length, slot indices)
           unsigned old = 0;
           if (lane == 0) old = atomicOr(a.claimed + (j >> 5), 1u << (j & 31));
-          if (lane < W) nword = __ldg(a.reads + (size_t)j * W + lane);
-          nlen = __ldg(a.lens + j);
-          if (lane < kNumDict) nsidx = __ldg(a.dict[lane].slot_of_read + j);
           old = __shfl_sync(FULL, old, 0);
           cursor = (int)j - 1;
-          if (!((old >> (j & 31)) & 1u)) { got = true; preloaded = true; break; }
+          if (!((old >> (j & 31)) & 1u)) { got = true; break; }
         }
         // Own slice exhausted: instead of idling until the slowest chain is done, seed the next contig from
         // the slice of a randomly chosen other chain (the reference's threads all pick from ONE pool,
@@ -627,16 +616,13 @@ __global__ void __launch_bounds__(WPB * 32, MINB) k_chains(ChainArgs a) {
           n_single++;
         }
         if (got) {
-          if (!preloaded) {  // a stolen read
-            if (lane < W) nword = __ldg(a.reads + (size_t)j * W + lane);
-            nlen = __ldg(a.lens + j);
-            if (lane < kNumDict) nsidx = __ldg(a.dict[lane].slot_of_read + j);
+          if (lane < kNumDict) {
+            const uint32_t sidx = __ldg(a.dict[lane].slot_of_read + j);
+            if (sidx != 0xFFFFFFFFu) atomicSub(&a.dict[lane].slots[sidx].live, 1u);
           }
-          if (lane < kNumDict && nsidx != 0xFFFFFFFFu) atomicSub(&a.dict[lane].slots[nsidx].live, 1u);
           c_unmatched++;
-          if (lane < W) curw[lane] = nword;
-          __syncwarp();
-          new_contig_len(j, nlen);
+          stage_read(j);
+          new_contig(j);
         } else {
           prev_unmatched = 0;
           state = ST_DONE;

@@ -338,7 +338,9 @@ int spring_b200_write_merged(const char *temp_dir, const spring_b200_merged *m);
  * Reads the same files from temp_dir, block-distributes the reads over the GPUs, runs exchange -> reorder + encode ->
  * finalisation on every GPU, merges the shards (src/encoder.h:386-487) and writes the same output files, the consensus
  * cut into cp->num_thr pieces as in the single-GPU call -- so cp.bin and every later host stage stay as they are.
- * device_ids may be NULL (devices 0 .. num_gpus-1).  stats (may be NULL): GPU 0's, with the match counters summed. */
+ * device_ids may be NULL (devices 0 .. num_gpus-1).  stats (may be NULL): GPU 0's, with the match counters summed.
+ * Everything that can be checked is checked before the per-GPU threads start; a CUDA or NCCL failure on one GPU after
+ * that point leaves the others waiting in the exchange (as a failed rank does in any NCCL job). */
 int spring_b200_reorder_encode_files_multi(const char *temp_dir, const spring_b200_cp *cp, int num_gpus, const int *device_ids,
                                            uint32_t num_chains, spring_b200_stats *stats, char *err, size_t errlen);
 

@@ -9,6 +9,8 @@
 #include <atomic>
 #include <cstddef>
 #include <fstream>
+#include <memory>
+#include <mutex>
 #include <thread>
 #include "../../include/spring_b200.h"
 #include "kernels.cuh"
@@ -525,7 +527,9 @@ int spring_b200_create(int device, void *stream, spring_b200_ctx **out) {
 // and the streams left in HBM are shared between the stages.  Never destroyed explicitly (process exit releases it).
 int spring_b200_shared_ctx(int device, spring_b200_ctx **out) {
   static std::map<int, spring_b200_ctx *> shared;
+  static std::mutex mu;
   if (!out) return SPRING_B200_EINVAL;
+  std::lock_guard<std::mutex> lock(mu);
   auto it = shared.find(device);
   if (it != shared.end()) { *out = it->second; return SPRING_B200_OK; }
   const int rc = spring_b200_create(device, nullptr, out);
@@ -921,11 +925,12 @@ struct MergedOwner {
 int spring_b200_merge_shards(const spring_b200_streams *shards, int n, spring_b200_merged *out) {
   if (!shards || n < 1 || !out) return SPRING_B200_EINVAL;
   try {
-    auto *o = new MergedOwner();
+    std::unique_ptr<MergedOwner> owner(new MergedOwner());
+    MergedOwner *o = owner.get();
     uint64_t na = 0, nr = 0, nb = 0, nn = 0, ub = 0, ul = 0, sl = 0;
     for (int i = 0; i < n; i++) {
       const spring_b200_streams &s = shards[i];
-      if (s.num_aligned > s.num_reads || s.noise_bytes != s.num_noise + s.num_aligned) { delete o; return SPRING_B200_EINVAL; }
+      if (s.num_aligned > s.num_reads || s.noise_bytes != s.num_noise + s.num_aligned) return SPRING_B200_EINVAL;
       na += s.num_aligned; nr += s.num_reads; nb += s.noise_bytes; nn += s.num_noise; ub += s.unaligned_bytes; ul += s.unaligned_len;
       sl += s.seq_len;
       o->shard_seq.push_back(s.seq_packed); o->shard_seq_len.push_back(s.seq_len);
@@ -988,7 +993,7 @@ int spring_b200_merge_shards(const spring_b200_streams *shards, int n, spring_b2
     m.noisepos = o->noisepos.data(); m.num_noise = nn; m.rev = o->rev.data(); m.order = o->order.data(); m.lengths = o->lengths.data();
     m.unaligned = o->unaligned.data(); m.unaligned_bytes = ub; m.unaligned_len = ul; m.num_aligned = na; m.num_reads = nr;
     for (int i = 0; i < n; i++) { m.singletons_aligned += shards[i].singletons_aligned; m.n_reads_aligned += shards[i].n_reads_aligned; }
-    out->num_shards = n; out->shard_seq = o->shard_seq.data(); out->shard_seq_len = o->shard_seq_len.data(); out->owner = o;
+    out->num_shards = n; out->shard_seq = o->shard_seq.data(); out->shard_seq_len = o->shard_seq_len.data(); out->owner = owner.release();
     return SPRING_B200_OK;
   } catch (const std::exception &e) { g_create_err = e.what(); return SPRING_B200_ECUDA; }
 }

@@ -25,6 +25,7 @@ struct ChainArgs {
   unsigned leader_mask;  // scan_bin: lanes g * W, g < G
   int generic_update;    // debugging aid: always use the per-column update_ref
   int prefetch_slots;    // pass 1 of a batch prefetches the slot of every filter positive into L2
+  uint64_t pol_keep, pol_stream;  // L2 cache policies (evict_last for the filter words, evict_first for slot sectors)
   int fast_tail;         // free-running chains: batches of 8, 16, then all remaining shifts
   int filter_hint;       // filter words are loaded with the L2 evict_last policy (they should outlive the slot sectors)
   int steal_probes;      // free-running schedule: random slices an idle chain probes for an unclaimed read (0 = off)

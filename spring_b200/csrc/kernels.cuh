@@ -14,6 +14,7 @@ struct Ctx {
   uint64_t launches = 0;  // kernels launched since the last reset (ours + CUB passes)
   cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;  // around the chain kernel
   cudaEvent_t ev_x0 = nullptr, ev_x1 = nullptr;  // around the multi-GPU exchange
+  unsigned long long l2_policies[2] = {0, 0};  // createpolicy results (evict_last, evict_first), made once
   bool lockstep = false;  // chain schedule: deterministic round-synchronous, or free-running (default)
 };
 

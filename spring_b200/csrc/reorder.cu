@@ -298,7 +298,7 @@ __device__ __forceinline__ bool chain_search(const ChainArgs &a, const uint64_t 
   const int kind = lane & 3, rev = kind >> 1, sub = lane >> 2;
   const DictView &d = a.dict[kind & 1];
   const uint64_t *src = rev ? revref : ref;
-  const uint64_t pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
+  const uint64_t pol_keep = a.pol_keep, pol_stream = a.pol_stream;  // createpolicy results, made once on the host side's behalf
   // shifts this lane's probe kind may use: forward d.end + s < ref_len (reorder.h:264-265), reverse
   // d.end < ref_len + s and s < d.start (:266-267), all below maxshift
   const int s_lo = rev ? d.end - ref_len + 1 : 0;
@@ -309,7 +309,8 @@ __device__ __forceinline__ bool chain_search(const ChainArgs &a, const uint64_t 
     // probes per lane: the deterministic schedule keeps the oracle's rounds of 8, 16, 32, 64, then 128 shifts; a free-running
     // chain goes 8, 16, then everything that is left (up to 128 shifts): 99 % of the matches sit below shift 24, so the
     // third batch is almost always the last one of a dead end -- three round trips per dead end instead of four or five
-    // (SPRING_B200_FAST_TAIL=1; off by default: measured slower together with the contig-start preload, visit 13)
+    // (SPRING_B200_FAST_TAIL=0 restores the oracle's batches: -6.5 % kernel time on config 5's contig-start-heavy input, neutral
+    // on configs 2 and 3; profiles/r02_chains2_experiment.txt)
     const int n = (FAST_TAIL && a.fast_tail) ? (b < 2 ? 1 << b : 16) : (b < 4 ? 1 << b : 16);
     // ---- pass 1: bounds + filter bit for this lane's n probes (independent 4-byte loads) ----
     unsigned okm = 0, cand = 0;
@@ -507,7 +508,6 @@ __global__ void __launch_bounds__(WPB * 32, MINB) k_chains(ChainArgs a) {
     // the spot with an atomic test-and-set of its claim bit (the reference's remainingreads[] under
     // read_lock, reorder.h:303-309); losing that race just continues the search.  No grid barrier,
     // no proposals; the result depends on timing for more than one chain -- as the reference's does.
-    const long long t_begin = clock64();
     while (state != ST_DONE) {
       if (state == ST_SEARCH) {
         if (!iter_started) {  // loop top, reorder.h:433-439
@@ -630,7 +630,6 @@ __global__ void __launch_bounds__(WPB * 32, MINB) k_chains(ChainArgs a) {
       }
       round++;
     }
-    cy_search = clock64() - t_begin;
     if (lane == 0 && a.chain_dbg) {
       unsigned long long ns;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
@@ -770,6 +769,11 @@ __global__ void __launch_bounds__(WPB * 32, MINB) k_chains(ChainArgs a) {
   }
 }
 
+__global__ void k_make_policies(unsigned long long *out) {
+  out[0] = l2_policy_evict_last();
+  out[1] = l2_policy_evict_first();
+}
+
 // Chain logs -> one stream, chain after chain (what the merge of per-thread files gives,
 // encoder.h:386-423): record k of chain c lands at offset[c] + k.
 __global__ void k_scatter_records(const uint32_t *__restrict__ rec_chain, const uint32_t *__restrict__ rec_k,
@@ -881,7 +885,14 @@ void run_reorder(Ctx &c, const uint64_t *reads, const uint16_t *lens, uint32_t n
   for (uint32_t g = 0; g < a.G; g++) a.leader_mask |= 1u << (g * W);
   a.generic_update = getenv("SPRING_B200_GENERIC_UPDATE") ? 1 : 0;
   a.prefetch_slots = getenv("SPRING_B200_PREFETCH") ? atoi(getenv("SPRING_B200_PREFETCH")) : 1;
-  a.fast_tail = getenv("SPRING_B200_FAST_TAIL") ? atoi(getenv("SPRING_B200_FAST_TAIL")) : 0;
+  if (!c.l2_policies[0]) {  // createpolicy.fractional.L2::evict_last / evict_first, evaluated once per context
+    unsigned long long *d_pol = c.pool.dev<unsigned long long>("ro.l2pol", 2);
+    k_make_policies<<<1, 1, 0, st>>>(d_pol);
+    SB_CUDA(cudaMemcpyAsync(c.l2_policies, d_pol, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    SB_CUDA(cudaStreamSynchronize(st));
+  }
+  a.pol_keep = c.l2_policies[0]; a.pol_stream = c.l2_policies[1];
+  a.fast_tail = getenv("SPRING_B200_FAST_TAIL") ? atoi(getenv("SPRING_B200_FAST_TAIL")) : 1;
   a.filter_hint = getenv("SPRING_B200_FILTER_HINT") ? atoi(getenv("SPRING_B200_FILTER_HINT")) : 1;  // L2 evict_last on the filter words  // -1 to -2 % on configs 2 and 3
   a.steal_probes = lockstep ? 0 : (getenv("SPRING_B200_STEAL") ? atoi(getenv("SPRING_B200_STEAL")) : 64);
   a.max_rounds = 8ull * n + 4096ull;

@@ -4,13 +4,17 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from spring_b200 import capi, synth
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 10_000_000
-chains = int(sys.argv[2]) if len(sys.argv) > 2 else 0
-genome = int(sys.argv[3]) if len(sys.argv) > 3 else n * 150 // 30
+chains = int(sys.argv[2]) if len(sys.argv) > 2 and sys.argv[2].isdigit() else 0
+genome = int(sys.argv[3]) if len(sys.argv) > 3 and sys.argv[3].isdigit() else n * 150 // 30
 dev = torch.device("cuda", 0)
-rs = synth.generate(n, 150, genome_len=genome, seed=3, sub_rate=0.005, device=dev)
-d_reads = synth.pack_reads(rs.codes, rs.lengths, 150).contiguous(); d_lens = rs.lengths.to(torch.int16).contiguous(); del rs
+var = "var" in sys.argv  # config 5's shape: 35-250 bp reads, 46 % of them end a contig (contig-start dominated)
+L = 250 if var else 150
+if var and len(sys.argv) <= 3:
+    genome = int(n * 142.5 / 30)
+rs = synth.generate(n, L, genome_len=genome, seed=6 if var else 3, sub_rate=0.005, device=dev, var_len=(35, 250) if var else None)
+d_reads = synth.pack_reads(rs.codes, rs.lengths, L).contiguous(); d_lens = rs.lengths.to(torch.int16).contiguous(); del rs
 ctx = capi.Context(0, torch.cuda.current_stream().cuda_stream)
-inp = ctx.make_input(d_reads.data_ptr(), d_lens.data_ptr(), n, 150)
+inp = ctx.make_input(d_reads.data_ptr(), d_lens.data_ptr(), n, L)
 for it in range(3):
     ctx.reorder_encode_raw(inp, chains, device=True)
     st = ctx.stats()

@@ -145,6 +145,12 @@ int spring_b200_get_stats(const spring_b200_ctx *ctx, spring_b200_stats *out);
  * id wins / commit); the output is a pure function of (input, num_chains).  With num_chains = 1 both
  * reproduce the reference's single-thread result. */
 int spring_b200_set_schedule(spring_b200_ctx *ctx, int deterministic);
+/* Lookup / compare counters of the free-running schedule (spring_b200_stats: probes_issued, probes_seq, compares,
+ * slot_probes).  on = 0 (default): the production chain kernel, which leaves the counting out of its hot loops (the
+ * four fields read 0); on = 1: the counting instantiation -- what the roofline's algorithmic bytes are computed from
+ * (bench.py runs one counted pass outside the timed region).  The deterministic schedule always counts: its counters
+ * are part of the parity tests against the oracle's (src/reorder.h:262-311 counted the same way). */
+int spring_b200_set_chain_stats(spring_b200_ctx *ctx, int on);
 
 /* ---- the hot path ------------------------------------------------------------------------ */
 /* reorder_main + encoder_main (src/reorder.h:732-786, src/encoder.h:572-633) on HOST buffers:

@@ -51,7 +51,7 @@
 #define THRESH_ENCODER 24         /* params.h:35 */
 #define STOP_WINDOW 1000000u      /* reorder.h:433 */
 #define STOP_FRACTION 0.5         /* params.h:31 */
-#define MAX_LIST_SIZE 10000000u   /* encoder.h:215 */
+#define MAX_LIST_SIZE_DEFAULT 10000000u   /* encoder.h:215; SPRING_ORACLE_MAX_LIST lowers it so that tests reach it */
 
 /* ------------------------------------------------------------------------------------ */
 /* small helpers                                                                          */
@@ -714,6 +714,8 @@ int orc_encode(const uint64_t *reads, const uint16_t *lens, uint32_t N, int max_
   uint8_t *removed = (uint8_t *)xcalloc(n_sn ? n_sn : 1, 1); /* removed from dicts (lags `remaining` within a probe) */
 
   /* oriented strings of stream reads are produced lazily per contig */
+  uint64_t max_list_size = MAX_LIST_SIZE_DEFAULT;
+  { const char *e = getenv("SPRING_ORACLE_MAX_LIST"); if (e && atol(e) > 0) max_list_size = (uint64_t)atol(e); }
   contig_read *list = NULL; uint64_t list_n = 0, list_cap = 0;
   char *arena = NULL; size_t arena_n = 0, arena_cap = 0; /* strings owned by current contig */
   uint64_t seqno = 0, abs_pos = 0;
@@ -735,7 +737,7 @@ int orc_encode(const uint64_t *reads, const uint16_t *lens, uint32_t N, int max_
   char tmp[MAX_READ_LEN + 1], tmp2[MAX_READ_LEN + 1];
   for (uint64_t i = 0; i <= n_st; i++) {
     int done = (i == n_st);
-    if (done || st_flag[i] == 0 || list_n > MAX_LIST_SIZE) { /* encoder.h:215 */
+    if (done || st_flag[i] == 0 || list_n > max_list_size) { /* encoder.h:215 */
       if (list_n != 0) {
         qsort(list, list_n, sizeof(contig_read), cmp_contig_read); /* :221 */
         int64_t first_pos = list[0].pos;

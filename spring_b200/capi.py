@@ -19,7 +19,7 @@ EXPORTS = [
     "spring_b200_last_error", "spring_b200_get_stats", "spring_b200_reorder_encode",
     "spring_b200_reorder_encode_device", "spring_b200_fetch_streams", "spring_b200_build_dictionary",
     "spring_b200_reorder", "spring_b200_reorder_encode_files", "spring_b200_write_streams",
-    "spring_b200_bucket_reads", "spring_b200_set_schedule", "spring_b200_fetch_reorder", "spring_b200_set_stream",
+    "spring_b200_bucket_reads", "spring_b200_set_schedule", "spring_b200_set_chain_stats", "spring_b200_fetch_reorder", "spring_b200_set_stream",
     "spring_b200_pe_encode", "spring_b200_reblock_streams", "spring_b200_reblock_files", "spring_b200_pack_reads",
     "spring_b200_decode_blocks", "spring_b200_verify_roundtrip",
     "spring_b200_comm_unique_id", "spring_b200_comm_init", "spring_b200_comm_free", "spring_b200_exchange_reads",
@@ -251,6 +251,11 @@ class Context:
         """True: round-synchronous chains (reproducible output); False (default): free-running chains."""
         self._lib.spring_b200_set_schedule.argtypes = [C.c_void_p, C.c_int]
         self._check(self._lib.spring_b200_set_schedule(self._h, 1 if deterministic else 0))
+
+    def set_chain_stats(self, on: bool) -> None:
+        """True: the free-running chain kernel also counts lookups / compares (probes_seq, compares, ... in stats())."""
+        self._lib.spring_b200_set_chain_stats.argtypes = [C.c_void_p, C.c_int]
+        self._check(self._lib.spring_b200_set_chain_stats(self._h, 1 if on else 0))
 
     def stats(self) -> dict:
         s = Stats()

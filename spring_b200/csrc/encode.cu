@@ -117,6 +117,20 @@ __global__ void k_heads(const uint8_t *__restrict__ flag, uint32_t m, uint32_t *
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < m) head[i] = flag[i] == 0 ? 1u : 0u;
 }
+// encoder.h:215: the reference flushes its read list once it holds more than 10 000 000 reads, so a longer contig is
+// written as pieces of 10 000 001 stream records, each sorted and voted on its own.  start[i] = stream index of the
+// head of record i's contig (inclusive max scan of "head ? i : 0"); every `piece`-th record after it opens a new piece.
+__global__ void k_head_index(const uint32_t *__restrict__ head, uint32_t m, uint32_t *start) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < m) start[i] = head[i] ? i : 0u;
+}
+__global__ void k_split_heads(const uint32_t *__restrict__ start, uint32_t m, uint32_t piece, uint32_t *head) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < m && (i - start[i]) % piece == 0) head[i] = 1u;
+}
+struct MaxU32 {
+  __device__ __forceinline__ uint32_t operator()(uint32_t a, uint32_t b) const { return a > b ? a : b; }
+};
 
 // per contig min(pos), max(pos+len): warp-segmented reduction, one atomic per (warp, contig)
 __global__ void k_contig_bounds(const uint32_t *__restrict__ cidx1, const int64_t *__restrict__ pos,
@@ -622,6 +636,18 @@ void run_encode(Ctx &c, const uint64_t *reads, const uint16_t *lens, uint32_t n,
     uint32_t *head = c.pool.dev<uint32_t>("en.head", Mn);
     k_heads<<<grid_for(M, 256), 256, 0, st>>>(ro.flag, M, head);
     size_t need = 0;
+    // contigs of more than 10 000 001 reads are cut like the reference cuts them (encoder.h:215); SPRING_B200_CONTIG_SPLIT
+    // lowers the limit so that the tests reach it
+    const char *split_env = getenv("SPRING_B200_CONTIG_SPLIT");
+    const uint32_t kMaxList = split_env && atol(split_env) > 0 ? (uint32_t)atol(split_env) : 10000000u;
+    if ((uint64_t)M > (uint64_t)kMaxList + 1) {
+      uint32_t *cs = c.pool.dev<uint32_t>("en.contig_head", Mn);
+      k_head_index<<<grid_for(M, 256), 256, 0, st>>>(head, M, cs);
+      cub::DeviceScan::InclusiveScan(nullptr, need, cs, cs, MaxU32(), (int)M, st); cub_need(need);
+      need = cub_bytes; cub::DeviceScan::InclusiveScan(cub_tmp, need, cs, cs, MaxU32(), (int)M, st);
+      k_split_heads<<<grid_for(M, 256), 256, 0, st>>>(cs, M, kMaxList + 1, head);
+      c.launches += 3;
+    }
     cub::DeviceScan::InclusiveSum(nullptr, need, head, cidx1, (int)M, st); cub_need(need);
     need = cub_bytes; cub::DeviceScan::InclusiveSum(cub_tmp, need, head, cidx1, (int)M, st);
     c.launches += 2;

@@ -16,6 +16,7 @@ struct Ctx {
   cudaEvent_t ev_x0 = nullptr, ev_x1 = nullptr;  // around the multi-GPU exchange
   unsigned long long l2_policies[2] = {0, 0};  // createpolicy results (evict_last, evict_first), made once
   bool lockstep = false;  // chain schedule: deterministic round-synchronous, or free-running (default)
+  bool chain_stats = false;  // free-running chains also count lookups / compares (spring_b200_set_chain_stats; the deterministic schedule always does)
 };
 
 // ---- dict.cu : constructdictionary (bitset_util.h:74-221) ---------------------------------------
@@ -59,7 +60,7 @@ struct EncodeDev {
   uint64_t num_aligned = 0, num_reads = 0;
   uint32_t singletons_aligned = 0, n_reads_aligned = 0;
 };
-struct NReads {  // reads with N, parsed from input_N.dna on the host and uploaded
+struct NReads {  // reads with N: input_N.dna records uploaded as they are and unpacked by k_unpack_n
   const uint64_t *codes = nullptr;  // [num][W] 2-bit, N stored as 00
   const uint64_t *nflag = nullptr;  // [num][W] bit 2j set where base j is N
   const uint16_t *lens = nullptr;
@@ -111,6 +112,9 @@ struct PackDev {
 };
 // d_bases: the reads' sequence lines concatenated, file 1 then file 2; d_offsets[n + 1]: start of read i
 void run_pack_reads(Ctx &c, const uint8_t *d_bases, const unsigned long long *d_offsets, uint32_t n, uint32_t n_file1, PackDev &out);
+// input_N.dna records (device) at the given byte offsets -> 2-bit rows + N bit-plane + lengths (readsingletons' N half, encoder.h:556-567)
+void run_unpack_n(Ctx &c, const uint8_t *d_records, const unsigned long long *d_offsets, uint32_t nn, int W, uint64_t *codes,
+                  uint64_t *nflag, uint16_t *lens);
 
 // ---- exchange.cu : the multi-GPU exchange and the shard finalisation -------------------------------
 struct Comm;  // NCCL communicator of one rank (opaque; NCCL is dlopen'ed on first use)

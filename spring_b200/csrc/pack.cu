@@ -90,6 +90,30 @@ __global__ void k_pack_n(const uint8_t *__restrict__ bases, const unsigned long 
   order_n[n_rank[i]] = i;  // preprocess.cpp:300-301: original index, file 2 after file 1
 }
 
+
+// input_N.dna records {u16 len; ceil(len / 2) bytes, 4 bits per base A0 G1 C2 T3 N4} (util.cpp:322-374) -> the 2-bit
+// rows (N stored as 00) + N bit-plane the encoder's pool keeps: thread per (read, word of 32 bases).  The record
+// offsets come from the host (one hop per record over the length fields; the per-base work is here).
+__global__ void k_unpack_n(const uint8_t *__restrict__ rec, const unsigned long long *__restrict__ off, uint32_t nn, int W,
+                           uint64_t *__restrict__ codes, uint64_t *__restrict__ nflag, uint16_t *__restrict__ lens) {
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (uint64_t)nn * W) return;
+  const uint32_t i = (uint32_t)(t / W);
+  const int w = (int)(t - (uint64_t)i * W);
+  const uint8_t *r = rec + off[i];
+  const int len = (int)r[0] | ((int)r[1] << 8);
+  if (w == 0) lens[i] = (uint16_t)len;
+  uint64_t c = 0, f = 0;
+  const int j0 = 32 * w, j1 = min(len, j0 + 32);
+  for (int j = j0; j < j1; j += 2) {  // j0 is even: one byte = bases j, j + 1
+    const uint32_t b = r[2 + (j >> 1)];
+    const uint32_t v0 = b & 15u, v1 = b >> 4;
+    const int sh = 2 * (j - j0);
+    if (v0 >= 4) f |= 1ull << sh; else c |= (uint64_t)v0 << sh;
+    if (j + 1 < j1) { if (v1 >= 4) f |= 1ull << (sh + 2); else c |= (uint64_t)v1 << (sh + 2); }
+  }
+  codes[t] = c; nflag[t] = f;
+}
 }  // namespace
 
 void run_pack_reads(Ctx &c, const uint8_t *d_bases, const unsigned long long *d_offsets, uint32_t n, uint32_t n_file1, PackDev &out) {
@@ -136,6 +160,14 @@ void run_pack_reads(Ctx &c, const uint8_t *d_bases, const unsigned long long *d_
     k_pack_n<<<grid_for(n, 128), 128, 0, st>>>(d_bases, d_offsets, is_n, n_rank, nrec_off, n, out.n_records, out.order_n);
     c.launches += 2;
   }
+  SB_CUDA(cudaGetLastError());
+}
+
+void run_unpack_n(Ctx &c, const uint8_t *d_records, const unsigned long long *d_offsets, uint32_t nn, int W, uint64_t *codes,
+                  uint64_t *nflag, uint16_t *lens) {
+  if (!nn) return;
+  k_unpack_n<<<grid_for((uint64_t)nn * W, 256), 256, 0, c.stream>>>(d_records, d_offsets, nn, W, codes, nflag, lens);
+  c.launches++;
   SB_CUDA(cudaGetLastError());
 }
 

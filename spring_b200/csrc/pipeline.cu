@@ -77,43 +77,36 @@ void check_input(const spring_b200_input *in) {
   if (in->num_reads > (1u << 30)) throw ArgError("too many reads for one GPU shard (> 2^30)");
 }
 
-// input_N.dna records (util.cpp:322-374) -> 2-bit codes (N as 00) + N bit-plane, uploaded
+// input_N.dna records (util.cpp:322-374) -> 2-bit codes (N as 00) + N bit-plane.  The host only hops over the length
+// fields (record i starts where record i - 1 ends) and checks them; the records travel as they are and are unpacked on
+// the GPU (k_unpack_n) -- the per-base host loop this replaces was 47 ms of every 100 M-read pass (200 k reads with N).
 NReads upload_n_reads(Ctx &c, const spring_b200_input *in, int W) {
   NReads nr{};
   nr.num = in->num_n;
   if (!in->num_n) return nr;
   const uint32_t nn = in->num_n;
-  uint64_t *h_codes = c.pool.pin<uint64_t>("n.h_codes", (size_t)nn * W);
-  uint64_t *h_flag = c.pool.pin<uint64_t>("n.h_flag", (size_t)nn * W);
-  uint16_t *h_len = c.pool.pin<uint16_t>("n.h_len", nn);
-  uint32_t *h_order = c.pool.pin<uint32_t>("n.h_order", nn);
-  memset(h_codes, 0, sizeof(uint64_t) * (size_t)nn * W);
-  memset(h_flag, 0, sizeof(uint64_t) * (size_t)nn * W);
+  unsigned long long *h_off = c.pool.pin<unsigned long long>("n.h_off", nn);
   uint64_t off = 0;
   for (uint32_t i = 0; i < nn; i++) {
     if (off + 2 > in->n_record_bytes) throw ArgError("input_N.dna truncated");
-    uint16_t len; memcpy(&len, in->n_records + off, 2); off += 2;
+    uint16_t len; memcpy(&len, in->n_records + off, 2);
     if (len > in->max_readlen) throw ArgError("N read longer than max_readlen");
     const uint64_t nb = ((uint64_t)len + 1) / 2;
-    if (off + nb > in->n_record_bytes) throw ArgError("input_N.dna truncated");
-    for (int j = 0; j < len; j++) {
-      const int v = (in->n_records[off + j / 2] >> (4 * (j & 1))) & 15;
-      if (v >= 4) h_flag[(size_t)i * W + (j >> 5)] |= 1ull << (2 * (j & 31));
-      else h_codes[(size_t)i * W + (j >> 5)] |= (uint64_t)v << (2 * (j & 31));
-    }
-    off += nb;
-    h_len[i] = len;
-    h_order[i] = in->order_n[i];
-    if (i && h_order[i] <= h_order[i - 1]) throw ArgError("read_order_N.bin must be strictly ascending");
+    if (off + 2 + nb > in->n_record_bytes) throw ArgError("input_N.dna truncated");
+    h_off[i] = off;
+    off += 2 + nb;
+    if (i && in->order_n[i] <= in->order_n[i - 1]) throw ArgError("read_order_N.bin must be strictly ascending");
   }
+  uint8_t *d_rec = c.pool.dev<uint8_t>("n.rec", off + 1);
+  unsigned long long *d_off = c.pool.dev<unsigned long long>("n.off", nn);
   uint64_t *d_codes = c.pool.dev<uint64_t>("n.codes", (size_t)nn * W);
   uint64_t *d_flag = c.pool.dev<uint64_t>("n.flag", (size_t)nn * W);
   uint16_t *d_len = c.pool.dev<uint16_t>("n.len", nn);
   uint32_t *d_order = c.pool.dev<uint32_t>("n.order", nn);
-  SB_CUDA(cudaMemcpyAsync(d_codes, h_codes, sizeof(uint64_t) * (size_t)nn * W, cudaMemcpyHostToDevice, c.stream));
-  SB_CUDA(cudaMemcpyAsync(d_flag, h_flag, sizeof(uint64_t) * (size_t)nn * W, cudaMemcpyHostToDevice, c.stream));
-  SB_CUDA(cudaMemcpyAsync(d_len, h_len, sizeof(uint16_t) * nn, cudaMemcpyHostToDevice, c.stream));
-  SB_CUDA(cudaMemcpyAsync(d_order, h_order, sizeof(uint32_t) * nn, cudaMemcpyHostToDevice, c.stream));
+  SB_CUDA(cudaMemcpyAsync(d_rec, in->n_records, off, cudaMemcpyHostToDevice, c.stream));
+  SB_CUDA(cudaMemcpyAsync(d_off, h_off, sizeof(unsigned long long) * nn, cudaMemcpyHostToDevice, c.stream));
+  SB_CUDA(cudaMemcpyAsync(d_order, in->order_n, sizeof(uint32_t) * nn, cudaMemcpyHostToDevice, c.stream));
+  run_unpack_n(c, d_rec, d_off, nn, W, d_codes, d_flag, d_len);
   nr.codes = d_codes; nr.nflag = d_flag; nr.lens = d_len; nr.order = d_order;
   return nr;
 }
@@ -513,6 +506,7 @@ int spring_b200_create(int device, void *stream, spring_b200_ctx **out) {
     if (stream) { ctx->c.stream = (cudaStream_t)stream; ctx->c.own_stream = false; }
     else { SB_CUDA(cudaStreamCreateWithFlags(&ctx->c.stream, cudaStreamNonBlocking)); ctx->c.own_stream = true; }
     for (auto &e : ctx->ev) SB_CUDA(cudaEventCreate(&e));
+    if (const char *e = getenv("SPRING_B200_CHAIN_STATS")) ctx->c.chain_stats = atoi(e) != 0;  // tools: counters without an API call
   } catch (const std::exception &e) {
     g_create_err = e.what();
     delete ctx;
@@ -571,6 +565,12 @@ int spring_b200_set_stream(spring_b200_ctx *ctx, void *stream) {
 int spring_b200_set_schedule(spring_b200_ctx *ctx, int deterministic) {
   if (!ctx) return SPRING_B200_EINVAL;
   ctx->c.lockstep = deterministic != 0;
+  return SPRING_B200_OK;
+}
+
+int spring_b200_set_chain_stats(spring_b200_ctx *ctx, int on) {
+  if (!ctx) return SPRING_B200_EINVAL;
+  ctx->c.chain_stats = on != 0;
   return SPRING_B200_OK;
 }
 

@@ -208,7 +208,7 @@ __device__ void update_ref_fast(uint64_t *ref, uint64_t *revref, uint64_t *curw,
 // XOR / mask / popcount per lane, a W-lane segmented sum.  (A lane per candidate would spend W times the
 // instructions on the one or two candidates a typical bin holds.)  The shifted reference word is the
 // same for every candidate of the scan and is computed once.
-template <int WT>
+template <int WT, bool STATS>
 __device__ __forceinline__ bool scan_bin(const ChainArgs &a, const DictView &d, uint32_t bs, uint32_t bc, uint32_t r0, uint32_t r1, uint32_t r2,
                          const uint64_t *refsm, bool rev, int s, int ref_len, int lane, int grp, int wig, uint32_t &rid_out,
                          uint32_t &compares) {
@@ -266,10 +266,10 @@ __device__ __forceinline__ bool scan_bin(const ChainArgs &a, const DictView &d, 
     if (pm) {
       const int wl = __ffs(pm) - 1;
       rid_out = __shfl_sync(FULL, rid, wl);
-      compares += __popc(em & ((2u << wl) - 1u));
+      if (STATS) compares += __popc(em & ((2u << wl) - 1u));
       return true;
     }
-    compares += __popc(em);
+    if (STATS) compares += __popc(em);
     live_before += __popc(lm);
     if (live_before >= kMaxSearch) break;
   }
@@ -290,7 +290,7 @@ __device__ __forceinline__ bool scan_bin(const ChainArgs &a, const DictView &d, 
 // batch b = 0, 1, ...; a chain that finds nothing continues with the next batch in the next round
 // (bounded work per round keeps the lock-step chains balanced; claims only grow, so earlier batches
 // cannot turn productive later -- same result as a full search, see oracle/spring_oracle.c).
-template <int WT, bool FAST_TAIL>
+template <int WT, bool FAST_TAIL, bool STATS>
 __device__ __forceinline__ bool chain_search(const ChainArgs &a, const uint64_t *ref, const uint64_t *revref, int ref_len, int lane, int grp,
                              int wig, int b, int S, uint32_t &prop_rid, int &prop_shift, int &prop_rev, uint32_t &probes_issued,
                              uint32_t &probes_seq, uint32_t &compares, uint32_t &slot_probes) {
@@ -326,7 +326,7 @@ __device__ __forceinline__ bool chain_search(const ChainArgs &a, const uint64_t 
         }
       }
     }
-    probes_issued += (unsigned)__popc(okm);  // per-lane partial sum, reduced when the chain ends
+    if (STATS) probes_issued += (unsigned)__popc(okm);  // per-lane partial sum, reduced when the chain ends
     // ---- pass 2: resolve hits in priority order ----------------------------------------------------
     int cur_j = -1, found_p = -1;
     uint32_t cur_start1 = 0, cur_count = 0, cur_r0 = 0, cur_r1 = 0, cur_r2 = 0;
@@ -337,7 +337,7 @@ __device__ __forceinline__ bool chain_search(const ChainArgs &a, const uint64_t 
         const int s = S + sub + 8 * j;
         const uint64_t hk = mix64(window_key(src, kbase + kstep * s, d.key_bits));
         uint32_t h = slot_home(hk, d.slot_shift);
-        slot_probes++;
+        if (STATS) slot_probes++;
         for (;;) {  // ordered probing: every key between the home slot and hk's own slot is smaller than hk
           const DictSlot sl = load_slot_hint(d.slots + h, pol_stream);
           if (sl.start1 == 0 || sl.key > hk) break;
@@ -359,7 +359,7 @@ __device__ __forceinline__ bool chain_search(const ChainArgs &a, const uint64_t 
       const uint32_t r0 = __shfl_sync(FULL, cur_r0, owner), r1 = __shfl_sync(FULL, cur_r1, owner), r2 = __shfl_sync(FULL, cur_r2, owner);
       const DictView &pd = a.dict[pk & 1];
       uint32_t rid;
-      if (scan_bin<WT>(a, pd, mb, mc, r0, r1, r2, (pk >> 1) ? revref : ref, pk >> 1, ps, ref_len, lane, grp, wig, rid, compares)) {
+      if (scan_bin<WT, STATS>(a, pd, mb, mc, r0, r1, r2, (pk >> 1) ? revref : ref, pk >> 1, ps, ref_len, lane, grp, wig, rid, compares)) {
         prop_rid = rid; prop_shift = ps; prop_rev = pk >> 1; found_p = p;
         break;
       }
@@ -367,7 +367,7 @@ __device__ __forceinline__ bool chain_search(const ChainArgs &a, const uint64_t 
     }
     // lookups a sequential search would have issued: all of this batch, or those up to the hit
     unsigned seqmask = okm;
-    if (found_p >= 0) {
+    if (STATS && found_p >= 0) {
       const int fs = found_p >> 2, fk = found_p & 3;
       const int rel = fs - S - sub;  // this lane's shifts <= fs are j <= rel / 8
       if (rel < 0) seqmask = 0;
@@ -377,7 +377,7 @@ __device__ __forceinline__ bool chain_search(const ChainArgs &a, const uint64_t 
         seqmask = jm < 0 ? 0u : (jm >= 31 ? seqmask : seqmask & ((2u << jm) - 1u));
       }
     }
-    probes_seq += (unsigned)__popc(seqmask);
+    if (STATS) probes_seq += (unsigned)__popc(seqmask);
     if (found_p >= 0) return true;
   }
   return false;
@@ -414,7 +414,9 @@ __host__ __device__ inline size_t chain_smem_words(int W, int Lp) { return 3 * (
 // decides how many chains co-reside (run_reorder picks the configuration)
 // WT > 0: specialised for reads of WT words (W = 5: up to 160 bases, W = 8: up to 256) -- every row address, lane / W
 // split, per-chain shared-memory offset and loop bound becomes a constant; WT = 0: any length, from the arguments
-template <bool LOCKSTEP, int WPB, int MINB, int WT>
+// STATS: count the dictionary lookups / Hamming evaluations the oracle counts (parity tests, the roofline's
+// algorithmic bytes); the production instantiation leaves the counting out of the hot loops
+template <bool LOCKSTEP, int WPB, int MINB, int WT, bool STATS = true>
 __global__ void __launch_bounds__(WPB * 32, MINB) k_chains(ChainArgs a) {
   constexpr int kWarpsPerBlock = WPB;
   extern __shared__ __align__(16) uint64_t smem[];
@@ -438,6 +440,7 @@ __global__ void __launch_bounds__(WPB * 32, MINB) k_chains(ChainArgs a) {
   uint32_t c_unmatched = 0, c_lost = 0, c_issued = 0, c_seq = 0, c_cmp = 0, c_slot = 0;
   unsigned long long target = 0, round = 0;
   auto flush_counters = [&](bool force) {
+    if (!STATS && !force) return;  // only c_lost is counted: one increment per lost claim, flushed at the end
     if (!force && !__any_sync(FULL, (c_issued | c_seq | c_slot | c_cmp | c_lost) >> 30)) return;
     auto wsum = [&](uint32_t v) {  // exact 64-bit warp sum of 32-bit lane values
       return (unsigned long long)__reduce_add_sync(FULL, v & 0xFFFFu) + ((unsigned long long)__reduce_add_sync(FULL, v >> 16) << 16);
@@ -525,7 +528,7 @@ __global__ void __launch_bounds__(WPB * 32, MINB) k_chains(ChainArgs a) {
         if (!stop_searching) {
           int b = 0, S = 0;
           while (S < a.maxshift) {
-            if (chain_search<WT, true>(a, ref, revref, ref_len, lane, grp, wig, b, S, k, shift, prev_rev, c_issued, c_seq, c_cmp, c_slot)) {
+            if (chain_search<WT, true, STATS>(a, ref, revref, ref_len, lane, grp, wig, b, S, k, shift, prev_rev, c_issued, c_seq, c_cmp, c_slot)) {
               // the claim's round trip overlaps the loads the update will need (row, length, slot indices)
               unsigned old = 0;
               if (lane == 0) old = atomicOr(a.claimed + (k >> 5), 1u << (k & 31));
@@ -653,7 +656,7 @@ __global__ void __launch_bounds__(WPB * 32, MINB) k_chains(ChainArgs a) {
         iter_started = 1;
       }
       if (!stop_searching) {
-        has_prop = chain_search<WT, false>(a, ref, revref, ref_len, lane, grp, wig, batch, batch_S, prop_rid, prop_shift, prop_rev, c_issued,
+        has_prop = chain_search<WT, false, true>(a, ref, revref, ref_len, lane, grp, wig, batch, batch_S, prop_rid, prop_shift, prop_rev, c_issued,
                                 c_seq, c_cmp, c_slot);
         if (!has_prop) {
           const int nshift = 8 * (batch < 4 ? 1 << batch : 16);
@@ -822,10 +825,11 @@ void run_reorder(Ctx &c, const uint64_t *reads, const uint16_t *lens, uint32_t n
     const bool generic_w = getenv("SPRING_B200_GENERIC_W") != nullptr;  // A/B: the any-length instantiation
     if (want == "8x4") {
       kWarpsPerBlock = 8;
-      if (W == 5 && !generic_w) kern = k_chains<false, 8, 4, 5>;       // 129..160 bases (150 bp reads)
-      else if (W == 8 && !generic_w) kern = k_chains<false, 8, 4, 8>;  // 225..256 bases (250 bp reads)
-      else if (W == 4 && !generic_w) kern = k_chains<false, 8, 4, 4>;  // 97..128 bases (100 / 125 bp reads)
-      else kern = k_chains<false, 8, 4, 0>;
+      const bool stats = c.chain_stats;
+      if (W == 5 && !generic_w) kern = stats ? k_chains<false, 8, 4, 5> : k_chains<false, 8, 4, 5, false>;       // 129..160 bases (150 bp reads)
+      else if (W == 8 && !generic_w) kern = stats ? k_chains<false, 8, 4, 8> : k_chains<false, 8, 4, 8, false>;  // 225..256 bases (250 bp reads)
+      else if (W == 4 && !generic_w) kern = stats ? k_chains<false, 8, 4, 4> : k_chains<false, 8, 4, 4, false>;  // 97..128 bases (100 / 125 bp reads)
+      else kern = stats ? k_chains<false, 8, 4, 0> : k_chains<false, 8, 4, 0, false>;
     }
     else if (want == "8x5") { kern = k_chains<false, 8, 5, 0>; kWarpsPerBlock = 8; }
     else if (want == "8x6") { kern = k_chains<false, 8, 6, 0>; kWarpsPerBlock = 8; }

@@ -140,6 +140,24 @@ def test_free_running_schedule(ctx, name):
         check_roundtrip(got, hp, po.decode)
 
 
+@pytest.mark.parametrize("name", ["se150", "dups", "pe100_illumina"])
+def test_long_contigs_are_cut_like_the_reference(ctx, name, monkeypatch):
+    """encoder.h:215: a contig whose read list grows beyond 10 000 000 reads is written in pieces of 10 000 001 stream
+    records.  With the limit lowered on both sides (SPRING_B200_CONTIG_SPLIT / SPRING_ORACLE_MAX_LIST = 7) most contigs
+    are cut: the streams must still equal the oracle's bit for bit and decode to the input."""
+    monkeypatch.setenv("SPRING_B200_CONTIG_SPLIT", "7")
+    monkeypatch.setenv("SPRING_ORACLE_MAX_LIST", "7")
+    hp = make_input(**CASES[name])
+    got = ctx.reorder_encode(hp.packed, hp.lengths, hp.max_readlen, hp.n_records, hp.order_n, hp.num_reads, 1)
+    _, er = po.reorder_encode(hp.packed, hp.lengths, hp.max_readlen, hp.n_records, hp.order_n, hp.num_reads, 1)
+    assert_streams_equal(got, er, f"{name}, contigs cut every 8 reads")
+    check_roundtrip(got, hp, po.decode)
+    monkeypatch.delenv("SPRING_B200_CONTIG_SPLIT")
+    monkeypatch.delenv("SPRING_ORACLE_MAX_LIST")
+    whole = ctx.reorder_encode(hp.packed, hp.lengths, hp.max_readlen, hp.n_records, hp.order_n, hp.num_reads, 1)
+    assert whole.seq_len < got.seq_len  # the cut really happened: pieces repeat consensus the whole contig shares
+
+
 def test_auto_chains_roundtrip_and_determinism(det):
     """Default chain count (as many as co-reside), deterministic schedule: decode == input, and two
     runs are identical."""

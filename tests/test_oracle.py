@@ -78,3 +78,14 @@ def test_empty_and_tiny_inputs():
     nrec = dnaio.write_dnaN_records([b"ACGNNACGT", b"NNNN"])
     ro, er = po.reorder_encode(np.zeros((0, 1), np.uint64), np.zeros(0, np.uint16), 9, nrec, np.array([0, 1], np.uint32), 2)
     assert po.decode(er) == [b"ACGNNACGT", b"NNNN"]
+
+
+def test_cut_contigs_still_decode(monkeypatch):
+    """encoder.h:215 cuts a contig after 10 000 001 reads; with the oracle's limit lowered the pieces are real and the
+    streams must still decode to the input (the GPU test compares the CUDA path with this setting bit for bit)."""
+    hp = make_input(**CASES["se150"])
+    _, whole = po.reorder_encode(hp.packed, hp.lengths, hp.max_readlen, hp.n_records, hp.order_n, hp.num_reads, 1)
+    monkeypatch.setenv("SPRING_ORACLE_MAX_LIST", "7")
+    _, cut = po.reorder_encode(hp.packed, hp.lengths, hp.max_readlen, hp.n_records, hp.order_n, hp.num_reads, 1)
+    assert len(cut.seq) > len(whole.seq)
+    check_roundtrip(cut, hp, po.decode)

@@ -274,6 +274,13 @@ typedef struct spring_b200_packed_reads {
 } spring_b200_packed_reads;
 int spring_b200_pack_reads(spring_b200_ctx *ctx, const uint8_t *bases, const uint64_t *offsets, uint32_t num_reads,
                            uint32_t num_reads_file1, int keep_on_device, spring_b200_packed_reads *out);
+/* call_reorder + call_encoder's stream generation (as spring_b200_reorder_encode_files: same output files in temp_dir,
+ * same use of cp) on the reads the last spring_b200_pack_reads(keep_on_device != 0) of this context left in HBM -- what
+ * a preprocess that packs on the GPU hands over instead of input_clean_{1,2}.dna, input_N.dna and read_order_N.bin
+ * (src/preprocess.cpp:293-304 -> src/reorder.h:222-244 without the files in between).  cp must describe those reads
+ * (num_reads, num_reads_clean[2], max_readlen).  spring_b200_packed_pending: 1 while such reads wait to be consumed. */
+int spring_b200_packed_pending(const spring_b200_ctx *ctx);
+int spring_b200_reorder_encode_packed(spring_b200_ctx *ctx, const char *temp_dir, const spring_b200_cp *cp, uint32_t num_chains);
 
 /* ---- multi-GPU partitioning ------------------------------------------------------------------ */
 /* DEVICE pointers.  bucket[i] = hash(strand-canonical 16-mer minimizer of read i) mod num_buckets:

@@ -17,6 +17,7 @@ LIB_PATH = os.path.join(HERE, "liboracle.so")
 REF_BIN = os.path.join(HERE, "_ref", "spring_ref")
 SPLICE_BIN = os.path.join(HERE, "_ref", "spring_b200_ref")
 SPLICE2_BIN = os.path.join(HERE, "_ref", "spring_b200_ref2")  # + pe_encode / reorder_compress_streams on the GPU
+SPLICE3_BIN = os.path.join(HERE, "_ref", "spring_b200_ref3")  # + preprocess's read path and decompress_short's block decode on the GPU
 REFERENCE_SRC = "/root/reference"
 
 
@@ -31,7 +32,7 @@ def build(force: bool = False) -> None:
     # the reference host with our library spliced in at call_reorder / call_encoder (end-to-end parity)
     b200 = os.path.join(HERE, "..", "spring_b200", "libspring_b200.so")
     if os.path.isdir(os.path.join(REFERENCE_SRC, "src")) and os.path.exists(b200):
-        subprocess.check_call(["make", "-s", "-j8", "-C", HERE, "splice", "splice2"])
+        subprocess.check_call(["make", "-s", "-j8", "-C", HERE, "splice", "splice2", "splice3"])
 
 
 class _ByteVec(C.Structure):

@@ -19,7 +19,7 @@ EXPORTS = [
     "spring_b200_last_error", "spring_b200_get_stats", "spring_b200_reorder_encode",
     "spring_b200_reorder_encode_device", "spring_b200_fetch_streams", "spring_b200_build_dictionary",
     "spring_b200_reorder", "spring_b200_reorder_encode_files", "spring_b200_write_streams",
-    "spring_b200_bucket_reads", "spring_b200_set_schedule", "spring_b200_set_chain_stats", "spring_b200_fetch_reorder", "spring_b200_set_stream",
+    "spring_b200_bucket_reads", "spring_b200_set_schedule", "spring_b200_set_chain_stats", "spring_b200_packed_pending", "spring_b200_reorder_encode_packed", "spring_b200_fetch_reorder", "spring_b200_set_stream",
     "spring_b200_pe_encode", "spring_b200_reblock_streams", "spring_b200_reblock_files", "spring_b200_pack_reads",
     "spring_b200_decode_blocks", "spring_b200_verify_roundtrip",
     "spring_b200_comm_unique_id", "spring_b200_comm_init", "spring_b200_comm_free", "spring_b200_exchange_reads",

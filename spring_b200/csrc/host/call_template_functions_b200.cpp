@@ -58,7 +58,10 @@ void call_reorder(const std::string &temp_dir, compression_params &cp) {
       throw std::runtime_error(std::string("spring_b200: ") + err);
     g_stats = st;
   } else {
-    const int rc = spring_b200_reorder_encode_files(ctx, temp_dir.c_str(), &c, (uint32_t)env_int("SPRING_B200_CHAINS", 0));
+    // reads packed on the GPU by preprocess_b200.cpp are still in HBM: no .dna files to read
+    const uint32_t chains = (uint32_t)env_int("SPRING_B200_CHAINS", 0);
+    const int rc = spring_b200_packed_pending(ctx) ? spring_b200_reorder_encode_packed(ctx, temp_dir.c_str(), &c, chains)
+                                                   : spring_b200_reorder_encode_files(ctx, temp_dir.c_str(), &c, chains);
     if (rc != SPRING_B200_OK) throw std::runtime_error(std::string("spring_b200: ") + spring_b200_last_error(ctx));
     spring_b200_get_stats(ctx, &st);
     g_stats = st;

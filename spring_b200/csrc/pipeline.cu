@@ -38,6 +38,9 @@ struct spring_b200_ctx {
   NReads last_nr{};
   Comm *comm = nullptr;  // multi-GPU communicator (spring_b200_comm_init)
   std::string files_dir;  // temp_dir whose stream files hold exactly the resident streams (spring_b200_reorder_encode_files)
+  // reads left in HBM by spring_b200_pack_reads(keep_on_device != 0) and not consumed yet (spring_b200_reorder_encode_packed)
+  bool packed_pending = false;
+  spring_b200_packed_reads packed{};
   cudaEvent_t ev[8]{};  // 0-5: the hot path's stages, 6-7: around the re-blocking
 };
 
@@ -743,7 +746,8 @@ int spring_b200_pack_reads(spring_b200_ctx *ctx, const uint8_t *bases, const uin
     if (pk.n_record_bytes) SB_CUDA(cudaMemcpyAsync(h_nrec, pk.n_records, pk.n_record_bytes, cudaMemcpyDeviceToHost, c.stream));
     if (pk.num_n) SB_CUDA(cudaMemcpyAsync(h_on, pk.order_n, sizeof(uint32_t) * pk.num_n, cudaMemcpyDeviceToHost, c.stream));
     out->n_records = h_nrec; out->order_n = h_on;
-    if (keep_on_device) { out->reads = pk.reads; out->lengths = pk.lengths; }
+    ctx->packed_pending = false;
+    if (keep_on_device) { out->reads = pk.reads; out->lengths = pk.lengths; ctx->packed = *out; ctx->packed_pending = true; }
     else {
       uint64_t *h_reads = c.pool.pin<uint64_t>("pk.h_reads", (size_t)pk.num_clean * pk.W + 1);
       uint16_t *h_len = c.pool.pin<uint16_t>("pk.h_len", (size_t)pk.num_clean + 1);
@@ -1058,6 +1062,34 @@ int spring_b200_reorder_encode_files(spring_b200_ctx *ctx, const char *temp_dir,
     unlink(f1.c_str()); unlink(f2.c_str()); unlink(fn.c_str()); unlink(fo.c_str());
     write_streams(dir, &s, cp->num_thr > 0 ? cp->num_thr : 1);
     ctx->files_dir = dir;
+  });
+}
+
+int spring_b200_packed_pending(const spring_b200_ctx *ctx) { return ctx && ctx->packed_pending ? 1 : 0; }
+
+// call_reorder behind a preprocess that packed the reads on the GPU (csrc/host/preprocess_b200.cpp): no input_clean_*.dna /
+// input_N.dna / read_order_N.bin round trip -- the hot path starts from the rows spring_b200_pack_reads left in HBM and
+// writes the same stream files as spring_b200_reorder_encode_files.
+int spring_b200_reorder_encode_packed(spring_b200_ctx *ctx, const char *temp_dir, const spring_b200_cp *cp, uint32_t num_chains) {
+  return guarded(ctx, [&] {
+    if (!temp_dir || !cp) throw ArgError("null argument");
+    if (!ctx->packed_pending) throw ArgError("no packed reads resident on the device (spring_b200_pack_reads with keep_on_device first)");
+    const spring_b200_packed_reads &pk = ctx->packed;
+    if (cp->long_flag) throw ArgError("long mode has no reorder/encode stage (spring.cpp:150)");
+    if (cp->num_reads != pk.num_reads || cp->max_readlen != pk.max_readlen || cp->num_reads_clean[0] != pk.num_clean_file1 ||
+        cp->num_reads_clean[0] + cp->num_reads_clean[1] != pk.num_clean)
+      throw ArgError("cp does not describe the packed reads on the device");
+    if (cp->max_readlen < 1 || cp->max_readlen > (uint32_t)kMaxReadLen) throw ArgError("Wrong bitset size.");
+    spring_b200_input in{};
+    in.reads = pk.reads; in.lengths = pk.lengths; in.num_clean = pk.num_clean; in.max_readlen = pk.max_readlen;
+    in.n_records = pk.n_records; in.n_record_bytes = pk.n_record_bytes; in.order_n = pk.order_n; in.num_n = pk.num_n;
+    in.num_reads = pk.num_reads;
+    spring_b200_streams dev{}, s{};
+    run_all(ctx, &in, num_chains, false, &dev);
+    ctx->packed_pending = false;
+    fetch(ctx, &s);
+    write_streams(std::string(temp_dir), &s, cp->num_thr > 0 ? cp->num_thr : 1);
+    ctx->files_dir = temp_dir;
   });
 }
 

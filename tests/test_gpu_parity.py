@@ -264,6 +264,66 @@ def test_end_to_end_archive_decodes_with_reference(paired, reorder, splice, tmp_
     assert got == want
 
 
+@pytest.mark.skipif(not (os.path.exists(po.SPLICE3_BIN) and po.have_reference()), reason="oracle/_ref binaries not built")
+@pytest.mark.parametrize("paired", [False, True])
+@pytest.mark.parametrize("reorder", [True, False])
+def test_preprocess_and_decompress_drop_ins(paired, reorder, tmp_path):
+    """oracle/_ref/spring_b200_ref3: the reference's host pipeline with preprocess (N split + packing on the GPU, reads
+    handed to call_reorder in HBM) and decompress_short (block decode on the GPU) replaced as well.  Three legs:
+    (a) its archive decodes with the UNMODIFIED reference, (b) its archive decodes with its own `-d` (GPU decode),
+    (c) an archive the unmodified reference wrote (consensus shards of any length, so shards start inside a byte) decodes
+    with its `-d`.  With SPRING_B200_PREPROCESS_FILES=1 the drop-in writes the .dna files instead: same archive contents."""
+    import subprocess
+    from spring_b200 import synth
+    rs = synth.generate(30000, 120, seed=33, paired=paired, n_frac=0.01, var_len=(60, 120), error_model="illumina")
+    f1, f2 = str(tmp_path / "in_1.fastq"), str(tmp_path / "in_2.fastq")
+    synth.write_fastq(rs, f1, f2 if paired else None)
+    ins = [f1, f2] if paired else [f1]
+    flags = ["-r"] if reorder else []
+
+    def run(binary, args, env=None):
+        r = subprocess.run([binary, *args, "-w", str(tmp_path)], capture_output=True, text=True, env=dict(os.environ, **(env or {})))
+        assert r.returncode == 0, r.stdout + r.stderr
+        return r.stdout
+
+    def records(prefix):
+        if not paired:
+            return _fastq_records(prefix)
+        return list(zip(_fastq_records(prefix + ".1"), _fastq_records(prefix + ".2")))
+
+    want = _fastq_records(f1) if not paired else list(zip(_fastq_records(f1), _fastq_records(f2)))
+    same = (lambda got: sorted(got) == sorted(want)) if reorder else (lambda got: got == want)
+    arc3, arc3f, arcr = str(tmp_path / "b200.spring"), str(tmp_path / "b200_files.spring"), str(tmp_path / "ref.spring")
+    out = run(po.SPLICE3_BIN, ["-c", *flags, "-i", *ins, "-o", arc3, "-t", "4"])
+    assert "were unmatched" in out and "Total number of reads without N" in out
+    run(po.SPLICE3_BIN, ["-c", *flags, "-i", *ins, "-o", arc3f, "-t", "4"], {"SPRING_B200_PREPROCESS_FILES": "1"})
+    run(po.REF_BIN, ["-c", *flags, "-i", *ins, "-o", arcr, "-t", "5"])
+    for name, binary, arc, thr in (("a", po.REF_BIN, arc3, "3"), ("a-files", po.REF_BIN, arc3f, "3"), ("b", po.SPLICE3_BIN, arc3, "3"),
+                                   ("c", po.SPLICE3_BIN, arcr, "2")):
+        dec = str(tmp_path / ("dec_" + name))
+        run(binary, ["-d", "-i", arc, "-o", dec, "-t", thr])
+        assert same(records(dec)), f"leg {name}"
+
+
+@pytest.mark.skipif(not (os.path.exists(po.SPLICE3_BIN) and po.have_reference()), reason="oracle/_ref binaries not built")
+def test_decompress_drop_in_over_several_steps(tmp_path):
+    """1.1 M paired reads = 550 k pairs = 3 blocks of 256 000 pairs: `-d -t 2` takes two steps (two blocks, then one),
+    each ONE spring_b200_decode_blocks call; archive written by the unmodified reference, and by the drop-in binary."""
+    import subprocess
+    from spring_b200 import synth
+    rs = synth.generate(1_100_000, 100, genome_len=4_000_000, seed=35, paired=True, n_frac=0.005, error_model="illumina", device="cuda")
+    f1, f2 = str(tmp_path / "in_1.fastq"), str(tmp_path / "in_2.fastq")
+    synth.write_fastq(rs, f1, f2)
+    want = sorted(zip(_fastq_records(f1), _fastq_records(f2)))
+    for who, binary in (("reference", po.REF_BIN), ("drop-in", po.SPLICE3_BIN)):
+        arc, dec = str(tmp_path / (who + ".spring")), str(tmp_path / ("dec_" + who))
+        r = subprocess.run([binary, "-c", "-r", "-i", f1, f2, "-o", arc, "-t", "8", "-w", str(tmp_path)], capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout + r.stderr
+        r = subprocess.run([po.SPLICE3_BIN, "-d", "-i", arc, "-o", dec, "-t", "2", "-w", str(tmp_path)], capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout + r.stderr
+        assert sorted(zip(_fastq_records(dec + ".1"), _fastq_records(dec + ".2"))) == want, who
+
+
 def test_bucket_kernel_matches_numpy_mirror(ctx):
     """k_bucket (multi-GPU owner of a read) against the numpy restatement used by the gloo CPU tests."""
     import torch

@@ -7,6 +7,11 @@ namespace chain {
 
 constexpr unsigned FULL = 0xFFFFFFFFu;
 constexpr const char *kChainCfgDefault = "8x4";  // 32 chains per SM (64 registers, a few spills) beat 24 spill-free ones
+// batches of a search whose slot sectors are prefetched before the filter answers (SPRING_B200_PREFETCH = 1 + this in the
+// tunable instantiation: 0 no prefetch at all, 1 filter positives only, 2 all probes of batch 0, 3 of batches 0 and 1, ...)
+constexpr int kEarlyPrefetchBatches = 0;
+// probes per lane in the first batch of a free-running search (fast tail): batches cover 8 k, 16 k, then all remaining shifts
+constexpr int kBatch0 = 1;
 enum { ST_SEARCH = 0, ST_NEWREAD = 1, ST_DONE = 2 };
 enum { CTR_UNMATCHED = 0, CTR_ROUNDS, CTR_LOST, CTR_PROBES_ISSUED, CTR_PROBES_SEQ, CTR_COMPARES, CTR_ABORT,
        CTR_CYC_SEARCH, CTR_CYC_WAIT_A, CTR_CYC_COMMIT, CTR_CYC_WAIT_B, CTR_SLOT_PROBES, CTR_N };
@@ -16,7 +21,7 @@ struct ChainArgs {
   DictView dict[2];
   uint32_t *claimed;   // bitmap, one bit per read
   uint32_t *winner;    // [N], kNoWinner until proposed
-  uint32_t *rec_chain; uint32_t *rec_k; int64_t *rec_pos; uint8_t *rec_meta;
+  uint4 *rec;          // [N] {pos lo, pos hi, index in the chain's log, chain id | meta << 24}: one store per claimed read
   uint32_t *chain_aligned; uint32_t *chain_single;
   uint32_t num_chains, per;
   unsigned long long *barrier; int *active; unsigned long long *ctr;
@@ -24,9 +29,10 @@ struct ChainArgs {
   uint32_t G;            // scan_bin: candidates verified per pass = 32 / W
   unsigned leader_mask;  // scan_bin: lanes g * W, g < G
   int generic_update;    // debugging aid: always use the per-column update_ref
-  int prefetch_slots;    // pass 1 of a batch prefetches the slot of every filter positive into L2
+  int prefetch_slots;    // 1: pass 1 of a batch prefetches the slot of every filter positive into L2; 1 + k: and of EVERY probe in the first k batches
   uint64_t pol_keep, pol_stream;  // L2 cache policies (evict_last for the filter words, evict_first for slot sectors)
   int fast_tail;         // free-running chains: batches of 8, 16, then all remaining shifts
+  int batch0;            // ... times this many (tunable instantiation; kBatch0 in production)
   int filter_hint;       // filter words are loaded with the L2 evict_last policy (they should outlive the slot sectors)
   int steal_probes;      // free-running schedule: random slices an idle chain probes for an unclaimed read (0 = off)
   unsigned long long *chain_dbg;  // [2 * chains]: steps, globaltimer ns at finish (profiling aid)

@@ -311,7 +311,7 @@ __device__ __forceinline__ bool chain_search(const ChainArgs &a, const uint64_t 
     // third batch is almost always the last one of a dead end -- three round trips per dead end instead of four or five
     // (SPRING_B200_FAST_TAIL=0 restores the oracle's batches: -6.5 % kernel time on config 5's contig-start-heavy input, neutral
     // on configs 2 and 3; profiles/r02_chains2_experiment.txt)
-    const int n = (FAST_TAIL && a.fast_tail) ? (b < 2 ? 1 << b : 16) : (b < 4 ? 1 << b : 16);
+    const int n = (FAST_TAIL && (STATS ? a.fast_tail : 1)) ? (b < 2 ? (STATS ? a.batch0 : kBatch0) << b : 16) : (b < 4 ? 1 << b : 16);
     // ---- pass 1: bounds + filter bit for this lane's n probes (independent 4-byte loads) ----
     unsigned okm = 0, cand = 0;
 #pragma unroll 4
@@ -320,9 +320,15 @@ __device__ __forceinline__ bool chain_search(const ChainArgs &a, const uint64_t 
       if (s >= s_lo && s < s_hi) {
         okm |= 1u << j;
         const uint64_t hk = mix64(window_key(src, kbase + kstep * s, d.key_bits));
-        if (a.filter_hint ? filter_test_hint(d.filter, d.filter_words, hk, pol_keep) : filter_test(d.filter, d.filter_words, hk)) {
+        // early batches: the slot sector is requested together with the filter word, before the filter's answer is known
+        // (no register is held for it): a filter positive then finds its slot in L2 instead of paying a second DRAM
+        // round trip behind the first.  Costs one wasted sector per filter negative, so only where hits are likely.
+        if (b < (STATS ? a.prefetch_slots - 1 : kEarlyPrefetchBatches)) asm volatile("prefetch.global.L2 [%0];" ::"l"(d.slots + slot_home(hk, d.slot_shift)));
+        // the production instantiation (STATS = false) has the tuning knobs compiled in: L2 evict_last on the filter
+        // words, slot prefetch, fast tail
+        if ((STATS ? a.filter_hint : 1) ? filter_test_hint(d.filter, d.filter_words, hk, pol_keep) : filter_test(d.filter, d.filter_words, hk)) {
           cand |= 1u << j;
-          if (a.prefetch_slots) asm volatile("prefetch.global.L2 [%0];" ::"l"(d.slots + slot_home(hk, d.slot_shift)));
+          if (STATS ? (a.prefetch_slots > 0 && b >= a.prefetch_slots - 1) : b >= kEarlyPrefetchBatches) asm volatile("prefetch.global.L2 [%0];" ::"l"(d.slots + slot_home(hk, d.slot_shift)));
         }
       }
     }
@@ -383,6 +389,12 @@ __device__ __forceinline__ bool chain_search(const ChainArgs &a, const uint64_t 
   return false;
 }
 
+// One 16-byte record per read, written by the chain that claims it (one store): position in the contig, index in the
+// chain's aligned / singleton log, chain id + meta (bit 0 reverse, bit 1 flag '1', bit 2 singleton) in the top byte.
+__device__ __forceinline__ uint4 make_rec(long long pos, uint32_t k, uint32_t chain, uint32_t meta) {
+  return make_uint4((uint32_t)(unsigned long long)pos, (uint32_t)((unsigned long long)pos >> 32), k, chain | (meta << 24));
+}
+
 // Highest unclaimed read in [lo, cursor] (reorder.h:576-592), 32 bitmap words per step.
 __device__ bool find_unclaimed(const uint32_t *claimed, long long lo, long long cursor, int lane, uint32_t &rid) {
   if (cursor < lo) return false;
@@ -434,7 +446,7 @@ __global__ void __launch_bounds__(WPB * 32, MINB) k_chains(ChainArgs a) {
   int ref_len = 0, prev_unmatched = 0, left_search = 0, iter_started = 0, stop_searching = 0, batch = 0, batch_S = 0;
   long long ref_pos = 0, cur_read_pos = 0;
   int cursor = -1, slice_lo = 0;  // read ids fit 31 bits (check_input)
-  uint32_t first_rid = 0, prev = 0, num_reads_thr = 0, num_unmatched_1m = 0, n_aligned = 0, n_single = 0;
+  uint32_t first_rid = 0, prev = 0, num_reads_thr = 0, num_unmatched_1m = 0, n_aligned = 0, n_single = 0, window_left = 0;
   // statistics: c_issued / c_seq / c_slot are per-lane partial sums, c_cmp / c_unmatched / c_lost are
   // warp-uniform; 32-bit in registers, flushed to the 64-bit totals before they can wrap
   uint32_t c_unmatched = 0, c_lost = 0, c_issued = 0, c_seq = 0, c_cmp = 0, c_slot = 0;
@@ -468,7 +480,7 @@ __global__ void __launch_bounds__(WPB * 32, MINB) k_chains(ChainArgs a) {
   // fold the read staged in curw into the window: word-parallel fast path, or the per-column generic
   // version for the reference's in-place "fold" quirk (and on request, as a cross-check)
   auto upd = [&](int old_len, int delta, int cs, int cur_len, bool rev, int new_len, int fold) {
-    if (fold > 0 || a.generic_update) update_ref(ref, revref, curw, cnt, W, lane, old_len, delta, cs, cur_len, rev, new_len, fold);
+    if (fold > 0 || (STATS && a.generic_update)) update_ref(ref, revref, curw, cnt, W, lane, old_len, delta, cs, cur_len, rev, new_len, fold);
     else update_ref_fast(ref, revref, curw, cnt, W, lane, old_len, delta, cs, cur_len, rev, new_len);
   };
   // the read must already be staged in curw
@@ -513,11 +525,13 @@ __global__ void __launch_bounds__(WPB * 32, MINB) k_chains(ChainArgs a) {
     // no proposals; the result depends on timing for more than one chain -- as the reference's does.
     while (state != ST_DONE) {
       if (state == ST_SEARCH) {
-        if (!iter_started) {  // loop top, reorder.h:433-439
-          if (num_reads_thr % kStopWindow == 0) {
+        if (!iter_started) {  // loop top, reorder.h:433-439 (the window's end is counted down: no modulo per step)
+          if (window_left == 0) {
             if (num_unmatched_1m > kStopUnmatched) stop_searching = 1;
             num_unmatched_1m = 0;
+            window_left = kStopWindow;
           }
+          window_left--;
           num_reads_thr++;
           iter_started = 1;
         }
@@ -540,7 +554,7 @@ __global__ void __launch_bounds__(WPB * 32, MINB) k_chains(ChainArgs a) {
               c_lost++;  // another chain took it between the check and the claim: search this batch again
               continue;
             }
-            S += 8 * (a.fast_tail ? (b < 2 ? 1 << b : 16) : (b < 4 ? 1 << b : 16));
+            S += 8 * ((STATS ? a.fast_tail : 1) ? (b < 2 ? (STATS ? a.batch0 : kBatch0) << b : 16) : (b < 4 ? 1 << b : 16));
             b++;
           }
         }
@@ -564,10 +578,10 @@ __global__ void __launch_bounds__(WPB * 32, MINB) k_chains(ChainArgs a) {
             else { cur_read_pos = ref_pos - shift; ref_pos = cur_read_pos; }
           }
           if (lane == 0) {
-            if (prev_unmatched) { a.rec_chain[prev] = cid; a.rec_k[prev] = n_aligned; a.rec_pos[prev] = 0; a.rec_meta[prev] = 0; }
+            if (prev_unmatched) a.rec[prev] = make_rec(0, n_aligned, cid, 0);
             const uint32_t kk = n_aligned + (prev_unmatched ? 1u : 0u);
             const int is_r = prev_rev ? !left_search : left_search;
-            a.rec_chain[k] = cid; a.rec_k[k] = kk; a.rec_pos[k] = cur_read_pos; a.rec_meta[k] = (uint8_t)(2 | (is_r ? 1 : 0));
+            a.rec[k] = make_rec(cur_read_pos, kk, cid, 2u | (is_r ? 1u : 0u));
           }
           n_aligned += prev_unmatched ? 2u : 1u;
           prev_unmatched = 0;
@@ -615,7 +629,7 @@ __global__ void __launch_bounds__(WPB * 32, MINB) k_chains(ChainArgs a) {
           }
         }
         if (prev_unmatched) {
-          if (lane == 0) { a.rec_chain[prev] = cid; a.rec_k[prev] = n_single; a.rec_meta[prev] = 4; }
+          if (lane == 0) a.rec[prev] = make_rec(0, n_single, cid, 4);
           n_single++;
         }
         if (got) {
@@ -702,11 +716,11 @@ __global__ void __launch_bounds__(WPB * 32, MINB) k_chains(ChainArgs a) {
           }
           if (lane == 0) {
             if (prev_unmatched) {  // the contig's first read is written lazily, reorder.h:498-507
-              a.rec_chain[prev] = cid; a.rec_k[prev] = n_aligned; a.rec_pos[prev] = 0; a.rec_meta[prev] = 0;
+              a.rec[prev] = make_rec(0, n_aligned, cid, 0);
             }
             const uint32_t kk = n_aligned + (prev_unmatched ? 1u : 0u);
             const int is_r = prop_rev ? !left_search : left_search;  // reorder.h:508, :546
-            a.rec_chain[k] = cid; a.rec_k[k] = kk; a.rec_pos[k] = cur_read_pos; a.rec_meta[k] = (uint8_t)(2 | (is_r ? 1 : 0));
+            a.rec[k] = make_rec(cur_read_pos, kk, cid, 2u | (is_r ? 1u : 0u));
           }
           n_aligned += prev_unmatched ? 2u : 1u;
           prev_unmatched = 0;
@@ -732,7 +746,7 @@ __global__ void __launch_bounds__(WPB * 32, MINB) k_chains(ChainArgs a) {
         if (__ldcg(a.winner + prop_rid) == cid) {
           const uint32_t j = prop_rid;
           claim_pre(j, pre_sidx);
-          if (lane == 0 && prev_unmatched) { a.rec_chain[prev] = cid; a.rec_k[prev] = n_single; a.rec_meta[prev] = 4; }
+          if (lane == 0 && prev_unmatched) a.rec[prev] = make_rec(0, n_single, cid, 4);
           if (prev_unmatched) n_single++;
           cursor = (int)j - 1;
           c_unmatched++;
@@ -742,7 +756,7 @@ __global__ void __launch_bounds__(WPB * 32, MINB) k_chains(ChainArgs a) {
         }
       } else {
         if (prev_unmatched) {
-          if (lane == 0) { a.rec_chain[prev] = cid; a.rec_k[prev] = n_single; a.rec_meta[prev] = 4; }
+          if (lane == 0) a.rec[prev] = make_rec(0, n_single, cid, 4);
           n_single++;
         }
         state = ST_DONE;
@@ -779,21 +793,20 @@ __global__ void k_make_policies(unsigned long long *out) {
 
 // Chain logs -> one stream, chain after chain (what the merge of per-thread files gives,
 // encoder.h:386-423): record k of chain c lands at offset[c] + k.
-__global__ void k_scatter_records(const uint32_t *__restrict__ rec_chain, const uint32_t *__restrict__ rec_k,
-                                  const int64_t *__restrict__ rec_pos, const uint8_t *__restrict__ rec_meta, uint32_t n,
-                                  const uint32_t *__restrict__ off_aligned, const uint32_t *__restrict__ off_single,
-                                  uint32_t *order, uint8_t *flag, int64_t *pos, uint8_t *rev, uint32_t *s_order) {
+__global__ void k_scatter_records(const uint4 *__restrict__ rec, uint32_t n, const uint32_t *__restrict__ off_aligned,
+                                  const uint32_t *__restrict__ off_single, uint32_t *order, uint8_t *flag, int64_t *pos, uint8_t *rev,
+                                  uint32_t *s_order) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const uint8_t m = rec_meta[i];
-  const uint32_t c = rec_chain[i], k = rec_k[i];
+  const uint4 r = rec[i];
+  const uint32_t m = r.w >> 24, c = r.w & 0xFFFFFFu, k = r.z;
   if (m & 4) {
     s_order[off_single[c] + k] = i;
   } else {
     const uint32_t o = off_aligned[c] + k;
     order[o] = i;
     flag[o] = (m >> 1) & 1;
-    pos[o] = rec_pos[i];
+    pos[o] = (int64_t)((unsigned long long)r.x | ((unsigned long long)r.y << 32));
     rev[o] = (m & 1) ? 'r' : 'd';
   }
 }
@@ -825,7 +838,9 @@ void run_reorder(Ctx &c, const uint64_t *reads, const uint16_t *lens, uint32_t n
     const bool generic_w = getenv("SPRING_B200_GENERIC_W") != nullptr;  // A/B: the any-length instantiation
     if (want == "8x4") {
       kWarpsPerBlock = 8;
-      const bool stats = c.chain_stats;
+      // the tuning knobs exist in the counting instantiation only; the production one has their defaults compiled in
+      const bool stats = c.chain_stats || getenv("SPRING_B200_FAST_TAIL") || getenv("SPRING_B200_FILTER_HINT") ||
+                         getenv("SPRING_B200_PREFETCH") || getenv("SPRING_B200_GENERIC_UPDATE") || getenv("SPRING_B200_BATCH0");
       if (W == 5 && !generic_w) kern = stats ? k_chains<false, 8, 4, 5> : k_chains<false, 8, 4, 5, false>;       // 129..160 bases (150 bp reads)
       else if (W == 8 && !generic_w) kern = stats ? k_chains<false, 8, 4, 8> : k_chains<false, 8, 4, 8, false>;  // 225..256 bases (250 bp reads)
       else if (W == 4 && !generic_w) kern = stats ? k_chains<false, 8, 4, 4> : k_chains<false, 8, 4, 4, false>;  // 97..128 bases (100 / 125 bp reads)
@@ -862,6 +877,7 @@ void run_reorder(Ctx &c, const uint64_t *reads, const uint16_t *lens, uint32_t n
   if (C > max_chains) C = max_chains;
   if (C > n) C = n;
   const uint32_t grid = (C + chains_per_block - 1) / chains_per_block;
+  if (C >= (1u << 24)) throw LimitError("reorder: more than 2^24 chains");  // a record keeps the chain id in 24 bits
   out.num_chains = C;
 
   ChainArgs a{};
@@ -870,10 +886,7 @@ void run_reorder(Ctx &c, const uint64_t *reads, const uint16_t *lens, uint32_t n
   const size_t bm_words = ((size_t)n + 31) / 32;
   a.claimed = c.pool.dev<uint32_t>("ro.claimed", bm_words);
   a.winner = c.pool.dev<uint32_t>("ro.winner", nn);
-  a.rec_chain = c.pool.dev<uint32_t>("ro.rec_chain", nn);
-  a.rec_k = c.pool.dev<uint32_t>("ro.rec_k", nn);
-  a.rec_pos = c.pool.dev<int64_t>("ro.rec_pos", nn);
-  a.rec_meta = c.pool.dev<uint8_t>("ro.rec_meta", nn);
+  a.rec = c.pool.dev<uint4>("ro.rec", nn);
   const uint32_t nslots = grid * chains_per_block;
   a.chain_aligned = c.pool.dev<uint32_t>("ro.chain_aligned", nslots + 1);
   a.chain_single = c.pool.dev<uint32_t>("ro.chain_single", nslots + 1);
@@ -897,6 +910,7 @@ void run_reorder(Ctx &c, const uint64_t *reads, const uint16_t *lens, uint32_t n
   }
   a.pol_keep = c.l2_policies[0]; a.pol_stream = c.l2_policies[1];
   a.fast_tail = getenv("SPRING_B200_FAST_TAIL") ? atoi(getenv("SPRING_B200_FAST_TAIL")) : 1;
+  a.batch0 = getenv("SPRING_B200_BATCH0") ? std::max(1, std::min(4, atoi(getenv("SPRING_B200_BATCH0")))) : kBatch0;
   a.filter_hint = getenv("SPRING_B200_FILTER_HINT") ? atoi(getenv("SPRING_B200_FILTER_HINT")) : 1;  // L2 evict_last on the filter words  // -1 to -2 % on configs 2 and 3
   a.steal_probes = lockstep ? 0 : (getenv("SPRING_B200_STEAL") ? atoi(getenv("SPRING_B200_STEAL")) : 64);
   a.max_rounds = 8ull * n + 4096ull;
@@ -921,8 +935,7 @@ void run_reorder(Ctx &c, const uint64_t *reads, const uint16_t *lens, uint32_t n
   need = tmp_bytes; cub::DeviceScan::ExclusiveSum(tmp, need, a.chain_aligned, off_aligned, (int)nslots + 1, st);
   need = tmp_bytes; cub::DeviceScan::ExclusiveSum(tmp, need, a.chain_single, off_single, (int)nslots + 1, st);
   c.launches += 2;
-  k_scatter_records<<<(n + 255) / 256, 256, 0, st>>>(a.rec_chain, a.rec_k, a.rec_pos, a.rec_meta, n, off_aligned, off_single,
-                                                     out.order, out.flag, out.pos, out.rev, out.s_order);
+  k_scatter_records<<<(n + 255) / 256, 256, 0, st>>>(a.rec, n, off_aligned, off_single, out.order, out.flag, out.pos, out.rev, out.s_order);
   c.launches++;
   unsigned long long *h = c.pool.pin<unsigned long long>("ro.hsync", CTR_N + 4);
   SB_CUDA(cudaMemcpyAsync(h, a.ctr, CTR_N * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));

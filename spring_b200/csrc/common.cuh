@@ -70,8 +70,6 @@ struct DictView {
   const uint32_t *filter;        // blocked Bloom filter over the keys: 2 bits in one 32-bit word, >= 8 bits per key
   uint32_t filter_words;         // filter word of hk = (top 32 bits of hk) * filter_words >> 32: any size, monotone in hk
                                  // (the build sets it front to back too)
-  const uint32_t *filter1;       // optional first-level filter of a dictionary whose `filter` does not fit L2: a few bits per key,
-  uint32_t filter1_words;        // kept L2-resident; only its positives go on to `filter` (in DRAM then).  0 = absent
   int start, end;                // base window [start, end]
   int key_bits;                  // bits per base * (end - start + 1)
 };
@@ -88,7 +86,6 @@ __host__ __device__ inline uint64_t mix64(uint64_t x) {
 // size (no power-of-two rounding: at 100 M keys that rounding alone was 128 MB instead of 100), bits hk[0:5) and hk[5:10)
 __host__ __device__ inline uint32_t filter_word(uint64_t hk, uint32_t nwords) { return (uint32_t)(((hk >> 32) * (uint64_t)nwords) >> 32); }
 __host__ __device__ inline uint32_t filter_bits(uint64_t hk) { return (1u << (hk & 31)) | (1u << ((hk >> 5) & 31)); }
-__host__ __device__ inline uint32_t filter1_bits(uint64_t hk) { return (1u << ((hk >> 10) & 31)) | (1u << ((hk >> 15) & 31)); }  // independent of filter_bits
 __host__ __device__ inline uint32_t slot_home(uint64_t hk, int sshift) { return (uint32_t)(hk >> sshift); }
 constexpr uint64_t kInvalidKey = ~0ull;  // hk of a read that is not indexed (too short for the window, N inside it)
 

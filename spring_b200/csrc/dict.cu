@@ -114,7 +114,7 @@ __global__ void k_insert_slots(const uint64_t *__restrict__ hkeys, const uint32_
                                const uint32_t *__restrict__ bin_start_idx, const uint32_t *__restrict__ numkeys_p,
                                const uint32_t *__restrict__ num_valid, const int *__restrict__ m, uint32_t n, uint32_t slot_limit,
                                uint32_t filter_words, DictSlot *slots, uint32_t *bins, uint32_t *slot_of_bin, uint32_t *filter,
-                               uint32_t *filter1, uint32_t filter1_words, uint32_t *dropped) {
+                               uint32_t *dropped) {
   const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t numkeys = *numkeys_p;
   if (k >= n || k >= numkeys) return;
@@ -139,7 +139,6 @@ __global__ void k_insert_slots(const uint64_t *__restrict__ hkeys, const uint32_
   slot_of_bin[k] = (uint32_t)slot;
   // keys arrive in ascending hk and the filter word is the top bits of hk: neighbouring threads hit neighbouring words
   atomicOr(filter + filter_word(hk, filter_words), filter_bits(hk));
-  if (filter1_words) atomicOr(filter1 + filter_word(hk, filter1_words), filter1_bits(hk));
 }
 
 // sorted entry i (ascending id inside its bin) -> descending position behind the bin header
@@ -208,22 +207,6 @@ void build_dictionary(Ctx &c, const uint64_t *reads, const uint16_t *lens, const
   SB_CUDA(cudaMemsetAsync(filter, 0, fwords * sizeof(uint32_t), st));
   out.view.filter = filter;
   out.view.filter_words = (uint32_t)fwords;
-  // A filter that cannot stay in L2 (two dictionaries of 100 M keys: 2 x 100 MB against 126 MB) turns most probes into DRAM
-  // accesses of their own: 4.2 KB of the 5.8 KB a read of config 3 pulls from DRAM.  Such a dictionary gets a first-level
-  // filter of SPRING_B200_FILTER1_BITS bits per key (default 2: 25 MB per 100 M keys, ~40 % pass) that does stay resident;
-  // only its positives look at the big one.  SPRING_B200_FILTER1_MIN_MB: size of `filter` from which on it is built (default 32).
-  static const double kFilter1Bits = getenv("SPRING_B200_FILTER1_BITS") ? atof(getenv("SPRING_B200_FILTER1_BITS")) : 2.0;
-  static const double kFilter1MinMB = getenv("SPRING_B200_FILTER1_MIN_MB") ? atof(getenv("SPRING_B200_FILTER1_MIN_MB")) : 32.0;
-  uint64_t f1words = 0;
-  uint32_t *filter1 = nullptr;
-  if (kFilter1Bits > 0 && (double)fwords * 4.0 >= kFilter1MinMB * 1048576.0) {
-    f1words = (uint64_t)(kFilter1Bits * (double)n / 32.0) + 1;
-    if (f1words < 2048) f1words = 2048;
-    filter1 = c.pool.dev<uint32_t>(nm(".filter1").c_str(), f1words);
-    SB_CUDA(cudaMemsetAsync(filter1, 0, f1words * sizeof(uint32_t), st));
-  }
-  out.view.filter1 = filter1;
-  out.view.filter1_words = (uint32_t)f1words;
   out.view.slots = slots;
   out.view.bins = bins;
   out.view.slot_of_read = slot_of_read;
@@ -266,7 +249,7 @@ void build_dictionary(Ctx &c, const uint64_t *reads, const uint16_t *lens, const
   need = tmp_bytes;
   cub::DeviceScan::InclusiveScan(tmp, need, hm, hmax, MaxOp(), (int)n, st);
   k_insert_slots<<<grid_for(n, 256), 256, 0, st>>>(keys_b, rid_c, bin_start_idx, d_count + 1, d_count, hmax, n, (uint32_t)cap + kSlotPad - 1,
-                                                  out.view.filter_words, slots, bins, slot_of_bin, filter, filter1, out.view.filter1_words, d_count + 2);
+                                                  out.view.filter_words, slots, bins, slot_of_bin, filter, d_count + 2);
   k_fill_bins<<<grid_for(n, 256), 256, 0, st>>>(keys_b, rid_c, kidx1, bin_start_idx, slot_of_bin, d_count + 1, d_count, n, bins, slot_of_read);
   c.launches += 6 + (2 + 4) + 2 + 3 + 2;  // ours + CUB (sort: histogram + 4 x onesweep, scans, select)
   SB_CUDA(cudaGetLastError());

@@ -326,17 +326,7 @@ __device__ __forceinline__ bool chain_search(const ChainArgs &a, const uint64_t 
         if (b < (STATS ? a.prefetch_slots - 1 : kEarlyPrefetchBatches)) asm volatile("prefetch.global.L2 [%0];" ::"l"(d.slots + slot_home(hk, d.slot_shift)));
         // the production instantiation (STATS = false) has the tuning knobs compiled in: L2 evict_last on the filter
         // words, slot prefetch, fast tail
-        // two-level filter of a big dictionary: the small first level is the one kept in L2 (evict_last), the big second
-        // level streams (evict_first) and is asked only by the first level's positives
-        bool pass1 = true;
-        if (d.filter1_words) {
-          const uint32_t b1 = filter1_bits(hk);
-          uint32_t w1;
-          asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(w1) : "l"(d.filter1 + filter_word(hk, d.filter1_words)), "l"(pol_keep));
-          pass1 = (w1 & b1) == b1;
-        }
-        if (pass1 && ((STATS ? a.filter_hint : 1) ? filter_test_hint(d.filter, d.filter_words, hk, d.filter1_words ? pol_stream : pol_keep)
-                                                  : filter_test(d.filter, d.filter_words, hk))) {
+        if ((STATS ? a.filter_hint : 1) ? filter_test_hint(d.filter, d.filter_words, hk, pol_keep) : filter_test(d.filter, d.filter_words, hk)) {
           cand |= 1u << j;
           if (STATS ? (a.prefetch_slots > 0 && b >= a.prefetch_slots - 1) : b >= kEarlyPrefetchBatches) asm volatile("prefetch.global.L2 [%0];" ::"l"(d.slots + slot_home(hk, d.slot_shift)));
         }

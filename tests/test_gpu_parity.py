@@ -70,36 +70,6 @@ def test_multi_key_runs_everywhere(tmp_path):
     assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
 
 
-def test_two_level_filter_same_streams():
-    """SPRING_B200_FILTER1_MIN_MB=0: every dictionary gets the first-level key filter that normally only dictionaries too
-    big for L2 get (dict.cu).  A filter never changes an answer, so the streams must stay the oracle's bit for bit --
-    deterministic schedule, many chains -- and the free-running schedule must still decode to the input."""
-    import subprocess, sys, textwrap
-    code = textwrap.dedent("""
-        import sys
-        sys.path.insert(0, %r); sys.path.insert(0, %r)
-        from helpers import CASES, assert_streams_equal, check_roundtrip, make_input
-        from oracle import pyoracle as po
-        from spring_b200 import capi
-        ctx = capi.Context(0)
-        for name in ("se150", "var250", "heavy_bins", "pe100_illumina", "dups"):
-            hp = make_input(**CASES[name])
-            ctx.set_schedule(True)
-            for chains in (1, 64):
-                got = ctx.reorder_encode(hp.packed, hp.lengths, hp.max_readlen, hp.n_records, hp.order_n, hp.num_reads, chains)
-                c = ctx.stats()["num_chains"]
-                _, er = po.reorder_encode(hp.packed, hp.lengths, hp.max_readlen, hp.n_records, hp.order_n, hp.num_reads, c)
-                assert_streams_equal(got, er, name)
-            ctx.set_schedule(False)
-            got = ctx.reorder_encode(hp.packed, hp.lengths, hp.max_readlen, hp.n_records, hp.order_n, hp.num_reads, 0)
-            check_roundtrip(got, hp, po.decode)
-        print("ok")
-    """) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
-    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300,
-                       env=dict(os.environ, SPRING_B200_FILTER1_MIN_MB="0"))
-    assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
-
-
 @pytest.mark.parametrize("name", sorted(CASES))
 def test_reorder_stream_matches_oracle(det, name):
     """reorder<>(), deterministic schedule: order / flag / pos / rev / singleton lists bit-exact

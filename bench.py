@@ -237,6 +237,8 @@ def main() -> None:
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-verify", action="store_true")
     ap.add_argument("--no-files-leg", action="store_true")
+    ap.add_argument("--profile-after-setup", action="store_true",
+                    help="cudaProfilerStart() once the synthetic input exists (ncu --profile-from-start off: launch lists without the generator's kernels)")
     args = ap.parse_args()
     cfg_id, cfg = args.config, CONFIGS[args.config]
     if not args.reads:
@@ -280,6 +282,8 @@ def main() -> None:
     torch.cuda.synchronize()
     stream = torch.cuda.current_stream()
     ctx = capi.Context(local, stream.cuda_stream)
+    if args.profile_after_setup:
+        torch.cuda.cudart().cudaProfilerStart()
     # global ids of this rank's reads (paired: file-2 mates are numbered total / 2 + pair index); they travel with the
     # clean reads through the exchange, the rank's own N reads keep theirs for the shard finalisation
     d_ids, n_ids = None, None

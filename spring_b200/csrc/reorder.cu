@@ -34,6 +34,10 @@
 #include <cub/cub.cuh>
 #include "chain_common.cuh"
 
+#ifndef SB_KEEP_HK
+#define SB_KEEP_HK 1  // pass 2 reuses the hashed key of a lane's first probe instead of cutting it out and hashing it again
+#endif
+
 namespace sb {
 
 using namespace chain;
@@ -140,8 +144,14 @@ __device__ __noinline__ void update_ref(uint64_t *ref, uint64_t *revref, const u
 //     read's words, and only the columns where read and old consensus DIFFER -- at most THRESH_REORDER
 //     of them, the match passed the Hamming test on exactly these bits -- need the vote.
 // curw is overwritten with the read as oriented in the contig.
-__device__ void update_ref_fast(uint64_t *ref, uint64_t *revref, uint64_t *curw, uint64_t *cnt, int W, int lane, int old_len,
-                                int delta, int cs, int cur_len, bool rev, int new_len) {
+// WT > 0: words per read known at compile time (the chunk loop unrolls into straight-line, branch-free code: the count
+// pass was the largest single block of the kernel, 47 instructions per 32 columns with its bounds branches; now ~20).
+// saturating: some column of this contig may have reached 65535 (more than 65534 reads folded in since the counts were
+// reset) -- only then is the per-field saturation check of count_add needed.
+template <int WT>
+__device__ __forceinline__ void update_ref_fast(uint64_t *ref, uint64_t *revref, uint64_t *curw, uint64_t *cnt, int Wrt, int lane,
+                                                int old_len, int delta, int cs, int cur_len, bool rev, int new_len, bool saturating) {
+  const int W = WT ? WT : Wrt;
   if (rev) {
     uint64_t o = 0;
     if (lane < W) o = revcomp_word(curw, W, cur_len, lane);
@@ -149,34 +159,59 @@ __device__ void update_ref_fast(uint64_t *ref, uint64_t *revref, uint64_t *curw,
     if (lane < W) curw[lane] = o;
     __syncwarp();
   }
-  const int nchunks = (new_len + 31) >> 5;
-  for (int cc = 0; cc < nchunks; cc++) {  // ascending is safe: delta >= 0, sources lie at or above the column
-    const int i = (cc << 5) + lane;
-    const bool in = i < new_len;
-    uint2 v = make_uint2(0u, 0u);  // .x: rows A (bits 0-15), C (16-31); .y: rows T, G
-    if (in && i + delta < old_len) v = reinterpret_cast<const uint2 *>(cnt)[i + delta];
+  // the read in window coordinates (shifted up by cs columns, nothing outside its columns), and what the consensus merge
+  // below needs from the old consensus -- both before curw / ref are overwritten
+  uint64_t A = 0, B = 0, MA = 0, MB = 0;
+  if (lane < W) {
+    MA = range_mask(lane, 0, 2 * (old_len - delta));        // columns that have a source column
+    MB = range_mask(lane, 2 * cs, 2 * (cs + cur_len));      // columns the read covers
+    A = shr_word(ref, W, lane, 2 * delta) & MA;
+    B = shl_word(curw, W, lane, 2 * cs) & MB;
+  }
+  __syncwarp();
+  if (lane < W) curw[lane] = B;
+  __syncwarp();
+  // counts: cnt[i] = cnt[i + delta] (+ the read's base), 32 columns per chunk, column i = 32 cc + lane.  All sources are
+  // loaded before any column is stored (a chunk's sources overlap the columns the same chunk writes when delta < 32).
+  // cnt[col] packs the four per-base counts as u16 fields, rows A,C,T,G (reorder.h:120-123); 2-bit read codes are
+  // A0 G1 C2 T3 -> field 0, 3, 1, 2 = (0x9C >> 2 code) & 3.
+  const int sh2 = 2 * (lane & 15);
+  const bool hi_half = (lane & 16) != 0;
+  if (WT) {
+    uint64_t v[WT ? WT : 1];
+#pragma unroll
+    for (int cc = 0; cc < WT; cc++) {
+      const int src = (cc << 5) + lane + delta;
+      v[cc] = src < old_len ? cnt[src] : 0ull;
+    }
     __syncwarp();
-    if (in) {
-      const unsigned ci = (unsigned)(i - cs);
-      if (ci < (unsigned)cur_len) {
-        // cnt[col] packs the four per-base counts as u16 fields, rows A,C,T,G (reorder.h:120-123);
-        // 2-bit read codes are A0 G1 C2 T3 -> field shift 0, 48, 16, 32: odd codes live in the high
-        // word, codes 1 and 2 in the upper half of their word
-        const int b = base_code(curw, (int)ci);
-        const int sh = ((b ^ (b >> 1)) & 1) << 4;
-        const uint32_t f = (b & 1) ? v.y : v.x;
-        const uint32_t inc = ((f >> sh) & 0xFFFFu) != 0xFFFFu ? 1u << sh : 0u;  // counts saturate at 65535 (count_add)
-        if (b & 1) v.y += inc; else v.x += inc;
-      }
-      reinterpret_cast<uint2 *>(cnt)[i] = v;
+#pragma unroll
+    for (int cc = 0; cc < WT; cc++) {
+      const int i = (cc << 5) + lane;
+      const uint2 bw = reinterpret_cast<const uint2 *>(curw)[cc];                 // same word for the whole warp: a broadcast
+      const uint32_t code = ((hi_half ? bw.y : bw.x) >> sh2) & 3u;
+      const bool covered = (unsigned)(i - cs) < (unsigned)cur_len;
+      const int fsh = (int)((0x9Cu >> (2 * code)) & 3u) << 4;
+      if (!saturating) v[cc] += (uint64_t)(covered ? 1u : 0u) << fsh;
+      else if (covered && ((v[cc] >> fsh) & 0xFFFFull) != 0xFFFFull) v[cc] += 1ull << fsh;  // counts saturate at 65535 (count_add)
+      if (i < new_len) cnt[i] = v[cc];
+    }
+  } else {
+    const int nchunks = (new_len + 31) >> 5;
+    for (int cc = 0; cc < nchunks; cc++) {  // ascending is safe: delta >= 0, sources lie at or above the column
+      const int i = (cc << 5) + lane;
+      uint64_t v = i + delta < old_len ? cnt[i + delta] : 0ull;
+      __syncwarp();
+      const uint2 bw = reinterpret_cast<const uint2 *>(curw)[cc];
+      const uint32_t code = ((hi_half ? bw.y : bw.x) >> sh2) & 3u;
+      const bool covered = (unsigned)(i - cs) < (unsigned)cur_len;
+      const int fsh = (int)((0x9Cu >> (2 * code)) & 3u) << 4;
+      if (covered && ((v >> fsh) & 0xFFFFull) != 0xFFFFull) v += 1ull << fsh;
+      if (i < new_len) cnt[i] = v;
     }
   }
   uint64_t nw = 0, mm = 0;
   if (lane < W) {
-    const uint64_t MA = range_mask(lane, 0, 2 * (old_len - delta));        // columns that have a source column
-    const uint64_t MB = range_mask(lane, 2 * cs, 2 * (cs + cur_len));      // columns the read covers
-    const uint64_t A = shr_word(ref, W, lane, 2 * delta) & MA;
-    const uint64_t B = shl_word(curw, W, lane, 2 * cs) & MB;
     nw = A | (B & ~MA);
     const uint64_t X = (A ^ B) & MA & MB;
     mm = (X | (X >> 1)) & 0x5555555555555555ull;  // bit 2t: column 32*lane + t needs the vote
@@ -314,12 +349,16 @@ __device__ __forceinline__ bool chain_search(const ChainArgs &a, const uint64_t 
     const int n = (FAST_TAIL && (STATS ? a.fast_tail : 1)) ? (b < 2 ? (STATS ? a.batch0 : kBatch0) << b : 16) : (b < 4 ? 1 << b : 16);
     // ---- pass 1: bounds + filter bit for this lane's n probes (independent 4-byte loads) ----
     unsigned okm = 0, cand = 0;
+    uint64_t hk_first = 0;  // hashed key of this lane's first probe: most batches have one probe per lane, and pass 2 needs it again
 #pragma unroll 4
     for (int j = 0; j < n; j++) {
       const int s = S + sub + 8 * j;
       if (s >= s_lo && s < s_hi) {
         okm |= 1u << j;
         const uint64_t hk = mix64(window_key(src, kbase + kstep * s, d.key_bits));
+#if SB_KEEP_HK
+        if (j == 0) hk_first = hk;
+#endif
         // early batches: the slot sector is requested together with the filter word, before the filter's answer is known
         // (no register is held for it): a filter positive then finds its slot in L2 instead of paying a second DRAM
         // round trip behind the first.  Costs one wasted sector per filter negative, so only where hits are likely.
@@ -341,7 +380,11 @@ __device__ __forceinline__ bool chain_search(const ChainArgs &a, const uint64_t 
         const int j = __ffs(cand) - 1;
         cand &= cand - 1;
         const int s = S + sub + 8 * j;
+#if SB_KEEP_HK
+        const uint64_t hk = j == 0 ? hk_first : mix64(window_key(src, kbase + kstep * s, d.key_bits));
+#else
         const uint64_t hk = mix64(window_key(src, kbase + kstep * s, d.key_bits));
+#endif
         uint32_t h = slot_home(hk, d.slot_shift);
         if (STATS) slot_probes++;
         for (;;) {  // ordered probing: every key between the home slot and hk's own slot is smaller than hk
@@ -479,9 +522,16 @@ __global__ void __launch_bounds__(WPB * 32, MINB) k_chains(ChainArgs a) {
   };
   // fold the read staged in curw into the window: word-parallel fast path, or the per-column generic
   // version for the reference's in-place "fold" quirk (and on request, as a cross-check)
+  uint32_t depth = 0;  // reads folded into the counts since they were last reset (update_ref_fast: saturation only beyond 65534)
   auto upd = [&](int old_len, int delta, int cs, int cur_len, bool rev, int new_len, int fold) {
-    if (fold > 0 || (STATS && a.generic_update)) update_ref(ref, revref, curw, cnt, W, lane, old_len, delta, cs, cur_len, rev, new_len, fold);
-    else update_ref_fast(ref, revref, curw, cnt, W, lane, old_len, delta, cs, cur_len, rev, new_len);
+    if (old_len == 0) depth = 0;  // counts start from zero: a new contig, or its left search
+    if (depth < 65535u) depth++;
+    if (fold > 0 || (STATS && a.generic_update)) {
+      update_ref(ref, revref, curw, cnt, W, lane, old_len, delta, cs, cur_len, rev, new_len, fold);
+      if (fold > 0) depth = 65535u;  // the fold adds several of the read's bases to one column: no bound on the counts after it
+    } else {
+      update_ref_fast<WT>(ref, revref, curw, cnt, W, lane, old_len, delta, cs, cur_len, rev, new_len, depth > 65534u);
+    }
   };
   // the read must already be staged in curw
   auto new_contig = [&](uint32_t rid) {  // updaterefcount(..., resetcount = true, rev = false) + reorder.h:426-430,:601-612

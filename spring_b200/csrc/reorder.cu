@@ -35,8 +35,17 @@
 #include "chain_common.cuh"
 
 #ifndef SB_KEEP_HK
-#define SB_KEEP_HK 1  // pass 2 reuses the hashed key of a lane's first probe instead of cutting it out and hashing it again
+#define SB_KEEP_HK 0  // 1: pass 2 reuses the hashed key of a lane's first probe instead of hashing it again (measured: 1-3 % slower, visit 23)
 #endif
+#ifndef SB_PROBE_UNROLL
+#define SB_PROBE_UNROLL 4
+#endif
+#ifndef SB_OPAQUE_TID
+#define SB_OPAQUE_TID 0
+#endif
+#define SB_STR2(x) #x
+#define SB_STR(x) SB_STR2(x)
+#define SB_UNROLL(n) _Pragma(SB_STR(unroll n))
 
 namespace sb {
 
@@ -349,8 +358,10 @@ __device__ __forceinline__ bool chain_search(const ChainArgs &a, const uint64_t 
     const int n = (FAST_TAIL && (STATS ? a.fast_tail : 1)) ? (b < 2 ? (STATS ? a.batch0 : kBatch0) << b : 16) : (b < 4 ? 1 << b : 16);
     // ---- pass 1: bounds + filter bit for this lane's n probes (independent 4-byte loads) ----
     unsigned okm = 0, cand = 0;
+#if SB_KEEP_HK
     uint64_t hk_first = 0;  // hashed key of this lane's first probe: most batches have one probe per lane, and pass 2 needs it again
-#pragma unroll 4
+#endif
+    SB_UNROLL(SB_PROBE_UNROLL)
     for (int j = 0; j < n; j++) {
       const int s = S + sub + 8 * j;
       if (s >= s_lo && s < s_hi) {
@@ -362,12 +373,13 @@ __device__ __forceinline__ bool chain_search(const ChainArgs &a, const uint64_t 
         // early batches: the slot sector is requested together with the filter word, before the filter's answer is known
         // (no register is held for it): a filter positive then finds its slot in L2 instead of paying a second DRAM
         // round trip behind the first.  Costs one wasted sector per filter negative, so only where hits are likely.
-        if (b < (STATS ? a.prefetch_slots - 1 : kEarlyPrefetchBatches)) asm volatile("prefetch.global.L2 [%0];" ::"l"(d.slots + slot_home(hk, d.slot_shift)));
+        if ((STATS || kEarlyPrefetchBatches > 0) && b < (STATS ? a.prefetch_slots - 1 : kEarlyPrefetchBatches))
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(d.slots + slot_home(hk, d.slot_shift)));
         // the production instantiation (STATS = false) has the tuning knobs compiled in: L2 evict_last on the filter
         // words, slot prefetch, fast tail
         if ((STATS ? a.filter_hint : 1) ? filter_test_hint(d.filter, d.filter_words, hk, pol_keep) : filter_test(d.filter, d.filter_words, hk)) {
           cand |= 1u << j;
-          if (STATS ? (a.prefetch_slots > 0 && b >= a.prefetch_slots - 1) : b >= kEarlyPrefetchBatches) asm volatile("prefetch.global.L2 [%0];" ::"l"(d.slots + slot_home(hk, d.slot_shift)));
+          if (STATS ? (a.prefetch_slots > 0 && b >= a.prefetch_slots - 1) : (kEarlyPrefetchBatches == 0 || b >= kEarlyPrefetchBatches)) asm volatile("prefetch.global.L2 [%0];" ::"l"(d.slots + slot_home(hk, d.slot_shift)));
         }
       }
     }
@@ -463,7 +475,15 @@ __device__ bool find_unclaimed(const uint32_t *claimed, long long lo, long long 
 
 // shared memory of one chain, in uint64 words: ref and revref (W words + one zero word each, so that
 // window_key may read one word past the bitset), the staged read, Lp packed count columns
-__host__ __device__ inline size_t chain_smem_words(int W, int Lp) { return 3 * (size_t)W + 2 + (size_t)Lp; }
+// + the chain's cold state (ColdState: touched once per contig, kept out of the register file)
+__host__ __device__ inline size_t chain_smem_words(int W, int Lp) { return 3 * (size_t)W + 2 + (size_t)Lp + 4; }
+// Warp-uniform chain state that is read or written once per contig, not once per step: kept in shared memory (every lane
+// reads the same word -- a broadcast -- and writes the same value), so that it does not occupy six registers per lane for the
+// life of the kernel; the hot loops were rematerialising lane ids and shared-memory bases for want of them.
+struct ColdState {
+  int cursor, slice_lo;                                     // this chain's slice of the read ids still to seed from
+  uint32_t first_rid, prev, num_unmatched_1m, n_single;      // contig's first read; last read without a record; reorder.h:433-439; singletons logged
+};
 
 // WPB warps (= chains) per block, at least MINB blocks per SM: the register budget is the knob that
 // decides how many chains co-reside (run_reorder picks the configuration)
@@ -475,7 +495,15 @@ template <bool LOCKSTEP, int WPB, int MINB, int WT, bool STATS = true>
 __global__ void __launch_bounds__(WPB * 32, MINB) k_chains(ChainArgs a) {
   constexpr int kWarpsPerBlock = WPB;
   extern __shared__ __align__(16) uint64_t smem[];
+  // read once through volatile asm: the compiler otherwise re-reads %tid (S2R) and rebuilds lane / warp / shared-memory
+  // bases dozens of times in the hot loops rather than keep them in registers
+#if SB_OPAQUE_TID
+  uint32_t tid_once;
+  asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid_once));
+  const int lane = (int)(tid_once & 31u), wib = (int)(tid_once >> 5);
+#else
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+#endif
   const uint32_t cid = blockIdx.x * kWarpsPerBlock + wib;
   const int W = WT ? WT : a.W, Lp = WT ? 32 * WT : a.Lp;  // Lp = 32 W for every L (words_for)
   const int grp = lane / W, wig = lane - grp * W;  // scan_bin's lane layout
@@ -488,8 +516,12 @@ __global__ void __launch_bounds__(WPB * 32, MINB) k_chains(ChainArgs a) {
   int state = cid < a.num_chains ? ST_SEARCH : ST_DONE;
   int ref_len = 0, prev_unmatched = 0, left_search = 0, iter_started = 0, stop_searching = 0, batch = 0, batch_S = 0;
   long long ref_pos = 0, cur_read_pos = 0;
-  int cursor = -1, slice_lo = 0;  // read ids fit 31 bits (check_input)
-  uint32_t first_rid = 0, prev = 0, num_reads_thr = 0, num_unmatched_1m = 0, n_aligned = 0, n_single = 0, window_left = 0;
+  ColdState &cold = *reinterpret_cast<ColdState *>(cnt + Lp);
+  int &cursor = cold.cursor, &slice_lo = cold.slice_lo;  // read ids fit 31 bits (check_input)
+  uint32_t &first_rid = cold.first_rid, &prev = cold.prev, &num_unmatched_1m = cold.num_unmatched_1m, &n_single = cold.n_single;
+  cursor = -1; slice_lo = 0; first_rid = 0; prev = 0; num_unmatched_1m = 0; n_single = 0;
+  __syncwarp();
+  uint32_t num_reads_thr = 0, n_aligned = 0, window_left = 0;
   // statistics: c_issued / c_seq / c_slot are per-lane partial sums, c_cmp / c_unmatched / c_lost are
   // warp-uniform; 32-bit in registers, flushed to the 64-bit totals before they can wrap
   uint32_t c_unmatched = 0, c_lost = 0, c_issued = 0, c_seq = 0, c_cmp = 0, c_slot = 0;
@@ -843,22 +875,26 @@ __global__ void k_make_policies(unsigned long long *out) {
 
 // Chain logs -> one stream, chain after chain (what the merge of per-thread files gives,
 // encoder.h:386-423): record k of chain c lands at offset[c] + k.
+// Two passes: the scatter writes ONE 16-byte record per read at its (random) stream position -- one sector instead of four
+// (order, flag, pos, rev live in four arrays) -- and a coalesced pass splits the records into the arrays the encoder reads.
 __global__ void k_scatter_records(const uint4 *__restrict__ rec, uint32_t n, const uint32_t *__restrict__ off_aligned,
-                                  const uint32_t *__restrict__ off_single, uint32_t *order, uint8_t *flag, int64_t *pos, uint8_t *rev,
-                                  uint32_t *s_order) {
+                                  const uint32_t *__restrict__ off_single, uint4 *__restrict__ stream, uint32_t *s_order) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const uint4 r = rec[i];
   const uint32_t m = r.w >> 24, c = r.w & 0xFFFFFFu, k = r.z;
-  if (m & 4) {
-    s_order[off_single[c] + k] = i;
-  } else {
-    const uint32_t o = off_aligned[c] + k;
-    order[o] = i;
-    flag[o] = (m >> 1) & 1;
-    pos[o] = (int64_t)((unsigned long long)r.x | ((unsigned long long)r.y << 32));
-    rev[o] = (m & 1) ? 'r' : 'd';
-  }
+  if (m & 4) s_order[off_single[c] + k] = i;
+  else stream[off_aligned[c] + k] = make_uint4(r.x, r.y, i, m);
+}
+__global__ void k_unpack_records(const uint4 *__restrict__ stream, uint32_t n, const uint32_t *__restrict__ num_aligned, uint32_t *order,
+                                 uint8_t *flag, int64_t *pos, uint8_t *rev) {
+  uint32_t o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= n || o >= *num_aligned) return;  // the number of aligned records is still on the device (last entry of the scan)
+  const uint4 r = stream[o];
+  order[o] = r.z;
+  flag[o] = (r.w >> 1) & 1;
+  pos[o] = (int64_t)((unsigned long long)r.x | ((unsigned long long)r.y << 32));
+  rev[o] = (r.w & 1) ? 'r' : 'd';
 }
 
 }  // namespace
@@ -985,8 +1021,10 @@ void run_reorder(Ctx &c, const uint64_t *reads, const uint16_t *lens, uint32_t n
   need = tmp_bytes; cub::DeviceScan::ExclusiveSum(tmp, need, a.chain_aligned, off_aligned, (int)nslots + 1, st);
   need = tmp_bytes; cub::DeviceScan::ExclusiveSum(tmp, need, a.chain_single, off_single, (int)nslots + 1, st);
   c.launches += 2;
-  k_scatter_records<<<(n + 255) / 256, 256, 0, st>>>(a.rec, n, off_aligned, off_single, out.order, out.flag, out.pos, out.rev, out.s_order);
-  c.launches++;
+  uint4 *stream = c.pool.dev<uint4>("ro.stream", nn);
+  k_scatter_records<<<(n + 255) / 256, 256, 0, st>>>(a.rec, n, off_aligned, off_single, stream, out.s_order);
+  k_unpack_records<<<(n + 255) / 256, 256, 0, st>>>(stream, n, off_aligned + nslots, out.order, out.flag, out.pos, out.rev);
+  c.launches += 2;
   unsigned long long *h = c.pool.pin<unsigned long long>("ro.hsync", CTR_N + 4);
   SB_CUDA(cudaMemcpyAsync(h, a.ctr, CTR_N * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
   uint32_t *htot = reinterpret_cast<uint32_t *>(h + CTR_N);

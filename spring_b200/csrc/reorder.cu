@@ -38,10 +38,13 @@
 #define SB_KEEP_HK 0  // 1: pass 2 reuses the hashed key of a lane's first probe instead of hashing it again (measured: 1-3 % slower, visit 23)
 #endif
 #ifndef SB_PROBE_UNROLL
-#define SB_PROBE_UNROLL 4
-#endif
+#define SB_PROBE_UNROLL 1  // the probe loop is not unrolled: most batches have one probe per lane, and the kernel's code size costs instruction-cache
+#endif                     // misses (visit 24, k_chains ms on configs 2 / 3 / 5: unroll 4 15.6 / 191.0 / 227.5, unroll 1 15.5 / 190.0 / 212.6)
 #ifndef SB_OPAQUE_TID
-#define SB_OPAQUE_TID 0
+#define SB_OPAQUE_TID 1    // %tid is read once through volatile asm: lane / warp index stay in registers instead of being re-derived
+#endif
+#ifndef SB_SCAN_FAST
+#define SB_SCAN_FAST 1     // bins of <= 3 reads (ids inline in the slot) are verified by a straight-line pass without the big-bin machinery
 #endif
 #define SB_STR2(x) #x
 #define SB_STR(x) SB_STR2(x)
@@ -263,6 +266,39 @@ __device__ __forceinline__ bool scan_bin(const ChainArgs &a, const DictView &d, 
   if (WT) { leaders = 0; for (uint32_t q = 0; q < G; q++) leaders |= 1u << (q * (uint32_t)W); }  // a constant when W is
   const unsigned below = leaders & ((1u << (lane - wig)) - 1u);  // leaders of the groups before mine
   const uint64_t rw = rev ? shl_word(refsm, W, wig, 2 * s) : shr_word(refsm, W, wig, 2 * s);
+  if (SB_SCAN_FAST && bc <= 3 && bc <= G) {
+    // the usual bin: one to three reads, their ids came with the slot.  One pass, one candidate per lane group; none of
+    // the big-bin machinery (skip hints, MAX_SEARCH rank, bins[] access).
+    const bool mine = act && (uint32_t)grp < bc;
+    const uint32_t rid = grp == 0 ? r0 : grp == 1 ? r1 : r2;
+    uint64_t cw = 0;
+    int len = 0;
+    bool live = false;
+    if (mine) {
+      cw = __ldg(a.reads + (size_t)rid * W + wig);
+      len = __ldg(a.lens + rid);
+      live = !is_claimed(a.claimed, rid);
+    }
+    int h = 0;
+    if (live) {
+      int lo, hi;
+      if (!rev) { lo = 0; hi = 2 * min(ref_len - s, len); }
+      else { lo = 2 * s; hi = 2 * min(ref_len + s, len); }
+      h = __popcll((rw ^ cw) & range_mask(wig, lo, hi));
+    }
+    for (int o = 1; o < W; o <<= 1) {  // sum over the group's W lanes, into its leader
+      const int t2 = __shfl_down_sync(FULL, h, o);
+      if (wig + o < W) h += t2;
+    }
+    const unsigned pm = __ballot_sync(FULL, live && h <= kThreshReorder) & leaders;
+    if (STATS) {
+      const unsigned em = __ballot_sync(FULL, live) & leaders;
+      compares += pm ? __popc(em & ((2u << (__ffs(pm) - 1)) - 1u)) : __popc(em);
+    }
+    if (!pm) return false;
+    rid_out = __shfl_sync(FULL, rid, __ffs(pm) - 1);
+    return true;
+  }
   int live_before = 0;
   // big bins (repeats): skip the prefix of entries already known to be claimed, and extend that
   // hint when this scan meets more of them -- claims only grow, so the hint never hides a live read

@@ -7,9 +7,6 @@ namespace chain {
 
 constexpr unsigned FULL = 0xFFFFFFFFu;
 constexpr const char *kChainCfgDefault = "8x4";  // 32 chains per SM (64 registers, a few spills) beat 24 spill-free ones
-// batches of a search whose slot sectors are prefetched before the filter answers (SPRING_B200_PREFETCH = 1 + this in the
-// tunable instantiation: 0 no prefetch at all, 1 filter positives only, 2 all probes of batch 0, 3 of batches 0 and 1, ...)
-constexpr int kEarlyPrefetchBatches = 0;
 // probes per lane in the first batch of a free-running search (fast tail): batches cover 8 k, 16 k, then all remaining shifts
 constexpr int kBatch0 = 1;
 enum { ST_SEARCH = 0, ST_NEWREAD = 1, ST_DONE = 2 };
@@ -29,7 +26,7 @@ struct ChainArgs {
   uint32_t G;            // scan_bin: candidates verified per pass = 32 / W
   unsigned leader_mask;  // scan_bin: lanes g * W, g < G
   int generic_update;    // debugging aid: always use the per-column update_ref
-  int prefetch_slots;    // 1: pass 1 of a batch prefetches the slot of every filter positive into L2; 1 + k: and of EVERY probe in the first k batches
+  int prefetch_slots;    // pass 1 of a batch prefetches the slot of every filter positive into L2
   uint64_t pol_keep, pol_stream;  // L2 cache policies (evict_last for the filter words, evict_first for slot sectors)
   int fast_tail;         // free-running chains: batches of 8, 16, then all remaining shifts
   int batch0;            // ... times this many (tunable instantiation; kBatch0 in production)

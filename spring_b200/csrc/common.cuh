@@ -192,6 +192,11 @@ __device__ __forceinline__ bool filter_test_hint(const uint32_t *filter, uint32_
   asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(w) : "l"(filter + filter_word(hk, nwords)), "l"(pol));
   return (w & b) == b;
 }
+__device__ __forceinline__ uint32_t filter_load_hint(const uint32_t *filter, uint32_t nwords, uint64_t hk, uint64_t pol) {
+  uint32_t w;
+  asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(w) : "l"(filter + filter_word(hk, nwords)), "l"(pol));
+  return w;
+}
 // L2 (.cg) load: `live` is updated by other SMs between rounds, L1 must not serve it
 __device__ __forceinline__ DictSlot load_slot(const DictSlot *p) {
   const uint4 v = __ldcg(reinterpret_cast<const uint4 *>(p));

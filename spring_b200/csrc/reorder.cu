@@ -34,8 +34,8 @@
 #include <cub/cub.cuh>
 #include "chain_common.cuh"
 
-#ifndef SB_KEEP_HK
-#define SB_KEEP_HK 0  // 1: pass 2 reuses the hashed key of a lane's first probe instead of hashing it again (measured: 1-3 % slower, visit 23)
+#ifndef SB_PROBE_GROUP
+#define SB_PROBE_GROUP 4   // batches with more than one probe per lane: filter words requested in groups of this many before any is examined
 #endif
 #ifndef SB_PROBE_UNROLL
 #define SB_PROBE_UNROLL 1  // the probe loop is not unrolled: most batches have one probe per lane, and the kernel's code size costs instruction-cache
@@ -43,8 +43,11 @@
 #ifndef SB_OPAQUE_TID
 #define SB_OPAQUE_TID 1    // %tid is read once through volatile asm: lane / warp index stay in registers instead of being re-derived
 #endif
-#ifndef SB_SCAN_FAST
-#define SB_SCAN_FAST 1     // bins of <= 3 reads (ids inline in the slot) are verified by a straight-line pass without the big-bin machinery
+#ifndef SB_COUNT_UNROLL
+#define SB_COUNT_UNROLL 1  // count pass of update_ref_fast: straight-line code for the WT chunks (1) or the rolled loop (0)
+#endif
+#ifndef SB_NOINLINE_FIND
+#define SB_NOINLINE_FIND 0 // find_unclaimed as a real function call (cold path; smaller kernel)
 #endif
 #define SB_STR2(x) #x
 #define SB_STR(x) SB_STR2(x)
@@ -189,7 +192,7 @@ __device__ __forceinline__ void update_ref_fast(uint64_t *ref, uint64_t *revref,
   // A0 G1 C2 T3 -> field 0, 3, 1, 2 = (0x9C >> 2 code) & 3.
   const int sh2 = 2 * (lane & 15);
   const bool hi_half = (lane & 16) != 0;
-  if (WT) {
+  if (WT && SB_COUNT_UNROLL) {
     uint64_t v[WT ? WT : 1];
 #pragma unroll
     for (int cc = 0; cc < WT; cc++) {
@@ -266,39 +269,6 @@ __device__ __forceinline__ bool scan_bin(const ChainArgs &a, const DictView &d, 
   if (WT) { leaders = 0; for (uint32_t q = 0; q < G; q++) leaders |= 1u << (q * (uint32_t)W); }  // a constant when W is
   const unsigned below = leaders & ((1u << (lane - wig)) - 1u);  // leaders of the groups before mine
   const uint64_t rw = rev ? shl_word(refsm, W, wig, 2 * s) : shr_word(refsm, W, wig, 2 * s);
-  if (SB_SCAN_FAST && bc <= 3 && bc <= G) {
-    // the usual bin: one to three reads, their ids came with the slot.  One pass, one candidate per lane group; none of
-    // the big-bin machinery (skip hints, MAX_SEARCH rank, bins[] access).
-    const bool mine = act && (uint32_t)grp < bc;
-    const uint32_t rid = grp == 0 ? r0 : grp == 1 ? r1 : r2;
-    uint64_t cw = 0;
-    int len = 0;
-    bool live = false;
-    if (mine) {
-      cw = __ldg(a.reads + (size_t)rid * W + wig);
-      len = __ldg(a.lens + rid);
-      live = !is_claimed(a.claimed, rid);
-    }
-    int h = 0;
-    if (live) {
-      int lo, hi;
-      if (!rev) { lo = 0; hi = 2 * min(ref_len - s, len); }
-      else { lo = 2 * s; hi = 2 * min(ref_len + s, len); }
-      h = __popcll((rw ^ cw) & range_mask(wig, lo, hi));
-    }
-    for (int o = 1; o < W; o <<= 1) {  // sum over the group's W lanes, into its leader
-      const int t2 = __shfl_down_sync(FULL, h, o);
-      if (wig + o < W) h += t2;
-    }
-    const unsigned pm = __ballot_sync(FULL, live && h <= kThreshReorder) & leaders;
-    if (STATS) {
-      const unsigned em = __ballot_sync(FULL, live) & leaders;
-      compares += pm ? __popc(em & ((2u << (__ffs(pm) - 1)) - 1u)) : __popc(em);
-    }
-    if (!pm) return false;
-    rid_out = __shfl_sync(FULL, rid, __ffs(pm) - 1);
-    return true;
-  }
   int live_before = 0;
   // big bins (repeats): skip the prefix of entries already known to be claimed, and extend that
   // hint when this scan meets more of them -- claims only grow, so the hint never hides a live read
@@ -392,31 +362,50 @@ __device__ __forceinline__ bool chain_search(const ChainArgs &a, const uint64_t 
     // (SPRING_B200_FAST_TAIL=0 restores the oracle's batches: -6.5 % kernel time on config 5's contig-start-heavy input, neutral
     // on configs 2 and 3; profiles/r02_chains2_experiment.txt)
     const int n = (FAST_TAIL && (STATS ? a.fast_tail : 1)) ? (b < 2 ? (STATS ? a.batch0 : kBatch0) << b : 16) : (b < 4 ? 1 << b : 16);
-    // ---- pass 1: bounds + filter bit for this lane's n probes (independent 4-byte loads) ----
+    // ---- pass 1: bounds + filter bit for this lane's n probes ---------------------------------------------------------
+    // The production instantiation (STATS = false) has the tuning knobs compiled in: L2 evict_last on the filter words,
+    // slot prefetch for filter positives, fast tail.
     unsigned okm = 0, cand = 0;
-#if SB_KEEP_HK
-    uint64_t hk_first = 0;  // hashed key of this lane's first probe: most batches have one probe per lane, and pass 2 needs it again
-#endif
-    SB_UNROLL(SB_PROBE_UNROLL)
-    for (int j = 0; j < n; j++) {
-      const int s = S + sub + 8 * j;
-      if (s >= s_lo && s < s_hi) {
-        okm |= 1u << j;
-        const uint64_t hk = mix64(window_key(src, kbase + kstep * s, d.key_bits));
-#if SB_KEEP_HK
-        if (j == 0) hk_first = hk;
-#endif
-        // early batches: the slot sector is requested together with the filter word, before the filter's answer is known
-        // (no register is held for it): a filter positive then finds its slot in L2 instead of paying a second DRAM
-        // round trip behind the first.  Costs one wasted sector per filter negative, so only where hits are likely.
-        if ((STATS || kEarlyPrefetchBatches > 0) && b < (STATS ? a.prefetch_slots - 1 : kEarlyPrefetchBatches))
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(d.slots + slot_home(hk, d.slot_shift)));
-        // the production instantiation (STATS = false) has the tuning knobs compiled in: L2 evict_last on the filter
-        // words, slot prefetch, fast tail
-        if ((STATS ? a.filter_hint : 1) ? filter_test_hint(d.filter, d.filter_words, hk, pol_keep) : filter_test(d.filter, d.filter_words, hk)) {
-          cand |= 1u << j;
-          if (STATS ? (a.prefetch_slots > 0 && b >= a.prefetch_slots - 1) : (kEarlyPrefetchBatches == 0 || b >= kEarlyPrefetchBatches)) asm volatile("prefetch.global.L2 [%0];" ::"l"(d.slots + slot_home(hk, d.slot_shift)));
+    const bool hint = STATS ? a.filter_hint != 0 : true, pf = STATS ? a.prefetch_slots != 0 : true;
+    if (SB_PROBE_GROUP <= 1 || n == 1) {
+      SB_UNROLL(SB_PROBE_UNROLL)
+      for (int j = 0; j < n; j++) {
+        const int s = S + sub + 8 * j;
+        if (s >= s_lo && s < s_hi) {
+          okm |= 1u << j;
+          const uint64_t hk = mix64(window_key(src, kbase + kstep * s, d.key_bits));
+          if (hint ? filter_test_hint(d.filter, d.filter_words, hk, pol_keep) : filter_test(d.filter, d.filter_words, hk)) {
+            cand |= 1u << j;
+            if (pf) asm volatile("prefetch.global.L2 [%0];" ::"l"(d.slots + slot_home(hk, d.slot_shift)));
+          }
         }
+      }
+    } else {
+      // later batches (2 .. 16 probes per lane; a dead end walks them all): the filter words of SB_PROBE_GROUP probes are
+      // requested back to back and examined afterwards -- one memory round trip per group instead of one per probe
+      for (int j0 = 0; j0 < n; j0 += SB_PROBE_GROUP) {
+        uint32_t fw[SB_PROBE_GROUP], fb[SB_PROBE_GROUP], hm[SB_PROBE_GROUP];
+        unsigned okg = 0;
+#pragma unroll
+        for (int u = 0; u < SB_PROBE_GROUP; u++) {
+          const int s = S + sub + 8 * (j0 + u);
+          fw[u] = 0; fb[u] = 1; hm[u] = 0;
+          if (j0 + u < n && s >= s_lo && s < s_hi) {
+            okg |= 1u << u;
+            const uint64_t hk = mix64(window_key(src, kbase + kstep * s, d.key_bits));
+            fb[u] = filter_bits(hk);
+            hm[u] = slot_home(hk, d.slot_shift);
+            fw[u] = hint ? filter_load_hint(d.filter, d.filter_words, hk, pol_keep) : __ldg(d.filter + filter_word(hk, d.filter_words));
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < SB_PROBE_GROUP; u++) {
+          if ((fw[u] & fb[u]) == fb[u]) {  // never true for a probe that was not issued (fw = 0, fb = 1)
+            cand |= 1u << (j0 + u);
+            if (pf) asm volatile("prefetch.global.L2 [%0];" ::"l"(d.slots + hm[u]));
+          }
+        }
+        okm |= okg << j0;
       }
     }
     if (STATS) probes_issued += (unsigned)__popc(okm);  // per-lane partial sum, reduced when the chain ends
@@ -428,11 +417,7 @@ __device__ __forceinline__ bool chain_search(const ChainArgs &a, const uint64_t 
         const int j = __ffs(cand) - 1;
         cand &= cand - 1;
         const int s = S + sub + 8 * j;
-#if SB_KEEP_HK
-        const uint64_t hk = j == 0 ? hk_first : mix64(window_key(src, kbase + kstep * s, d.key_bits));
-#else
         const uint64_t hk = mix64(window_key(src, kbase + kstep * s, d.key_bits));
-#endif
         uint32_t h = slot_home(hk, d.slot_shift);
         if (STATS) slot_probes++;
         for (;;) {  // ordered probing: every key between the home slot and hk's own slot is smaller than hk
@@ -487,7 +472,11 @@ __device__ __forceinline__ uint4 make_rec(long long pos, uint32_t k, uint32_t ch
 }
 
 // Highest unclaimed read in [lo, cursor] (reorder.h:576-592), 32 bitmap words per step.
+#if SB_NOINLINE_FIND
+__device__ __noinline__ bool find_unclaimed(const uint32_t *claimed, long long lo, long long cursor, int lane, uint32_t &rid) {
+#else
 __device__ bool find_unclaimed(const uint32_t *claimed, long long lo, long long cursor, int lane, uint32_t &rid) {
+#endif
   if (cursor < lo) return false;
   const long long whi = cursor >> 5, wlo = lo >> 5;
   for (long long wbase = whi; wbase >= wlo; wbase -= 32) {

@@ -501,13 +501,14 @@ __device__ bool find_unclaimed(const uint32_t *claimed, long long lo, long long 
 // shared memory of one chain, in uint64 words: ref and revref (W words + one zero word each, so that
 // window_key may read one word past the bitset), the staged read, Lp packed count columns
 // + the chain's cold state (ColdState: touched once per contig, kept out of the register file)
-__host__ __device__ inline size_t chain_smem_words(int W, int Lp) { return 3 * (size_t)W + 2 + (size_t)Lp + 4; }
+__host__ __device__ inline size_t chain_smem_words(int W, int Lp) { return 3 * (size_t)W + 2 + (size_t)Lp + 4; }  // sizeof(ColdState) = 32
 // Warp-uniform chain state that is read or written once per contig, not once per step: kept in shared memory (every lane
 // reads the same word -- a broadcast -- and writes the same value), so that it does not occupy six registers per lane for the
 // life of the kernel; the hot loops were rematerialising lane ids and shared-memory bases for want of them.
 struct ColdState {
   int cursor, slice_lo;                                     // this chain's slice of the read ids still to seed from
   uint32_t first_rid, prev, num_unmatched_1m, n_single;      // contig's first read; last read without a record; reorder.h:433-439; singletons logged
+  int first_len, pad;                                        // length of the contig's first read (the left search starts from it again)
 };
 
 // WPB warps (= chains) per block, at least MINB blocks per SM: the register budget is the knob that
@@ -591,8 +592,8 @@ __global__ void __launch_bounds__(WPB * 32, MINB) k_chains(ChainArgs a) {
     }
   };
   // the read must already be staged in curw
-  auto new_contig = [&](uint32_t rid) {  // updaterefcount(..., resetcount = true, rev = false) + reorder.h:426-430,:601-612
-    const int len = __ldg(a.lens + rid);
+  auto new_contig = [&](uint32_t rid, int len) {  // updaterefcount(..., resetcount = true, rev = false) + reorder.h:426-430,:601-612
+    cold.first_len = len;
     upd(0, 0, 0, len, false, len, 0);
     ref_len = len; ref_pos = 0; cur_read_pos = 0;
     prev_unmatched = 1; first_rid = rid; prev = rid; left_search = 0;
@@ -618,8 +619,9 @@ __global__ void __launch_bounds__(WPB * 32, MINB) k_chains(ChainArgs a) {
         if (sidx != 0xFFFFFFFFu) atomicSub(&a.dict[lane].slots[sidx].live, 1u);
       }
       c_unmatched++;
+      const int first_len = __ldg(a.lens + first);
       stage_read(first);
-      new_contig(first);
+      new_contig(first, first_len);
     }
   }
   unsigned long long cy_search = 0, cy_wait_a = 0, cy_commit = 0, cy_wait_b = 0;
@@ -698,7 +700,7 @@ __global__ void __launch_bounds__(WPB * 32, MINB) k_chains(ChainArgs a) {
           if (!left_search) {
             left_search = 1;
             stage_read(first_rid);
-            const int len = __ldg(a.lens + first_rid);
+            const int len = cold.first_len;
             upd(0, 0, 0, len, true, len, 0);
             ref_len = len; ref_pos = 0; cur_read_pos = 0;
             iter_started = 0;
@@ -710,12 +712,23 @@ __global__ void __launch_bounds__(WPB * 32, MINB) k_chains(ChainArgs a) {
       } else {  // ST_NEWREAD, reorder.h:576-612
         uint32_t j = 0;
         bool got = false;
-        while (find_unclaimed(a.claimed, slice_lo, cursor, lane, j)) {
+        // as for a matched read, the loads the new contig needs (row, length, slot indices) travel under the claim's round trip
+        uint32_t seed_sidx = 0xFFFFFFFFu;
+        uint64_t seed_word = 0;
+        int seed_len = 0;
+        auto claim_seed = [&](uint32_t r) {
           unsigned old = 0;
-          if (lane == 0) old = atomicOr(a.claimed + (j >> 5), 1u << (j & 31));
+          if (lane == 0) old = atomicOr(a.claimed + (r >> 5), 1u << (r & 31));
+          if (lane < W) seed_word = __ldg(a.reads + (size_t)r * W + lane);
+          seed_len = __ldg(a.lens + r);
+          if (lane < kNumDict) seed_sidx = __ldg(a.dict[lane].slot_of_read + r);
           old = __shfl_sync(FULL, old, 0);
+          return !((old >> (r & 31)) & 1u);
+        };
+        while (find_unclaimed(a.claimed, slice_lo, cursor, lane, j)) {
+          const bool mine = claim_seed(j);
           cursor = (int)j - 1;
-          if (!((old >> (j & 31)) & 1u)) { got = true; break; }
+          if (mine) { got = true; break; }
         }
         // Own slice exhausted: instead of idling until the slowest chain is done, seed the next contig from
         // the slice of a randomly chosen other chain (the reference's threads all pick from ONE pool,
@@ -729,10 +742,7 @@ __global__ void __launch_bounds__(WPB * 32, MINB) k_chains(ChainArgs a) {
             const long long vlo = (long long)v * a.per;
             const long long vhi = v == a.num_chains - 1 ? (long long)a.N - 1 : vlo + a.per - 1;
             if (!find_unclaimed(a.claimed, vlo, vhi, lane, j)) continue;
-            unsigned old = 0;
-            if (lane == 0) old = atomicOr(a.claimed + (j >> 5), 1u << (j & 31));
-            old = __shfl_sync(FULL, old, 0);
-            if (!((old >> (j & 31)) & 1u)) got = true;
+            if (claim_seed(j)) got = true;
           }
         }
         if (prev_unmatched) {
@@ -740,13 +750,11 @@ __global__ void __launch_bounds__(WPB * 32, MINB) k_chains(ChainArgs a) {
           n_single++;
         }
         if (got) {
-          if (lane < kNumDict) {
-            const uint32_t sidx = __ldg(a.dict[lane].slot_of_read + j);
-            if (sidx != 0xFFFFFFFFu) atomicSub(&a.dict[lane].slots[sidx].live, 1u);
-          }
+          if (lane < kNumDict && seed_sidx != 0xFFFFFFFFu) atomicSub(&a.dict[lane].slots[seed_sidx].live, 1u);
           c_unmatched++;
-          stage_read(j);
-          new_contig(j);
+          if (lane < W) curw[lane] = seed_word;
+          __syncwarp();
+          new_contig(j, seed_len);
         } else {
           prev_unmatched = 0;
           state = ST_DONE;
@@ -839,7 +847,7 @@ __global__ void __launch_bounds__(WPB * 32, MINB) k_chains(ChainArgs a) {
         num_unmatched_1m++;
         if (!left_search) {
           left_search = 1;
-          const int len = __ldg(a.lens + first_rid);
+          const int len = cold.first_len;
           upd(0, 0, 0, len, true, len, 0);
           ref_len = len; ref_pos = 0; cur_read_pos = 0;
           iter_started = 0; batch = 0; batch_S = 0;
@@ -857,7 +865,7 @@ __global__ void __launch_bounds__(WPB * 32, MINB) k_chains(ChainArgs a) {
           if (prev_unmatched) n_single++;
           cursor = (int)j - 1;
           c_unmatched++;
-          new_contig(j);
+          new_contig(j, __ldg(a.lens + j));
         } else {
           c_lost++;
         }

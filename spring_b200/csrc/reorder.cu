@@ -163,13 +163,9 @@ __device__ __noinline__ void update_ref(uint64_t *ref, uint64_t *revref, const u
 // pass was the largest single block of the kernel, 47 instructions per 32 columns with its bounds branches; now ~20).
 // saturating: some column of this contig may have reached 65535 (more than 65534 reads folded in since the counts were
 // reset) -- only then is the per-field saturation check of count_add needed.
-// ref / cnt: the window as it is; ref_d / revref_d / cnt_d: where the updated window goes -- the same arrays (in place: all
-// sources are read before anything is written), or the chain's other set of buffers when the update runs ahead of the
-// claim that justifies it (free-running schedule) and may have to be dropped.
 template <int WT>
-__device__ __forceinline__ void update_ref_fast(const uint64_t *ref, uint64_t *curw, const uint64_t *cnt, uint64_t *ref_d, uint64_t *revref_d,
-                                                uint64_t *cnt_d, int Wrt, int lane, int old_len, int delta, int cs, int cur_len, bool rev,
-                                                int new_len, bool saturating) {
+__device__ __forceinline__ void update_ref_fast(uint64_t *ref, uint64_t *revref, uint64_t *curw, uint64_t *cnt, int Wrt, int lane,
+                                                int old_len, int delta, int cs, int cur_len, bool rev, int new_len, bool saturating) {
   const int W = WT ? WT : Wrt;
   if (rev) {
     uint64_t o = 0;
@@ -213,7 +209,7 @@ __device__ __forceinline__ void update_ref_fast(const uint64_t *ref, uint64_t *c
       const int fsh = (int)((0x9Cu >> (2 * code)) & 3u) << 4;
       if (!saturating) v[cc] += (uint64_t)(covered ? 1u : 0u) << fsh;
       else if (covered && ((v[cc] >> fsh) & 0xFFFFull) != 0xFFFFull) v[cc] += 1ull << fsh;  // counts saturate at 65535 (count_add)
-      if (i < new_len) cnt_d[i] = v[cc];
+      if (i < new_len) cnt[i] = v[cc];
     }
   } else {
     const int nchunks = (new_len + 31) >> 5;
@@ -226,7 +222,7 @@ __device__ __forceinline__ void update_ref_fast(const uint64_t *ref, uint64_t *c
       const bool covered = (unsigned)(i - cs) < (unsigned)cur_len;
       const int fsh = (int)((0x9Cu >> (2 * code)) & 3u) << 4;
       if (covered && ((v >> fsh) & 0xFFFFull) != 0xFFFFull) v += 1ull << fsh;
-      if (i < new_len) cnt_d[i] = v;
+      if (i < new_len) cnt[i] = v;
     }
   }
   uint64_t nw = 0, mm = 0;
@@ -239,7 +235,7 @@ __device__ __forceinline__ void update_ref_fast(const uint64_t *ref, uint64_t *c
   while (mm) {
     const int bp = __ffsll((long long)mm) - 1;
     mm &= mm - 1;
-    const uint64_t v = cnt_d[(lane << 5) + (bp >> 1)];
+    const uint64_t v = cnt[(lane << 5) + (bp >> 1)];
     const uint32_t f0 = (uint32_t)v & 0xFFFFu, f1 = (uint32_t)(v >> 16) & 0xFFFFu;
     const uint32_t f2 = (uint32_t)(v >> 32) & 0xFFFFu, f3 = (uint32_t)(v >> 48);
     uint32_t mx = f0, code = 0;  // first strict maximum over rows A,C,T,G (reorder.h:204-212) -> codes 0,2,3,1
@@ -248,35 +244,9 @@ __device__ __forceinline__ void update_ref_fast(const uint64_t *ref, uint64_t *c
     if (f3 > mx) { mx = f3; code = 1; }
     nw = (nw & ~(3ull << bp)) | ((uint64_t)code << bp);
   }
-  if (lane < W) ref_d[lane] = nw;
+  if (lane < W) ref[lane] = nw;
   __syncwarp();
-  if (lane < W) revref_d[lane] = revcomp_word(ref_d, W, new_len, lane);
-  __syncwarp();
-}
-
-// The window of a contig that starts (or starts its left search) with the read staged in curw: what update_ref_fast
-// does for old_len = 0 -- counts = the read's bases, ref = the read (reverse-complemented for the left search),
-// revref = its reverse complement -- as a small routine of its own: it runs once or twice per contig, from three places,
-// and is kept out of line so that the hot loop's code stays small.
-__device__ __noinline__ void reset_ref(uint64_t *ref, uint64_t *revref, uint64_t *curw, uint64_t *cnt, int W, int lane, int len, bool rev) {
-  if (rev) {
-    uint64_t o = 0;
-    if (lane < W) o = revcomp_word(curw, W, len, lane);
-    __syncwarp();
-    if (lane < W) curw[lane] = o;
-    __syncwarp();
-  }
-  const int sh2 = 2 * (lane & 15);
-  const bool hi_half = (lane & 16) != 0;
-  for (int cc = 0; (cc << 5) < len; cc++) {
-    const int i = (cc << 5) + lane;
-    const uint2 bw = reinterpret_cast<const uint2 *>(curw)[cc];
-    const uint32_t code = ((hi_half ? bw.y : bw.x) >> sh2) & 3u;
-    if (i < len) cnt[i] = 1ull << ((int)((0x9Cu >> (2 * code)) & 3u) << 4);
-  }
-  if (lane < W) ref[lane] = curw[lane] & range_mask(lane, 0, 2 * len);
-  __syncwarp();
-  if (lane < W) revref[lane] = revcomp_word(ref, W, len, lane);
+  if (lane < W) revref[lane] = revcomp_word(ref, W, new_len, lane);
   __syncwarp();
 }
 
@@ -291,7 +261,7 @@ __device__ __noinline__ void reset_ref(uint64_t *ref, uint64_t *revref, uint64_t
 template <int WT, bool STATS>
 __device__ __forceinline__ bool scan_bin(const ChainArgs &a, const DictView &d, uint32_t bs, uint32_t bc, uint32_t r0, uint32_t r1, uint32_t r2,
                          const uint64_t *refsm, bool rev, int s, int ref_len, int lane, int grp, int wig, uint32_t &rid_out,
-                         uint64_t &word_out, int &len_out, uint32_t &compares) {
+                         uint32_t &compares) {
   const int W = WT ? WT : a.W;  // WT > 0: words per read known at compile time (index arithmetic folds)
   const uint32_t G = WT ? 32u / (uint32_t)(WT ? WT : 1) : a.G;
   const bool act = (uint32_t)grp < G;
@@ -346,9 +316,6 @@ __device__ __forceinline__ bool scan_bin(const ChainArgs &a, const DictView &d, 
     if (pm) {
       const int wl = __ffs(pm) - 1;
       rid_out = __shfl_sync(FULL, rid, wl);
-      // the winner's row sits in its group's lanes: lane w < W takes word w (the update needs it; no second fetch)
-      word_out = __shfl_sync(FULL, cw, (wl + lane) & 31);
-      len_out = __shfl_sync(FULL, len, wl);
       if (STATS) compares += __popc(em & ((2u << wl) - 1u));
       return true;
     }
@@ -375,8 +342,8 @@ __device__ __forceinline__ bool scan_bin(const ChainArgs &a, const DictView &d, 
 // cannot turn productive later -- same result as a full search, see oracle/spring_oracle.c).
 template <int WT, bool FAST_TAIL, bool STATS>
 __device__ __forceinline__ bool chain_search(const ChainArgs &a, const uint64_t *ref, const uint64_t *revref, int ref_len, int lane, int grp,
-                             int wig, int b, int S, uint32_t &prop_rid, int &prop_shift, int &prop_rev, uint64_t &prop_word, int &prop_len,
-                             uint32_t &probes_issued, uint32_t &probes_seq, uint32_t &compares, uint32_t &slot_probes) {
+                             int wig, int b, int S, uint32_t &prop_rid, int &prop_shift, int &prop_rev, uint32_t &probes_issued,
+                             uint32_t &probes_seq, uint32_t &compares, uint32_t &slot_probes) {
   const int W = WT ? WT : a.W;
   const int kind = lane & 3, rev = kind >> 1, sub = lane >> 2;
   const DictView &d = a.dict[kind & 1];
@@ -474,8 +441,7 @@ __device__ __forceinline__ bool chain_search(const ChainArgs &a, const uint64_t 
       const uint32_t r0 = __shfl_sync(FULL, cur_r0, owner), r1 = __shfl_sync(FULL, cur_r1, owner), r2 = __shfl_sync(FULL, cur_r2, owner);
       const DictView &pd = a.dict[pk & 1];
       uint32_t rid;
-      if (scan_bin<WT, STATS>(a, pd, mb, mc, r0, r1, r2, (pk >> 1) ? revref : ref, pk >> 1, ps, ref_len, lane, grp, wig, rid, prop_word, prop_len,
-                              compares)) {
+      if (scan_bin<WT, STATS>(a, pd, mb, mc, r0, r1, r2, (pk >> 1) ? revref : ref, pk >> 1, ps, ref_len, lane, grp, wig, rid, compares)) {
         prop_rid = rid; prop_shift = ps; prop_rev = pk >> 1; found_p = p;
         break;
       }
@@ -532,22 +498,17 @@ __device__ bool find_unclaimed(const uint32_t *claimed, long long lo, long long 
   return false;
 }
 
-// shared memory of one chain, in uint64 words: two sets of ref and revref (W words + one zero word each, so that
-// window_key may read one word past the bitset), the staged read, two sets of Lp packed count columns
+// shared memory of one chain, in uint64 words: ref and revref (W words + one zero word each, so that
+// window_key may read one word past the bitset), the staged read, Lp packed count columns
 // + the chain's cold state (ColdState: touched once per contig, kept out of the register file)
-// Two sets of {ref, revref, counts}: a free-running chain folds a matched read into the OTHER set while the claim of that
-// read is still in flight and switches sets when the claim succeeds (a lost claim costs the wasted update, nothing to undo).
-__host__ __device__ inline size_t chain_smem_words(int W, int Lp) { return 5 * (size_t)W + 4 + 2 * (size_t)Lp + 6; }  // sizeof(ColdState) = 48
+__host__ __device__ inline size_t chain_smem_words(int W, int Lp) { return 3 * (size_t)W + 2 + (size_t)Lp + 4; }  // sizeof(ColdState) = 32
 // Warp-uniform chain state that is read or written once per contig, not once per step: kept in shared memory (every lane
 // reads the same word -- a broadcast -- and writes the same value), so that it does not occupy six registers per lane for the
 // life of the kernel; the hot loops were rematerialising lane ids and shared-memory bases for want of them.
 struct ColdState {
   int cursor, slice_lo;                                     // this chain's slice of the read ids still to seed from
   uint32_t first_rid, prev, num_unmatched_1m, n_single;      // contig's first read; last read without a record; reorder.h:433-439; singletons logged
-  int first_len;                                             // length of the contig's first read (the left search starts from it again)
-  uint32_t n_aligned;                                        // records this chain has logged
-  long long ref_pos;                                         // position of the window in the contig (once per step, like n_aligned and
-  uint32_t window_left, pad;                                 // the stop window's countdown: one shared-memory access instead of a register each)
+  int first_len, pad;                                        // length of the contig's first read (the left search starts from it again)
 };
 
 // WPB warps (= chains) per block, at least MINB blocks per SM: the register budget is the knob that
@@ -573,26 +534,20 @@ __global__ void __launch_bounds__(WPB * 32, MINB) k_chains(ChainArgs a) {
   const int W = WT ? WT : a.W, Lp = WT ? 32 * WT : a.Lp;  // Lp = 32 W for every L (words_for)
   const int grp = lane / W, wig = lane - grp * W;  // scan_bin's lane layout
   const size_t per_chain = chain_smem_words(W, Lp);
-  uint64_t *const cbase = smem + wib * per_chain;
-  uint64_t *ref = cbase, *revref = ref + W + 1;   // the current set; the other one sits 2 W + 2 words (counts: Lp words) further
-  uint64_t *const curw = cbase + 4 * W + 4;
+  uint64_t *ref = smem + wib * per_chain, *revref = ref + W + 1, *curw = revref + W + 1;
   uint64_t *cnt = curw + W;  // one word per column: four u16 counts {A,C,T,G}
-  if (lane < 4) cbase[lane * (W + 1) + W] = 0ull;  // the zero word behind each of the four bitsets
+  if (lane == 0) { ref[W] = 0ull; revref[W] = 0ull; }
   __syncwarp();
 
   int state = cid < a.num_chains ? ST_SEARCH : ST_DONE;
   int ref_len = 0, prev_unmatched = 0, left_search = 0, iter_started = 0, stop_searching = 0, batch = 0, batch_S = 0;
-  long long cur_read_pos = 0;
-  ColdState &cold = *reinterpret_cast<ColdState *>(cnt + 2 * Lp);
+  long long ref_pos = 0, cur_read_pos = 0;
+  ColdState &cold = *reinterpret_cast<ColdState *>(cnt + Lp);
   int &cursor = cold.cursor, &slice_lo = cold.slice_lo;  // read ids fit 31 bits (check_input)
   uint32_t &first_rid = cold.first_rid, &prev = cold.prev, &num_unmatched_1m = cold.num_unmatched_1m, &n_single = cold.n_single;
   cursor = -1; slice_lo = 0; first_rid = 0; prev = 0; num_unmatched_1m = 0; n_single = 0;
   __syncwarp();
-  long long &ref_pos = cold.ref_pos;
-  uint32_t &n_aligned = cold.n_aligned, &window_left = cold.window_left;
-  ref_pos = 0; n_aligned = 0; window_left = 0;
-  __syncwarp();
-  uint32_t num_reads_thr = 0;
+  uint32_t num_reads_thr = 0, n_aligned = 0, window_left = 0;
   // statistics: c_issued / c_seq / c_slot are per-lane partial sums, c_cmp / c_unmatched / c_lost are
   // warp-uniform; 32-bit in registers, flushed to the 64-bit totals before they can wrap
   uint32_t c_unmatched = 0, c_lost = 0, c_issued = 0, c_seq = 0, c_cmp = 0, c_slot = 0;
@@ -632,10 +587,8 @@ __global__ void __launch_bounds__(WPB * 32, MINB) k_chains(ChainArgs a) {
     if (fold > 0 || (STATS && a.generic_update)) {
       update_ref(ref, revref, curw, cnt, W, lane, old_len, delta, cs, cur_len, rev, new_len, fold);
       if (fold > 0) depth = 65535u;  // the fold adds several of the read's bases to one column: no bound on the counts after it
-    } else if (old_len == 0) {
-      reset_ref(ref, revref, curw, cnt, W, lane, cur_len, rev);
-    } else if (LOCKSTEP) {  // a free-running chain folds matched reads in at its claim site (ahead of the claim), not here
-      update_ref_fast<WT>(ref, curw, cnt, ref, revref, cnt, W, lane, old_len, delta, cs, cur_len, rev, new_len, depth > 65534u);
+    } else {
+      update_ref_fast<WT>(ref, revref, curw, cnt, W, lane, old_len, delta, cs, cur_len, rev, new_len, depth > 65534u);
     }
   };
   // the read must already be staged in curw
@@ -693,41 +646,22 @@ __global__ void __launch_bounds__(WPB * 32, MINB) k_chains(ChainArgs a) {
         }
         bool found = false;
         uint32_t k = 0, pre_sidx = 0xFFFFFFFFu;
-        uint64_t k_word = 0;
-        int shift = 0, prev_rev = 0, len = 0, old = 0, nl = 0;
+        uint64_t pre_word = 0;
+        int shift = 0, prev_rev = 0, pre_len = 0;
         if (!stop_searching) {
           int b = 0, S = 0;
           while (S < a.maxshift) {
-            if (chain_search<WT, true, STATS>(a, ref, revref, ref_len, lane, grp, wig, b, S, k, shift, prev_rev, k_word, len, c_issued, c_seq, c_cmp,
-                                              c_slot)) {
-              // Claim the read -- and do not wait for the answer: the update runs now, into the chain's other set of buffers,
-              // under the atomic's round trip (the row and its length came out of the verification; the slot indices the
-              // claim needs later are requested here too).  All but a fraction of a percent of the claims succeed.
-              unsigned got = 0;
-              if (lane == 0) got = atomicOr(a.claimed + (k >> 5), 1u << (k & 31));
+            if (chain_search<WT, true, STATS>(a, ref, revref, ref_len, lane, grp, wig, b, S, k, shift, prev_rev, c_issued, c_seq, c_cmp, c_slot)) {
+              // the claim's round trip overlaps the loads the update will need (row, length, slot indices)
+              unsigned old = 0;
+              if (lane == 0) old = atomicOr(a.claimed + (k >> 5), 1u << (k & 31));
+              if (lane < W) pre_word = __ldg(a.reads + (size_t)k * W + lane);
+              pre_len = __ldg(a.lens + k);
               if (lane < kNumDict) pre_sidx = __ldg(a.dict[lane].slot_of_read + k);
-              old = ref_len;
-              int delta, cs, fold = 0;
-              if (!prev_rev) { delta = shift; cs = 0; nl = max(old - shift, len); }
-              else if (len - shift >= old) { fold = len - shift - old; delta = -fold; cs = 0; nl = len; }
-              else if (old + shift <= a.L) { delta = 0; cs = old - len + shift; nl = old + shift; }
-              else { delta = old + shift - a.L; cs = a.L - len; nl = a.L; }
-              if (lane < W) curw[lane] = k_word;
-              __syncwarp();
-              const bool ahead = fold == 0 && !(STATS && a.generic_update);
-              const uint32_t depth_next = depth < 65535u ? depth + 1 : depth;
-              uint64_t *const ref_o = cbase + (ref == cbase ? 2 * W + 2 : 0), *const cnt_o = curw + W + (cnt == curw + W ? Lp : 0);
-              if (ahead)
-                update_ref_fast<WT>(ref, curw, cnt, ref_o, ref_o + W + 1, cnt_o, W, lane, old, delta, cs, len, prev_rev != 0, nl, depth_next > 65534u);
-              got = __shfl_sync(FULL, got, 0);
-              if ((got >> (k & 31)) & 1u) {
-                c_lost++;  // another chain took it between the check and the claim: search this batch again, on the window as it was
-                continue;
-              }
-              if (ahead) { ref = ref_o; revref = ref_o + W + 1; cnt = cnt_o; depth = depth_next; }
-              else upd(old, delta, cs, len, prev_rev != 0, nl, fold);  // the reference's fold quirk: in place, after the claim
-              found = true;
-              break;
+              old = __shfl_sync(FULL, old, 0);
+              if (!((old >> (k & 31)) & 1u)) { found = true; break; }
+              c_lost++;  // another chain took it between the check and the claim: search this batch again
+              continue;
             }
             S += 8 * ((STATS ? a.fast_tail : 1) ? (b < 2 ? (STATS ? a.batch0 : kBatch0) << b : 16) : (b < 4 ? 1 << b : 16));
             b++;
@@ -735,6 +669,15 @@ __global__ void __launch_bounds__(WPB * 32, MINB) k_chains(ChainArgs a) {
         }
         if (found) {
           if (lane < kNumDict && pre_sidx != 0xFFFFFFFFu) atomicSub(&a.dict[lane].slots[pre_sidx].live, 1u);
+          if (lane < W) curw[lane] = pre_word;
+          __syncwarp();
+          const int len = pre_len, old = ref_len;
+          int delta, cs, nl, fold = 0;
+          if (!prev_rev) { delta = shift; cs = 0; nl = max(old - shift, len); }
+          else if (len - shift >= old) { fold = len - shift - old; delta = -fold; cs = 0; nl = len; }
+          else if (old + shift <= a.L) { delta = 0; cs = old - len + shift; nl = old + shift; }
+          else { delta = old + shift - a.L; cs = a.L - len; nl = a.L; }
+          upd(old, delta, cs, len, prev_rev != 0, nl, fold);
           ref_len = nl;
           if (!prev_rev) {
             if (!left_search) { cur_read_pos = ref_pos + shift; ref_pos = cur_read_pos; }
@@ -842,10 +785,8 @@ __global__ void __launch_bounds__(WPB * 32, MINB) k_chains(ChainArgs a) {
         iter_started = 1;
       }
       if (!stop_searching) {
-        uint64_t prop_word;  // the deterministic schedule stages the proposed read again in phase A below (it may lose the round)
-        int prop_len;
-        has_prop = chain_search<WT, false, true>(a, ref, revref, ref_len, lane, grp, wig, batch, batch_S, prop_rid, prop_shift, prop_rev, prop_word,
-                                                 prop_len, c_issued, c_seq, c_cmp, c_slot);
+        has_prop = chain_search<WT, false, true>(a, ref, revref, ref_len, lane, grp, wig, batch, batch_S, prop_rid, prop_shift, prop_rev, c_issued,
+                                c_seq, c_cmp, c_slot);
         if (!has_prop) {
           const int nshift = 8 * (batch < 4 ? 1 << batch : 16);
           if (batch_S + nshift < a.maxshift) { batch++; batch_S += nshift; search_more = true; }

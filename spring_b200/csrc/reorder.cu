@@ -49,12 +49,6 @@
 #ifndef SB_NOINLINE_FIND
 #define SB_NOINLINE_FIND 0 // find_unclaimed as a real function call (cold path; smaller kernel)
 #endif
-#ifndef SB_USE_RESET
-#define SB_USE_RESET 1     // contig starts go through reset_ref instead of a further inlined copy of update_ref_fast
-#endif
-#ifndef SB_RESET_INLINE
-#define SB_RESET_INLINE __noinline__
-#endif
 #define SB_STR2(x) #x
 #define SB_STR(x) SB_STR2(x)
 #define SB_UNROLL(n) _Pragma(SB_STR(unroll n))
@@ -253,32 +247,6 @@ __device__ __forceinline__ void update_ref_fast(uint64_t *ref, uint64_t *revref,
   if (lane < W) ref[lane] = nw;
   __syncwarp();
   if (lane < W) revref[lane] = revcomp_word(ref, W, new_len, lane);
-  __syncwarp();
-}
-
-// The window of a contig that starts (or starts its left search) with the read staged in curw: what update_ref_fast
-// does for old_len = 0 -- counts = the read's bases, ref = the read (reverse-complemented for the left search),
-// revref = its reverse complement -- as a small routine of its own: it runs once or twice per contig, from three places,
-// and is kept out of line so that the hot loop's code stays small (update_ref_fast was inlined four times).
-__device__ SB_RESET_INLINE void reset_ref(uint64_t *ref, uint64_t *revref, uint64_t *curw, uint64_t *cnt, int W, int lane, int len, bool rev) {
-  if (rev) {
-    uint64_t o = 0;
-    if (lane < W) o = revcomp_word(curw, W, len, lane);
-    __syncwarp();
-    if (lane < W) curw[lane] = o;
-    __syncwarp();
-  }
-  const int sh2 = 2 * (lane & 15);
-  const bool hi_half = (lane & 16) != 0;
-  for (int cc = 0; (cc << 5) < len; cc++) {
-    const int i = (cc << 5) + lane;
-    const uint2 bw = reinterpret_cast<const uint2 *>(curw)[cc];
-    const uint32_t code = ((hi_half ? bw.y : bw.x) >> sh2) & 3u;
-    if (i < len) cnt[i] = 1ull << ((int)((0x9Cu >> (2 * code)) & 3u) << 4);
-  }
-  if (lane < W) ref[lane] = curw[lane] & range_mask(lane, 0, 2 * len);
-  __syncwarp();
-  if (lane < W) revref[lane] = revcomp_word(ref, W, len, lane);
   __syncwarp();
 }
 
@@ -619,8 +587,6 @@ __global__ void __launch_bounds__(WPB * 32, MINB) k_chains(ChainArgs a) {
     if (fold > 0 || (STATS && a.generic_update)) {
       update_ref(ref, revref, curw, cnt, W, lane, old_len, delta, cs, cur_len, rev, new_len, fold);
       if (fold > 0) depth = 65535u;  // the fold adds several of the read's bases to one column: no bound on the counts after it
-    } else if (SB_USE_RESET && old_len == 0) {
-      reset_ref(ref, revref, curw, cnt, W, lane, cur_len, rev);
     } else {
       update_ref_fast<WT>(ref, revref, curw, cnt, W, lane, old_len, delta, cs, cur_len, rev, new_len, depth > 65534u);
     }

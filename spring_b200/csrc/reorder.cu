@@ -545,7 +545,10 @@ __global__ void __launch_bounds__(WPB * 32, MINB) k_chains(ChainArgs a) {
   ColdState &cold = *reinterpret_cast<ColdState *>(cnt + Lp);
   int &cursor = cold.cursor, &slice_lo = cold.slice_lo;  // read ids fit 31 bits (check_input)
   uint32_t &first_rid = cold.first_rid, &prev = cold.prev, &num_unmatched_1m = cold.num_unmatched_1m, &n_single = cold.n_single;
-  cursor = -1; slice_lo = 0; first_rid = 0; prev = 0; num_unmatched_1m = 0; n_single = 0;
+  // One writer: lane 0 stores, __syncwarp() on both sides orders the store against the other lanes' reads (every lane
+  // storing the same value is what compute-sanitizer's racecheck rightly calls a hazard).
+  auto cold_set = [&](auto &field, auto v) { __syncwarp(); if (lane == 0) field = v; __syncwarp(); };
+  if (lane == 0) { cursor = -1; slice_lo = 0; first_rid = 0; prev = 0; num_unmatched_1m = 0; n_single = 0; cold.first_len = 0; }
   __syncwarp();
   uint32_t num_reads_thr = 0, n_aligned = 0, window_left = 0;
   // statistics: c_issued / c_seq / c_slot are per-lane partial sums, c_cmp / c_unmatched / c_lost are
@@ -593,18 +596,23 @@ __global__ void __launch_bounds__(WPB * 32, MINB) k_chains(ChainArgs a) {
   };
   // the read must already be staged in curw
   auto new_contig = [&](uint32_t rid, int len) {  // updaterefcount(..., resetcount = true, rev = false) + reorder.h:426-430,:601-612
-    cold.first_len = len;
+    __syncwarp();
+    if (lane == 0) { cold.first_len = len; first_rid = rid; prev = rid; }
+    __syncwarp();
     upd(0, 0, 0, len, false, len, 0);
     ref_len = len; ref_pos = 0; cur_read_pos = 0;
-    prev_unmatched = 1; first_rid = rid; prev = rid; left_search = 0;
+    prev_unmatched = 1; left_search = 0;
     state = ST_SEARCH; iter_started = 0; batch = 0; batch_S = 0;
     flush_counters(false);
   };
 
   if (state == ST_SEARCH) {  // reorder.h:405-431
     const uint32_t first = cid * a.per;
-    slice_lo = (int)first;
-    cursor = cid == a.num_chains - 1 ? (int)a.N - 1 : (int)((cid + 1) * a.per) - 1;
+    if (lane == 0) {
+      slice_lo = (int)first;
+      cursor = cid == a.num_chains - 1 ? (int)a.N - 1 : (int)((cid + 1) * a.per) - 1;
+    }
+    __syncwarp();
     // reorder.h:411-419: a thread gives up its start read if somebody already took it.  Chains of the
     // free-running schedule start whenever their block gets an SM, so an earlier chain may have claimed
     // `first` through a dictionary match: test-and-set, and on failure pick from the own slice instead.
@@ -637,7 +645,7 @@ __global__ void __launch_bounds__(WPB * 32, MINB) k_chains(ChainArgs a) {
         if (!iter_started) {  // loop top, reorder.h:433-439 (the window's end is counted down: no modulo per step)
           if (window_left == 0) {
             if (num_unmatched_1m > kStopUnmatched) stop_searching = 1;
-            num_unmatched_1m = 0;
+            cold_set(num_unmatched_1m, 0u);
             window_left = kStopWindow;
           }
           window_left--;
@@ -696,7 +704,7 @@ __global__ void __launch_bounds__(WPB * 32, MINB) k_chains(ChainArgs a) {
           prev_unmatched = 0;
           iter_started = 0;
         } else {
-          num_unmatched_1m++;
+          cold_set(num_unmatched_1m, num_unmatched_1m + 1u);
           if (!left_search) {
             left_search = 1;
             stage_read(first_rid);
@@ -727,7 +735,7 @@ __global__ void __launch_bounds__(WPB * 32, MINB) k_chains(ChainArgs a) {
         };
         while (find_unclaimed(a.claimed, slice_lo, cursor, lane, j)) {
           const bool mine = claim_seed(j);
-          cursor = (int)j - 1;
+          cold_set(cursor, (int)j - 1);
           if (mine) { got = true; break; }
         }
         // Own slice exhausted: instead of idling until the slowest chain is done, seed the next contig from
@@ -747,7 +755,7 @@ __global__ void __launch_bounds__(WPB * 32, MINB) k_chains(ChainArgs a) {
         }
         if (prev_unmatched) {
           if (lane == 0) a.rec[prev] = make_rec(0, n_single, cid, 4);
-          n_single++;
+          cold_set(n_single, n_single + 1u);
         }
         if (got) {
           if (lane < kNumDict && seed_sidx != 0xFFFFFFFFu) atomicSub(&a.dict[lane].slots[seed_sidx].live, 1u);
@@ -779,7 +787,7 @@ __global__ void __launch_bounds__(WPB * 32, MINB) k_chains(ChainArgs a) {
       if (!iter_started) {  // loop top, reorder.h:433-439
         if (num_reads_thr % kStopWindow == 0) {
           if (num_unmatched_1m > kStopUnmatched) stop_searching = 1;
-          num_unmatched_1m = 0;
+          cold_set(num_unmatched_1m, 0u);
         }
         num_reads_thr++;
         iter_started = 1;
@@ -844,7 +852,7 @@ __global__ void __launch_bounds__(WPB * 32, MINB) k_chains(ChainArgs a) {
           c_lost++;
         }
       } else if (!search_more) {  // no match, reorder.h:559-615
-        num_unmatched_1m++;
+        cold_set(num_unmatched_1m, num_unmatched_1m + 1u);
         if (!left_search) {
           left_search = 1;
           const int len = cold.first_len;
@@ -862,8 +870,8 @@ __global__ void __launch_bounds__(WPB * 32, MINB) k_chains(ChainArgs a) {
           const uint32_t j = prop_rid;
           claim_pre(j, pre_sidx);
           if (lane == 0 && prev_unmatched) a.rec[prev] = make_rec(0, n_single, cid, 4);
-          if (prev_unmatched) n_single++;
-          cursor = (int)j - 1;
+          if (prev_unmatched) cold_set(n_single, n_single + 1u);
+          cold_set(cursor, (int)j - 1);
           c_unmatched++;
           new_contig(j, __ldg(a.lens + j));
         } else {
@@ -872,7 +880,7 @@ __global__ void __launch_bounds__(WPB * 32, MINB) k_chains(ChainArgs a) {
       } else {
         if (prev_unmatched) {
           if (lane == 0) a.rec[prev] = make_rec(0, n_single, cid, 4);
-          n_single++;
+          cold_set(n_single, n_single + 1u);
         }
         state = ST_DONE;
         if (lane == 0) atomicSub(a.active, 1);

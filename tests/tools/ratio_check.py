@@ -18,6 +18,10 @@ if "--quick" in sys.argv:
 if "--policy" in sys.argv:  # chain-count policies: reads per chain of the auto rule (reorder.cu:run_reorder)
     runs = [("reference", po.REF_BIN, {})] + [(f"b200 {r} reads/chain", po.SPLICE2_BIN, {"SPRING_B200_READS_PER_CHAIN": str(r)})
                                               for r in (256, 2048, 6400)]
+if "--gpus" in sys.argv:  # ratio drift of the multi-GPU partitioning: the spliced binary on 1, 2, ... GPUs of this box
+    import torch
+    counts = [g for g in (1, 2, 4, 8) if g <= torch.cuda.device_count()]
+    runs = [("reference", po.REF_BIN, {})] + [(f"b200 {g} GPU", po.SPLICE2_BIN, {"SPRING_B200_GPUS": str(g)}) for g in counts]
 for name, binary, env in runs:
     out = os.path.join(d, name.replace(" ", "_").replace("/", "_per_") + ".spring")
     t0 = time.time()

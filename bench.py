@@ -493,6 +493,7 @@ def main() -> None:
             "gpu_launches": int(launches), "roofline": roofline, "clocks": clocks.summary(),
             "stages_ms": {k: stats_acc[k] for k in stats_acc if k.startswith("ms_")},
             "chains": stats_acc["num_chains"], "rounds": stats_acc["rounds"], "unmatched": stats_acc["unmatched"],
+            "contigs": stats_acc["contigs"], "contigs_stitched": stats_acc["contigs_stitched"],
             "mb_per_s_fastq": value * fastq_bytes_per_read, "verify": verify}
     if exchange_ms:  # rank 0's bucket + scatter kernels, count all-gather and the NCCL send / recv group, per step (inside ms_per_step)
         line["exchange_ms"] = exchange_avg

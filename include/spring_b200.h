@@ -120,6 +120,8 @@ typedef struct spring_b200_stats {
   float ms_exchange;         /* device time of the last spring_b200_exchange_reads (bucket + scatter kernels, NCCL group) */
   uint32_t singletons_aligned; /* "N singleton reads were aligned" / "N reads with N were aligned" (src/encoder.h:490-492) */
   uint32_t n_reads_aligned;
+  uint32_t contigs;          /* contigs the chains left in the aligned stream */
+  uint32_t contigs_stitched; /* ... of which the encoder laid into another contig (spring_b200_set_stitch) */
 } spring_b200_stats;
 
 /* ---- context ---------------------------------------------------------------------------- */
@@ -151,6 +153,16 @@ int spring_b200_set_schedule(spring_b200_ctx *ctx, int deterministic);
  * (bench.py runs one counted pass outside the timed region).  The deterministic schedule always counts: its counters
  * are part of the parity tests against the oracle's (src/reorder.h:262-311 counted the same way). */
 int spring_b200_set_chain_stats(spring_b200_ctx *ctx, int on);
+/* Contig stitching in the encoder.  The reference's threads seed every new contig from ONE pool of reads
+ * (src/reorder.h:576-592); thousands of GPU chains seed from their own slices, so neighbouring contigs overlap and the
+ * overlap's consensus is stored twice.  With stitching, after the first consensus pass every contig's head (its first
+ * max_readlen consensus bases) is searched in the other contigs' consensus -- the sweep that re-aligns singletons
+ * (src/encoder.h:231-352), with a tighter threshold -- and a contig whose head fits is laid into that contig's coordinates
+ * (flipped if it fits reversed) before the consensus is rebuilt.  Only positions / orientations of reads change.
+ * mode: -1 (default) automatic = on when the chains are so many for the input that their contig starts would cost more
+ * than ~1 % of the read streams (reads < 6400 * chains), free-running schedule only; 0 off (the encoder then equals the
+ * reference's encoder on the same reorder stream bit for bit); 1 on. */
+int spring_b200_set_stitch(spring_b200_ctx *ctx, int mode);
 
 /* ---- the hot path ------------------------------------------------------------------------ */
 /* reorder_main + encoder_main (src/reorder.h:732-786, src/encoder.h:572-633) on HOST buffers:

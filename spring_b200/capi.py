@@ -19,7 +19,7 @@ EXPORTS = [
     "spring_b200_last_error", "spring_b200_get_stats", "spring_b200_reorder_encode",
     "spring_b200_reorder_encode_device", "spring_b200_fetch_streams", "spring_b200_build_dictionary",
     "spring_b200_reorder", "spring_b200_reorder_encode_files", "spring_b200_write_streams",
-    "spring_b200_bucket_reads", "spring_b200_set_schedule", "spring_b200_set_chain_stats", "spring_b200_packed_pending", "spring_b200_reorder_encode_packed", "spring_b200_fetch_reorder", "spring_b200_set_stream",
+    "spring_b200_bucket_reads", "spring_b200_set_schedule", "spring_b200_set_chain_stats", "spring_b200_set_stitch", "spring_b200_packed_pending", "spring_b200_reorder_encode_packed", "spring_b200_fetch_reorder", "spring_b200_set_stream",
     "spring_b200_pe_encode", "spring_b200_reblock_streams", "spring_b200_reblock_files", "spring_b200_pack_reads",
     "spring_b200_decode_blocks", "spring_b200_verify_roundtrip",
     "spring_b200_comm_unique_id", "spring_b200_comm_init", "spring_b200_comm_free", "spring_b200_exchange_reads",
@@ -120,7 +120,8 @@ class Stats(C.Structure):
                 ("ms_total", C.c_float), ("ms_chain_kernel", C.c_float), ("cyc_search", C.c_uint64),
                 ("cyc_wait_a", C.c_uint64), ("cyc_commit", C.c_uint64), ("cyc_wait_b", C.c_uint64),
                 ("slot_probes", C.c_uint64), ("ms_reblock", C.c_float), ("ms_exchange", C.c_float),
-                ("singletons_aligned", C.c_uint32), ("n_reads_aligned", C.c_uint32)]
+                ("singletons_aligned", C.c_uint32), ("n_reads_aligned", C.c_uint32),
+                ("contigs", C.c_uint32), ("contigs_stitched", C.c_uint32)]
 
     def as_dict(self) -> dict:
         return {f: getattr(self, f) for f, _ in self._fields_}
@@ -251,6 +252,11 @@ class Context:
         """True: round-synchronous chains (reproducible output); False (default): free-running chains."""
         self._lib.spring_b200_set_schedule.argtypes = [C.c_void_p, C.c_int]
         self._check(self._lib.spring_b200_set_schedule(self._h, 1 if deterministic else 0))
+
+    def set_stitch(self, mode: int) -> None:
+        """-1: automatic (default), 0: off (encoder == the reference's encoder on the same reorder stream), 1: on."""
+        self._lib.spring_b200_set_stitch.argtypes = [C.c_void_p, C.c_int]
+        self._check(self._lib.spring_b200_set_stitch(self._h, int(mode)))
 
     def set_chain_stats(self, on: bool) -> None:
         """True: the free-running chain kernel also counts lookups / compares (probes_seq, compares, ... in stats())."""

@@ -155,7 +155,7 @@ __global__ void k_contig_bounds(const uint32_t *__restrict__ cidx1, const int64_
 __global__ void k_contig_len(const long long *__restrict__ cmin, const long long *__restrict__ cmaxend, uint32_t nc,
                              unsigned long long *clen) {
   const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c < nc) clen[c] = (unsigned long long)(cmaxend[c] - cmin[c]);
+  if (c < nc) clen[c] = cmaxend[c] > cmin[c] ? (unsigned long long)(cmaxend[c] - cmin[c]) : 0ull;  // a contig stitched into another holds no reads
   if (c == nc) clen[c] = 0;
 }
 
@@ -353,6 +353,107 @@ __global__ void __launch_bounds__(kConsThreads) k_consensus(const uint64_t *__re
   cons2[xw >> 5] = code_lo | (code_hi << 1);
 }
 
+// ---- contig stitching ---------------------------------------------------------------------------------------------------
+// The reference's threads seed every new contig from ONE pool of reads (reorder.h:576-592); thousands of GPU chains seed from
+// their own slices and end up with contigs that overlap their neighbours' -- every overlap is consensus stored twice (the ratio
+// cost of DESIGN.md section 6).  After the first consensus pass the contigs' own HEADS (first max_readlen bases of their
+// consensus) are treated like singleton reads: the same sweep that re-aligns singletons (k_align_singletons) finds, for every
+// head, the first place in ANOTHER contig's consensus where it fits; the contig is then laid into that contig's coordinates
+// (flipped if its head fits reversed), chains of such links are followed to their root, and the consensus is rebuilt once over
+// the merged layout.  Only read positions / orientations change: the streams stay decodable by construction.
+constexpr int kThreshStitch = 8;  // mismatches allowed between a contig's head and the consensus it is laid into
+__global__ void k_contig_heads(const uint64_t *__restrict__ cons2, const unsigned long long *__restrict__ cstart,
+                               const unsigned long long *__restrict__ clen, uint32_t nc, int W, int L, uint64_t *head_codes,
+                               uint16_t *head_len, uint32_t *head_ncount) {
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t c = (uint32_t)(t / W);
+  if (c >= nc) return;
+  const int w = (int)(t - (uint64_t)c * W);
+  const int hl = (int)(clen[c] < (unsigned long long)L ? clen[c] : (unsigned long long)L);
+  uint64_t v = 0;
+  if (32 * w < hl) {
+    v = cons_bits(cons2, cstart[c] + 32ull * w);
+    const int rem = hl - 32 * w;
+    if (rem < 32) v &= (1ull << (2 * rem)) - 1ull;
+  }
+  head_codes[t] = v;
+  if (w == 0) { head_len[c] = (uint16_t)hl; head_ncount[c] = 0; }
+}
+// best[c] = first window (position, strand, dictionary) another contig's consensus offers to contig c's head -> parent[c] and
+// the map x -> a + sgn * x from c's coordinates into the parent's (forward: the head sits at the window's start; reversed: base x
+// of the head faces consensus base j + L - 1 - x, k_align_singletons' convention)
+__global__ void k_stitch_links(const unsigned long long *__restrict__ best, const unsigned long long *__restrict__ cstart, uint32_t nc, int L,
+                               uint32_t *parent, long long *ta, int8_t *ts) {
+  const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nc) return;
+  const unsigned long long pr = best[c];
+  uint32_t p = c;
+  long long a = 0;
+  int8_t sg = 1;
+  if (pr != kNoPrio) {
+    const uint64_t j = pr >> 2;
+    p = upper_bound_u64(reinterpret_cast<const uint64_t *>(cstart), nc + 1, j) - 1;
+    const long long ja = (long long)(j - cstart[p]);
+    if ((pr >> 1) & 1) { a = ja + L - 1; sg = -1; } else { a = ja; }
+  }
+  parent[c] = p; ta[c] = a; ts[c] = sg;
+}
+// two contigs that each want to go into the other (heads overlapping head to head): the one with the higher index stays put
+__global__ void k_stitch_break2(const uint32_t *__restrict__ parent, uint32_t nc, uint8_t *drop) {
+  const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nc) return;
+  const uint32_t p = parent[c];
+  drop[c] = (p != c && parent[p] == c && c > p) ? 1 : 0;
+}
+__global__ void k_stitch_unlink(const uint8_t *__restrict__ drop, uint32_t nc, uint32_t *parent, long long *ta, int8_t *ts) {
+  const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < nc && drop[c]) { parent[c] = c; ta[c] = 0; ts[c] = 1; }
+}
+// one round of pointer jumping (old arrays in, new arrays out): c -> parent -> grandparent, maps composed
+__global__ void k_stitch_jump(const uint32_t *__restrict__ parent, const long long *__restrict__ ta, const int8_t *__restrict__ ts, uint32_t nc,
+                              uint32_t *parent2, long long *ta2, int8_t *ts2) {
+  const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nc) return;
+  const uint32_t p = parent[c];
+  long long a = ta[c];
+  int8_t sg = ts[c];
+  uint32_t g = p;
+  if (p != c) {
+    g = parent[p];
+    if (g != p) { a = ta[p] + (long long)ts[p] * a; sg = (int8_t)(ts[p] * sg); } else g = p;
+  }
+  parent2[c] = g; ta2[c] = a; ts2[c] = sg;
+}
+// a contig whose chain of links did not end in a contig that stays put (links going round in a circle: repeats) stays put itself
+__global__ void k_stitch_validate(const uint32_t *__restrict__ parent, uint32_t nc, uint8_t *drop, uint32_t *num_linked) {
+  const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  bool linked = false;
+  if (c < nc) {
+    const uint32_t r = parent[c];
+    const bool bad = r != c && parent[r] != r;
+    drop[c] = bad ? 1 : 0;
+    linked = r != c && !bad;
+  }
+  const int n = __syncthreads_count(linked);
+  if (threadIdx.x == 0 && n) atomicAdd(num_linked, (uint32_t)n);
+}
+// every stream record into its root contig's coordinates
+__global__ void k_stitch_apply(const uint32_t *__restrict__ cidx1, const int64_t *__restrict__ pos, const uint8_t *__restrict__ rev,
+                               const uint32_t *__restrict__ order, const uint16_t *__restrict__ lens, const long long *__restrict__ cmin,
+                               const uint32_t *__restrict__ root, const long long *__restrict__ ta, const int8_t *__restrict__ ts, uint32_t m,
+                               uint32_t *cidx2, int64_t *pos2, uint8_t *rev2) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  const uint32_t c = cidx1[i] - 1;
+  const long long p0 = pos[i] - cmin[c];
+  const int len = lens[order[i]];
+  const bool flip = ts[c] < 0;
+  cidx2[i] = root[c] + 1;
+  pos2[i] = flip ? ta[c] - p0 - len + 1 : ta[c] + p0;
+  const uint8_t r = rev[i];
+  rev2[i] = flip ? (r == 'r' ? 'd' : 'r') : r;
+}
+
 // ---- singleton re-alignment (encoder.h:231-352) ---------------------------------------------------
 struct AlignArgs {
   const uint64_t *cons2; uint64_t seq_len;
@@ -362,6 +463,8 @@ struct AlignArgs {
   int W, L;
   unsigned long long *best;
   const uint32_t *tile_contig;  // contig holding column 256 * t (k_tile_contigs)
+  int thresh;                   // Hamming threshold (THRESH_ENCODER for the singleton sweep)
+  int stitch;                   // the "reads" are the contigs' own heads (read r = head of contig r): a contig does not take its own head
 };
 // contig of the first column of every 256-column block: thread per contig, each writes the block starts
 // that fall inside it (contigs tile the consensus, so every block start has exactly one owner)
@@ -419,13 +522,14 @@ __global__ void k_align_singletons(AlignArgs a) {
       const uint64_t x0 = rev ? j + (uint64_t)(L - len) : j;
       int h = (int)a.pool_ncount[rid];
       const int nw = (len + 31) >> 5;
-      for (int i = 0; i < nw && h <= kThreshEncoder; i++) {
+      if (a.stitch && rid == lo) continue;
+      for (int i = 0; i < nw && h <= a.thresh; i++) {
         const uint64_t o = oriented_word(r, W, len, rev != 0, i);
         const int rem = len - 32 * i;
         const uint64_t lm = rem >= 32 ? ~0ull : (1ull << (2 * rem)) - 1ull;
         h += __popcll((o ^ cons_bits(a.cons2, x0 + 32ull * i)) & lm);
       }
-      if (h <= kThreshEncoder) atomicMin(a.best + rid, prio);
+      if (h <= a.thresh) atomicMin(a.best + rid, prio);
     }
   }
 }
@@ -661,47 +765,108 @@ void run_encode(Ctx &c, const uint64_t *reads, const uint16_t *lens, uint32_t n,
   uint64_t seq_len = 0;
   uint64_t *ap = c.pool.dev<uint64_t>("en.ap", Mn), *sorted_ap = c.pool.dev<uint64_t>("en.sorted_ap", Mn);
   uint32_t *idx = c.pool.dev<uint32_t>("en.idx", Mn), *perm = c.pool.dev<uint32_t>("en.perm", Mn);
-  if (M) {
-    k_fill_u64<<<grid_for(NC + 1, 256), 256, 0, st>>>((unsigned long long *)cmin, NC + 1, 0x7FFFFFFFFFFFFFFFull);
-    k_fill_u64<<<grid_for(NC + 1, 256), 256, 0, st>>>((unsigned long long *)cmaxend, NC + 1, 0x8000000000000000ull);
-    k_contig_bounds<<<grid_for(M, 256), 256, 0, st>>>(cidx1, ro.pos, ro.order, lens, M, cmin, cmaxend);
-    k_contig_len<<<grid_for(NC + 1, 256), 256, 0, st>>>(cmin, cmaxend, NC, clen);
-    size_t need = 0;
-    cub::DeviceScan::ExclusiveSum(nullptr, need, clen, cstart, (int)NC + 1, st); cub_need(need);
-    need = cub_bytes; cub::DeviceScan::ExclusiveSum(cub_tmp, need, clen, cstart, (int)NC + 1, st);
-    c.launches += 5;
-    seq_len = d2h(c, cstart + NC);
-    k_abs_pos<<<grid_for(M, 256), 256, 0, st>>>(cidx1, ro.pos, cmin, cstart, M, ap, idx);
-    const int kb = bits_for(seq_len);
-    need = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, need, ap, sorted_ap, idx, perm, (int)M, 0, kb, st); cub_need(need);
-    need = cub_bytes; cub::DeviceRadixSort::SortPairs(cub_tmp, need, ap, sorted_ap, idx, perm, (int)M, 0, kb, st);
-    c.launches += 2 + 2 * ((kb + 7) / 8);
-  }
-  out.seq_len = seq_len;
-
-  // ---- consensus ------------------------------------------------------------------------------------
-  const uint64_t cons_words = (seq_len + 31) / 32;
-  uint64_t *cons2 = c.pool.dev<uint64_t>("en.cons2", cons_words + 4);
-  SB_CUDA(cudaMemsetAsync(cons2 + cons_words, 0, 4 * sizeof(uint64_t), st));  // zero pad: windows may read 2 words past the end
-  const uint32_t num_tiles = grid_for(seq_len, kTile);
-  uint32_t *tile_lo = c.pool.dev<uint32_t>("en.tile_lo", (size_t)num_tiles + 2), *tile_hi = c.pool.dev<uint32_t>("en.tile_hi", (size_t)num_tiles + 2);
-  uint32_t *tile_contig = c.pool.dev<uint32_t>("en.tile_contig", (size_t)num_tiles + 2);
   uint64_t *srt_words = c.pool.dev<uint64_t>("en.srt_words", (size_t)Mn * W + 2);  // + slack: bulk copies round up to 16 B
   uint16_t *srt_len = c.pool.dev<uint16_t>("en.srt_len", Mn);
   uint32_t *srt_rid = c.pool.dev<uint32_t>("en.srt_rid", Mn);
   uint8_t *srt_rev = c.pool.dev<uint8_t>("en.srt_rev", Mn);
-  if (seq_len) {
-    k_gather_sorted<<<grid_for((uint64_t)M * W, 256), 256, 0, st>>>(reads, lens, ro.order, ro.rev, perm, M, W, srt_words, srt_len, srt_rid, srt_rev);
-    k_tile_ranges<<<grid_for((uint64_t)M + 1, 256), 256, 0, st>>>(sorted_ap, M, L, num_tiles, tile_lo, tile_hi);
-    // one stage usually holds every row of a block (4096 columns at 30x and 150 bp: ~850 rows): one bulk copy, one wait
-    const int stage_rows = std::max(64, std::min(kConsStageMax, (40 * 1024) / (8 * W)));
-    const size_t cons_smem = ((size_t)stage_rows * W + 2) * sizeof(uint64_t);
-    SB_CUDA(cudaFuncSetAttribute(k_consensus, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cons_smem));
-    k_consensus<<<grid_for(seq_len, kConsThreads * 32), kConsThreads, cons_smem, st>>>(srt_words, srt_len, sorted_ap, tile_lo, tile_hi,
-                                                                                       num_tiles, W, L, seq_len, stage_rows, cons2);
-    c.launches += 3;
+  uint64_t *cons2 = nullptr;
+  uint32_t *tile_lo = nullptr, *tile_hi = nullptr, *tile_contig = nullptr;
+  uint32_t num_tiles = 0;
+  // contig bounds -> concatenated layout -> one sort by absolute position -> oriented rows -> consensus; run once, or twice
+  // when contigs are stitched in between (the second time over the merged contigs' coordinates)
+  auto layout_and_consensus = [&](const uint32_t *cx, const int64_t *rpos, const uint8_t *rrev) {
+    seq_len = 0;
+    if (M) {
+      k_fill_u64<<<grid_for(NC + 1, 256), 256, 0, st>>>((unsigned long long *)cmin, NC + 1, 0x7FFFFFFFFFFFFFFFull);
+      k_fill_u64<<<grid_for(NC + 1, 256), 256, 0, st>>>((unsigned long long *)cmaxend, NC + 1, 0x8000000000000000ull);
+      k_contig_bounds<<<grid_for(M, 256), 256, 0, st>>>(cx, rpos, ro.order, lens, M, cmin, cmaxend);
+      k_contig_len<<<grid_for(NC + 1, 256), 256, 0, st>>>(cmin, cmaxend, NC, clen);
+      size_t need = 0;
+      cub::DeviceScan::ExclusiveSum(nullptr, need, clen, cstart, (int)NC + 1, st); cub_need(need);
+      need = cub_bytes; cub::DeviceScan::ExclusiveSum(cub_tmp, need, clen, cstart, (int)NC + 1, st);
+      c.launches += 5;
+      seq_len = d2h(c, cstart + NC);
+      k_abs_pos<<<grid_for(M, 256), 256, 0, st>>>(cx, rpos, cmin, cstart, M, ap, idx);
+      const int kb = bits_for(seq_len);
+      need = 0;
+      cub::DeviceRadixSort::SortPairs(nullptr, need, ap, sorted_ap, idx, perm, (int)M, 0, kb, st); cub_need(need);
+      need = cub_bytes; cub::DeviceRadixSort::SortPairs(cub_tmp, need, ap, sorted_ap, idx, perm, (int)M, 0, kb, st);
+      c.launches += 2 + 2 * ((kb + 7) / 8);
+    }
+    const uint64_t cons_words = (seq_len + 31) / 32;
+    cons2 = c.pool.dev<uint64_t>("en.cons2", cons_words + 4);
+    SB_CUDA(cudaMemsetAsync(cons2 + cons_words, 0, 4 * sizeof(uint64_t), st));  // zero pad: windows may read 2 words past the end
+    num_tiles = grid_for(seq_len, kTile);
+    tile_lo = c.pool.dev<uint32_t>("en.tile_lo", (size_t)num_tiles + 2); tile_hi = c.pool.dev<uint32_t>("en.tile_hi", (size_t)num_tiles + 2);
+    tile_contig = c.pool.dev<uint32_t>("en.tile_contig", (size_t)num_tiles + 2);
+    if (seq_len) {
+      k_gather_sorted<<<grid_for((uint64_t)M * W, 256), 256, 0, st>>>(reads, lens, ro.order, rrev, perm, M, W, srt_words, srt_len, srt_rid, srt_rev);
+      k_tile_ranges<<<grid_for((uint64_t)M + 1, 256), 256, 0, st>>>(sorted_ap, M, L, num_tiles, tile_lo, tile_hi);
+      // one stage usually holds every row of a block (4096 columns at 30x and 150 bp: ~850 rows): one bulk copy, one wait
+      const int stage_rows = std::max(64, std::min(kConsStageMax, (40 * 1024) / (8 * W)));
+      const size_t cons_smem = ((size_t)stage_rows * W + 2) * sizeof(uint64_t);
+      SB_CUDA(cudaFuncSetAttribute(k_consensus, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cons_smem));
+      k_consensus<<<grid_for(seq_len, kConsThreads * 32), kConsThreads, cons_smem, st>>>(srt_words, srt_len, sorted_ap, tile_lo, tile_hi,
+                                                                                         num_tiles, W, L, seq_len, stage_rows, cons2);
+      k_tile_contigs<<<grid_for(NC, 256), 256, 0, st>>>(cstart, NC, tile_contig);
+      c.launches += 4;
+    }
+  };
+  layout_and_consensus(cidx1, ro.pos, ro.rev);
+
+  // ---- contig stitching (see k_contig_heads) ------------------------------------------------------------------------------
+  // On when asked for, or -- by default -- when the chains are so many for the input that their contig starts cost more than ~1 %
+  // of the read streams (64 * chains / reads): free-running schedule only (the deterministic one is compared
+  // with the oracle bit for bit).
+  out.contigs = NC; out.contigs_stitched = 0;
+  const bool stitch = c.stitch == 1 || (c.stitch < 0 && !c.lockstep && ro.num_chains > 1 && (uint64_t)n < 6400ull * ro.num_chains);
+  if (stitch && NC > 1 && (int64_t)seq_len >= L) {
+    uint64_t *head_codes = c.pool.dev<uint64_t>("st.head_codes", (size_t)NC * W);
+    uint16_t *head_len = c.pool.dev<uint16_t>("st.head_len", NC);
+    uint32_t *head_ncount = c.pool.dev<uint32_t>("st.head_ncount", NC);
+    unsigned long long *sbest = c.pool.dev<unsigned long long>("st.best", NC);
+    k_contig_heads<<<grid_for((uint64_t)NC * W, 256), 256, 0, st>>>(cons2, cstart, clen, NC, W, L, head_codes, head_len, head_ncount);
+    k_fill_u64<<<grid_for(NC, 256), 256, 0, st>>>(sbest, NC, kNoPrio);
+    DictBuild sd[2];
+    int es[2], ee[2];
+    encoder_windows(L, es, ee);
+    build_dictionary(c, head_codes, head_len, nullptr, NC, W, es[0], ee[0], "st.dict0", sd[0]);
+    build_dictionary(c, head_codes, head_len, nullptr, NC, W, es[1], ee[1], "st.dict1", sd[1]);
+    AlignArgs sa{};
+    sa.cons2 = cons2; sa.seq_len = seq_len; sa.cstart = cstart; sa.num_contigs = NC;
+    sa.dict[0] = sd[0].view; sa.dict[1] = sd[1].view;
+    sa.pool_codes = head_codes; sa.pool_len = head_len; sa.pool_ncount = head_ncount; sa.W = W; sa.L = L; sa.best = sbest;
+    sa.tile_contig = tile_contig; sa.thresh = kThreshStitch; sa.stitch = 1;
+    k_align_singletons<<<grid_for(seq_len, 256), 256, 0, st>>>(sa);
+    uint32_t *par_a = c.pool.dev<uint32_t>("st.par_a", NC), *par_b = c.pool.dev<uint32_t>("st.par_b", NC);
+    long long *ta_a = c.pool.dev<long long>("st.ta_a", NC), *ta_b = c.pool.dev<long long>("st.ta_b", NC);
+    int8_t *ts_a = c.pool.dev<int8_t>("st.ts_a", NC), *ts_b = c.pool.dev<int8_t>("st.ts_b", NC);
+    uint8_t *drop = c.pool.dev<uint8_t>("st.drop", NC);
+    uint32_t *d_linked = c.pool.dev<uint32_t>("st.linked", 1);
+    k_stitch_links<<<grid_for(NC, 256), 256, 0, st>>>(sbest, cstart, NC, L, par_a, ta_a, ts_a);
+    k_stitch_break2<<<grid_for(NC, 256), 256, 0, st>>>(par_a, NC, drop);
+    k_stitch_unlink<<<grid_for(NC, 256), 256, 0, st>>>(drop, NC, par_a, ta_a, ts_a);
+    c.launches += 6;
+    for (int r = 0, rounds = bits_for(NC) + 1; r < rounds; r++) {  // 2^rounds > NC: every chain of links has reached its root
+      k_stitch_jump<<<grid_for(NC, 256), 256, 0, st>>>(par_a, ta_a, ts_a, NC, par_b, ta_b, ts_b);
+      std::swap(par_a, par_b); std::swap(ta_a, ta_b); std::swap(ts_a, ts_b);
+      c.launches++;
+    }
+    SB_CUDA(cudaMemsetAsync(d_linked, 0, sizeof(uint32_t), st));
+    k_stitch_validate<<<grid_for(NC, 256), 256, 0, st>>>(par_a, NC, drop, d_linked);
+    k_stitch_unlink<<<grid_for(NC, 256), 256, 0, st>>>(drop, NC, par_a, ta_a, ts_a);
+    c.launches += 2;
+    out.contigs_stitched = d2h(c, d_linked);
+    if (out.contigs_stitched) {
+      uint32_t *cidx2 = c.pool.dev<uint32_t>("st.cidx2", Mn);
+      int64_t *pos2 = c.pool.dev<int64_t>("st.pos2", Mn);
+      uint8_t *rev2 = c.pool.dev<uint8_t>("st.rev2", Mn);
+      k_stitch_apply<<<grid_for(M, 256), 256, 0, st>>>(cidx1, ro.pos, ro.rev, ro.order, lens, cmin, par_a, ta_a, ts_a, M, cidx2, pos2, rev2);
+      c.launches++;
+      layout_and_consensus(cidx2, pos2, rev2);
+    }
   }
+  out.seq_len = seq_len;
 
   // ---- singleton / N re-alignment ------------------------------------------------------------------
   unsigned long long *best = c.pool.dev<unsigned long long>("en.best", Pn);
@@ -724,10 +889,9 @@ void run_encode(Ctx &c, const uint64_t *reads, const uint16_t *lens, uint32_t n,
       aa.cons2 = cons2; aa.seq_len = seq_len; aa.cstart = cstart; aa.num_contigs = NC;
       aa.dict[0] = ed[0].view; aa.dict[1] = ed[1].view;
       aa.pool_codes = pool_codes; aa.pool_len = pool_len; aa.pool_ncount = pool_ncount; aa.W = W; aa.L = L; aa.best = best;
-      aa.tile_contig = tile_contig;
-      k_tile_contigs<<<grid_for(NC, 256), 256, 0, st>>>(cstart, NC, tile_contig);
+      aa.tile_contig = tile_contig; aa.thresh = kThreshEncoder; aa.stitch = 0;
       k_align_singletons<<<grid_for(seq_len, 256), 256, 0, st>>>(aa);
-      c.launches += 2;
+      c.launches++;
     }
     uint8_t *fl_a = c.pool.dev<uint8_t>("en.fl_a", Pn), *fl_u = c.pool.dev<uint8_t>("en.fl_u", Pn);
     k_pool_flags<<<grid_for(P, 256), 256, 0, st>>>(best, P, fl_a, fl_u);
@@ -822,6 +986,7 @@ void run_encode(Ctx &c, const uint64_t *reads, const uint16_t *lens, uint32_t n,
   }
 
   // ---- consensus packing --------------------------------------------------------------------------------
+  const uint64_t cons_words = (seq_len + 31) / 32;
   out.seq_packed = reinterpret_cast<uint8_t *>(c.pool.dev<uint64_t>("en.out_seq", cons_words + 1));
   if (seq_len) { k_pack_seq<<<grid_for(cons_words, 256), 256, 0, st>>>(cons2, cons_words, reinterpret_cast<uint64_t *>(out.seq_packed)); c.launches++; }
   SB_CUDA(cudaGetLastError());

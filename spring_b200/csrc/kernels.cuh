@@ -16,6 +16,7 @@ struct Ctx {
   cudaEvent_t ev_x0 = nullptr, ev_x1 = nullptr;  // around the multi-GPU exchange
   unsigned long long l2_policies[2] = {0, 0};  // createpolicy results (evict_last, evict_first), made once
   bool lockstep = false;  // chain schedule: deterministic round-synchronous, or free-running (default)
+  int stitch = -1;  // contig stitching in the encoder: -1 auto (many chains for the input, free-running schedule), 0 off, 1 on
   bool chain_stats = false;  // free-running chains also count lookups / compares (spring_b200_set_chain_stats; the deterministic schedule always does)
 };
 
@@ -59,6 +60,7 @@ struct EncodeDev {
   uint8_t *unaligned = nullptr; uint64_t unaligned_bytes = 0, unaligned_len = 0;
   uint64_t num_aligned = 0, num_reads = 0;
   uint32_t singletons_aligned = 0, n_reads_aligned = 0;
+  uint32_t contigs = 0, contigs_stitched = 0;  // contigs the chains left; how many of them were laid into another contig
 };
 struct NReads {  // reads with N: input_N.dna records uploaded as they are and unpacked by k_unpack_n
   const uint64_t *codes = nullptr;  // [num][W] 2-bit, N stored as 00

@@ -233,6 +233,7 @@ void run_all(spring_b200_ctx *ctx, const spring_b200_input *in, uint32_t num_cha
   st.ms_encode = ms(ctx, 3, 4); st.ms_d2h = ms(ctx, 4, 5); st.ms_total = ms(ctx, 0, 5);
   st.gpu_launches = c.launches;
   st.singletons_aligned = ctx->last_enc.singletons_aligned; st.n_reads_aligned = ctx->last_enc.n_reads_aligned;
+  st.contigs = ctx->last_enc.contigs; st.contigs_stitched = ctx->last_enc.contigs_stitched;
 }
 
 // ---- files ---------------------------------------------------------------------------------------
@@ -510,6 +511,7 @@ int spring_b200_create(int device, void *stream, spring_b200_ctx **out) {
     else { SB_CUDA(cudaStreamCreateWithFlags(&ctx->c.stream, cudaStreamNonBlocking)); ctx->c.own_stream = true; }
     for (auto &e : ctx->ev) SB_CUDA(cudaEventCreate(&e));
     if (const char *e = getenv("SPRING_B200_CHAIN_STATS")) ctx->c.chain_stats = atoi(e) != 0;  // tools: counters without an API call
+    if (const char *e = getenv("SPRING_B200_STITCH")) { const int m = atoi(e); if (m >= -1 && m <= 1) ctx->c.stitch = m; }
   } catch (const std::exception &e) {
     g_create_err = e.what();
     delete ctx;
@@ -574,6 +576,12 @@ int spring_b200_set_schedule(spring_b200_ctx *ctx, int deterministic) {
 int spring_b200_set_chain_stats(spring_b200_ctx *ctx, int on) {
   if (!ctx) return SPRING_B200_EINVAL;
   ctx->c.chain_stats = on != 0;
+  return SPRING_B200_OK;
+}
+
+int spring_b200_set_stitch(spring_b200_ctx *ctx, int mode) {
+  if (!ctx || mode < -1 || mode > 1) return SPRING_B200_EINVAL;
+  ctx->c.stitch = mode;
   return SPRING_B200_OK;
 }
 

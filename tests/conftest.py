@@ -17,5 +17,6 @@ def ctx():
     """One spring_b200 context on cuda:0 for the whole GPU session."""
     from spring_b200 import capi
     c = capi.Context(0)
+    c.set_stitch(0)  # contig stitching off: the parity tests compare the encoder with the oracle's on the same reorder stream
     yield c
     c.close()

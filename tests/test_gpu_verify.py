@@ -124,3 +124,53 @@ def test_repeat_rich_10M_verified(ctx):
     assert v["ok"] == 1 and v["reads_checked"] == 10_000_000, v
     st = ctx.stats()
     assert s.num_aligned > 0.9 * 10_000_000, (s.num_aligned, st)
+
+
+@pytest.mark.parametrize("name", ["se150", "pe100_illumina", "var250", "dups", "lowcov", "se100_n"])
+def test_stitched_contigs_decode(ctx, name):
+    """Contig stitching (spring_b200_set_stitch): contigs whose head fits into another contig's consensus are laid into it, flipped
+    when it fits reversed.  Only positions / orientations change, so every read must still decode to its original -- checked with
+    the oracle's decoder on the host and by the round trip in HBM -- and the consensus must not grow."""
+    from oracle import pyoracle as po
+    from helpers import CASES, check_roundtrip, make_input
+    from spring_b200 import dnaio
+    hp = make_input(**CASES[name])
+    try:
+        for chains in (7, 64, 300):
+            ctx.set_stitch(0)
+            plain = ctx.reorder_encode(hp.packed, hp.lengths, hp.max_readlen, hp.n_records, hp.order_n, hp.num_reads, chains)
+            ctx.set_stitch(1)
+            got = ctx.reorder_encode(hp.packed, hp.lengths, hp.max_readlen, hp.n_records, hp.order_n, hp.num_reads, chains)
+            st = ctx.stats()
+            check_roundtrip(got, hp, po.decode)
+            cp = dnaio.CompressionParams(paired_end=hp.paired, preserve_order=False, num_reads=hp.num_reads, max_readlen=hp.max_readlen,
+                                         num_reads_per_block=700)
+            v = ctx.verify_roundtrip(capi.CP.from_buffer_copy(cp.pack()))
+            assert v["ok"] == 1 and v["reads_checked"] == hp.num_reads, (name, chains, v)
+            assert st["contigs_stitched"] <= st["contigs"]
+            if name == "se150" and chains == 300:  # 8000 reads over 300 chains: most contigs abut another chain's
+                assert st["contigs_stitched"] > 0 and got.seq_len < plain.seq_len, (st["contigs_stitched"], got.seq_len, plain.seq_len)
+    finally:
+        ctx.set_stitch(0)
+
+
+def test_stitching_2M_reads_verified(ctx):
+    """2 M reads over 4736 chains (422 reads per chain: the regime where the chains' contig starts cost most): stitched, verified in HBM,
+    and the consensus shrinks towards the genome's length."""
+    from spring_b200 import dnaio, synth
+    rs = synth.generate(2_000_000, 150, genome_len=10_000_000, seed=41, sub_rate=0.005, device="cuda")
+    di = synth.to_device_input(rs)
+    n_clean = int(di.reads.shape[0])
+    inp = ctx.make_input(di.reads.data_ptr(), di.lengths.data_ptr(), n_clean, 150, di.n_records, di.order_n, rs.num_reads)
+    cp = capi.CP.from_buffer_copy(dnaio.CompressionParams(paired_end=False, preserve_order=False, num_reads=rs.num_reads, max_readlen=150).pack())
+    try:
+        lens = {}
+        for mode in (0, 1):
+            ctx.set_stitch(mode)
+            s = ctx.reorder_encode_raw(inp, 4736, device=True)
+            v = ctx.verify_roundtrip(cp)
+            assert v["ok"] == 1 and v["reads_checked"] == rs.num_reads, (mode, v)
+            lens[mode] = (int(s.seq_len), ctx.stats()["contigs_stitched"])
+        assert lens[1][1] > 0 and lens[1][0] < lens[0][0], lens
+    finally:
+        ctx.set_stitch(0)

@@ -356,45 +356,55 @@ __global__ void __launch_bounds__(kConsThreads) k_consensus(const uint64_t *__re
 // ---- contig stitching ---------------------------------------------------------------------------------------------------
 // The reference's threads seed every new contig from ONE pool of reads (reorder.h:576-592); thousands of GPU chains seed from
 // their own slices and end up with contigs that overlap their neighbours' -- every overlap is consensus stored twice (the ratio
-// cost of DESIGN.md section 6).  After the first consensus pass the contigs' own HEADS (first max_readlen bases of their
-// consensus) are treated like singleton reads: the same sweep that re-aligns singletons (k_align_singletons) finds, for every
-// head, the first place in ANOTHER contig's consensus where it fits; the contig is then laid into that contig's coordinates
-// (flipped if its head fits reversed), chains of such links are followed to their root, and the consensus is rebuilt once over
-// the merged layout.  Only read positions / orientations change: the streams stay decodable by construction.
-constexpr int kThreshStitch = 8;  // mismatches allowed between a contig's head and the consensus it is laid into
-__global__ void k_contig_heads(const uint64_t *__restrict__ cons2, const unsigned long long *__restrict__ cstart,
-                               const unsigned long long *__restrict__ clen, uint32_t nc, int W, int L, uint64_t *head_codes,
-                               uint16_t *head_len, uint32_t *head_ncount) {
+// cost of DESIGN.md section 6).  After the first consensus pass the contigs' own ENDS (the first and the last kStitchLen bases of
+// their consensus) are treated like singleton reads: the same sweep that re-aligns singletons (k_align_singletons, with windows
+// of kStitchLen bases) finds, for every end, the first place in ANOTHER contig's consensus where it fits; the contig is then laid
+// into that contig's coordinates (flipped if its end fits reversed), chains of such links are followed to their root, and the
+// consensus is rebuilt once over the merged layout.  Only read positions / orientations change: the streams stay decodable by construction.
+constexpr int kThreshStitch = 4;  // mismatches allowed between a contig's end and the consensus it is laid into
+constexpr int kStitchLen = 64;    // bases of a contig's head / tail that are searched: chains stop extending a contig when no unclaimed
+                                  // read overlaps its end by max_readlen / 2 or more, so neighbouring contigs overlap by at least about
+                                  // that much -- rarely by a whole read
+// pseudo-read 2c = head of contig c (its first el consensus bases), 2c + 1 = its tail (the last el), el = min(length, Ls)
+__global__ void k_contig_ends(const uint64_t *__restrict__ cons2, const unsigned long long *__restrict__ cstart,
+                              const unsigned long long *__restrict__ clen, uint32_t nc, int W, int Ls, uint64_t *end_codes,
+                              uint16_t *end_len, uint32_t *end_ncount) {
   const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const uint32_t c = (uint32_t)(t / W);
-  if (c >= nc) return;
-  const int w = (int)(t - (uint64_t)c * W);
-  const int hl = (int)(clen[c] < (unsigned long long)L ? clen[c] : (unsigned long long)L);
+  const uint32_t r = (uint32_t)(t / W);
+  if (r >= 2 * nc) return;
+  const uint32_t c = r >> 1;
+  const int w = (int)(t - (uint64_t)r * W);
+  const int el = (int)(clen[c] < (unsigned long long)Ls ? clen[c] : (unsigned long long)Ls);
+  const uint64_t from = (r & 1) ? cstart[c] + clen[c] - (unsigned long long)el : cstart[c];
   uint64_t v = 0;
-  if (32 * w < hl) {
-    v = cons_bits(cons2, cstart[c] + 32ull * w);
-    const int rem = hl - 32 * w;
+  if (32 * w < el) {
+    v = cons_bits(cons2, from + 32ull * w);
+    const int rem = el - 32 * w;
     if (rem < 32) v &= (1ull << (2 * rem)) - 1ull;
   }
-  head_codes[t] = v;
-  if (w == 0) { head_len[c] = (uint16_t)hl; head_ncount[c] = 0; }
+  end_codes[t] = v;
+  if (w == 0) { end_len[r] = (uint16_t)el; end_ncount[r] = 0; }
 }
-// best[c] = first window (position, strand, dictionary) another contig's consensus offers to contig c's head -> parent[c] and
-// the map x -> a + sgn * x from c's coordinates into the parent's (forward: the head sits at the window's start; reversed: base x
-// of the head faces consensus base j + L - 1 - x, k_align_singletons' convention)
-__global__ void k_stitch_links(const unsigned long long *__restrict__ best, const unsigned long long *__restrict__ cstart, uint32_t nc, int L,
-                               uint32_t *parent, long long *ta, int8_t *ts) {
+// best[2c], best[2c + 1] = first window (position, strand, dictionary) ANOTHER contig's consensus offers to contig c's head /
+// tail -> parent[c] (the head's offer if there is one, else the tail's) and the map x -> a + sgn * x from c's coordinates into the
+// parent's.  The end sits at c's coordinates [e0, e0 + el); forward it lies at the window's start (x -> ja + x - e0), reversed base
+// b of the end faces consensus base j + Ls - 1 - b (k_align_singletons' convention: x -> ja + Ls - 1 + e0 - x).
+__global__ void k_stitch_links(const unsigned long long *__restrict__ best, const unsigned long long *__restrict__ cstart,
+                               const unsigned long long *__restrict__ clen, uint32_t nc, int Ls, uint32_t *parent, long long *ta, int8_t *ts) {
   const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= nc) return;
-  const unsigned long long pr = best[c];
   uint32_t p = c;
   long long a = 0;
   int8_t sg = 1;
-  if (pr != kNoPrio) {
+  for (int end = 0; end < 2 && p == c; end++) {
+    const unsigned long long pr = best[2 * c + end];
+    if (pr == kNoPrio) continue;
     const uint64_t j = pr >> 2;
     p = upper_bound_u64(reinterpret_cast<const uint64_t *>(cstart), nc + 1, j) - 1;
     const long long ja = (long long)(j - cstart[p]);
-    if ((pr >> 1) & 1) { a = ja + L - 1; sg = -1; } else { a = ja; }
+    const long long el = (long long)(clen[c] < (unsigned long long)Ls ? clen[c] : (unsigned long long)Ls);
+    const long long e0 = end ? (long long)clen[c] - el : 0;
+    if ((pr >> 1) & 1) { a = ja + Ls - 1 + e0; sg = -1; } else { a = ja - e0; sg = 1; }
   }
   parent[c] = p; ta[c] = a; ts[c] = sg;
 }
@@ -464,7 +474,7 @@ struct AlignArgs {
   unsigned long long *best;
   const uint32_t *tile_contig;  // contig holding column 256 * t (k_tile_contigs)
   int thresh;                   // Hamming threshold (THRESH_ENCODER for the singleton sweep)
-  int stitch;                   // the "reads" are the contigs' own heads (read r = head of contig r): a contig does not take its own head
+  int stitch;                   // the "reads" are the contigs' own ends (read 2c / 2c + 1 = head / tail of contig c): a contig does not take its own
 };
 // contig of the first column of every 256-column block: thread per contig, each writes the block starts
 // that fall inside it (contigs tile the consensus, so every block start has exactly one owner)
@@ -522,7 +532,7 @@ __global__ void k_align_singletons(AlignArgs a) {
       const uint64_t x0 = rev ? j + (uint64_t)(L - len) : j;
       int h = (int)a.pool_ncount[rid];
       const int nw = (len + 31) >> 5;
-      if (a.stitch && rid == lo) continue;
+      if (a.stitch && (rid >> 1) == lo) continue;
       for (int i = 0; i < nw && h <= a.thresh; i++) {
         const uint64_t o = oriented_word(r, W, len, rev != 0, i);
         const int rem = len - 32 * i;
@@ -814,28 +824,30 @@ void run_encode(Ctx &c, const uint64_t *reads, const uint16_t *lens, uint32_t n,
   };
   layout_and_consensus(cidx1, ro.pos, ro.rev);
 
-  // ---- contig stitching (see k_contig_heads) ------------------------------------------------------------------------------
+  // ---- contig stitching (see k_contig_ends) ------------------------------------------------------------------------------
   // On when asked for, or -- by default -- when the chains are so many for the input that their contig starts cost more than ~1 %
   // of the read streams (64 * chains / reads): free-running schedule only (the deterministic one is compared
   // with the oracle bit for bit).
   out.contigs = NC; out.contigs_stitched = 0;
   const bool stitch = c.stitch == 1 || (c.stitch < 0 && !c.lockstep && ro.num_chains > 1 && (uint64_t)n < 6400ull * ro.num_chains);
-  if (stitch && NC > 1 && (int64_t)seq_len >= L) {
-    uint64_t *head_codes = c.pool.dev<uint64_t>("st.head_codes", (size_t)NC * W);
-    uint16_t *head_len = c.pool.dev<uint16_t>("st.head_len", NC);
-    uint32_t *head_ncount = c.pool.dev<uint32_t>("st.head_ncount", NC);
-    unsigned long long *sbest = c.pool.dev<unsigned long long>("st.best", NC);
-    k_contig_heads<<<grid_for((uint64_t)NC * W, 256), 256, 0, st>>>(cons2, cstart, clen, NC, W, L, head_codes, head_len, head_ncount);
-    k_fill_u64<<<grid_for(NC, 256), 256, 0, st>>>(sbest, NC, kNoPrio);
+  if (stitch && NC > 1 && NC < (1u << 30) && (int64_t)seq_len >= L) {
+    const int Ls = std::min(L, kStitchLen);
+    const uint32_t NE = 2 * NC;
+    uint64_t *end_codes = c.pool.dev<uint64_t>("st.end_codes", (size_t)NE * W);
+    uint16_t *end_len = c.pool.dev<uint16_t>("st.end_len", NE);
+    uint32_t *end_ncount = c.pool.dev<uint32_t>("st.end_ncount", NE);
+    unsigned long long *sbest = c.pool.dev<unsigned long long>("st.best", NE);
+    k_contig_ends<<<grid_for((uint64_t)NE * W, 256), 256, 0, st>>>(cons2, cstart, clen, NC, W, Ls, end_codes, end_len, end_ncount);
+    k_fill_u64<<<grid_for(NE, 256), 256, 0, st>>>(sbest, NE, kNoPrio);
     DictBuild sd[2];
     int es[2], ee[2];
-    encoder_windows(L, es, ee);
-    build_dictionary(c, head_codes, head_len, nullptr, NC, W, es[0], ee[0], "st.dict0", sd[0]);
-    build_dictionary(c, head_codes, head_len, nullptr, NC, W, es[1], ee[1], "st.dict1", sd[1]);
+    encoder_windows(Ls, es, ee);
+    build_dictionary(c, end_codes, end_len, nullptr, NE, W, es[0], ee[0], "st.dict0", sd[0]);
+    build_dictionary(c, end_codes, end_len, nullptr, NE, W, es[1], ee[1], "st.dict1", sd[1]);
     AlignArgs sa{};
     sa.cons2 = cons2; sa.seq_len = seq_len; sa.cstart = cstart; sa.num_contigs = NC;
     sa.dict[0] = sd[0].view; sa.dict[1] = sd[1].view;
-    sa.pool_codes = head_codes; sa.pool_len = head_len; sa.pool_ncount = head_ncount; sa.W = W; sa.L = L; sa.best = sbest;
+    sa.pool_codes = end_codes; sa.pool_len = end_len; sa.pool_ncount = end_ncount; sa.W = W; sa.L = Ls; sa.best = sbest;
     sa.tile_contig = tile_contig; sa.thresh = kThreshStitch; sa.stitch = 1;
     k_align_singletons<<<grid_for(seq_len, 256), 256, 0, st>>>(sa);
     uint32_t *par_a = c.pool.dev<uint32_t>("st.par_a", NC), *par_b = c.pool.dev<uint32_t>("st.par_b", NC);
@@ -843,7 +855,7 @@ void run_encode(Ctx &c, const uint64_t *reads, const uint16_t *lens, uint32_t n,
     int8_t *ts_a = c.pool.dev<int8_t>("st.ts_a", NC), *ts_b = c.pool.dev<int8_t>("st.ts_b", NC);
     uint8_t *drop = c.pool.dev<uint8_t>("st.drop", NC);
     uint32_t *d_linked = c.pool.dev<uint32_t>("st.linked", 1);
-    k_stitch_links<<<grid_for(NC, 256), 256, 0, st>>>(sbest, cstart, NC, L, par_a, ta_a, ts_a);
+    k_stitch_links<<<grid_for(NC, 256), 256, 0, st>>>(sbest, cstart, clen, NC, Ls, par_a, ta_a, ts_a);
     k_stitch_break2<<<grid_for(NC, 256), 256, 0, st>>>(par_a, NC, drop);
     k_stitch_unlink<<<grid_for(NC, 256), 256, 0, st>>>(drop, NC, par_a, ta_a, ts_a);
     c.launches += 6;

@@ -20,6 +20,8 @@ if "--policy" in sys.argv:  # chain-count policies: reads per chain of the auto 
                                               for r in (256, 2048, 6400)]
 if "--stitch" in sys.argv:  # contig stitching in the encoder (spring_b200_set_stitch) off / on at the default chain count
     runs = [("reference", po.REF_BIN, {})] + [(f"b200 stitch {m}", po.SPLICE2_BIN, {"SPRING_B200_STITCH": str(m)}) for m in (0, 1)]
+    if "--all-chains" in sys.argv:  # every co-resident chain whatever the input size (256 reads per chain: round 1's rule), stitched or not
+        runs = [("reference", po.REF_BIN, {})] + [(f"b200 256 reads/chain stitch {m}", po.SPLICE2_BIN, {"SPRING_B200_STITCH": str(m), "SPRING_B200_READS_PER_CHAIN": "256"}) for m in (0, 1)]
 if "--gpus" in sys.argv:  # ratio drift of the multi-GPU partitioning: the spliced binary on 1, 2, ... GPUs of this box
     import torch
     counts = [g for g in (1, 2, 4, 8) if g <= torch.cuda.device_count()]

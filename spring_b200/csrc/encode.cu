@@ -473,8 +473,6 @@ struct AlignArgs {
   int W, L;
   unsigned long long *best;
   const uint32_t *tile_contig;  // contig holding column 256 * t (k_tile_contigs)
-  int thresh;                   // Hamming threshold (THRESH_ENCODER for the singleton sweep)
-  int stitch;                   // the "reads" are the contigs' own ends (read 2c / 2c + 1 = head / tail of contig c): a contig does not take its own
 };
 // contig of the first column of every 256-column block: thread per contig, each writes the block starts
 // that fall inside it (contigs tile the consensus, so every block start has exactly one owner)
@@ -484,7 +482,11 @@ __global__ void k_tile_contigs(const unsigned long long *__restrict__ cstart, ui
   const unsigned long long b = cstart[c], e = cstart[c + 1];
   for (unsigned long long t = (b + 255) / 256; t * 256 < e; t++) tile_contig[t] = c;
 }
+// STITCH: the "reads" are contig ends (contig stitching): threshold kThreshStitch, a contig does not take its own ends.  A template
+// parameter, not a field: the singleton sweep is issue-bound and a run-time threshold / extra test in its inner loop cost it 25 %.
+template <bool STITCH>
 __global__ void k_align_singletons(AlignArgs a) {
+  constexpr int kThresh = STITCH ? kThreshStitch : kThreshEncoder;
   const uint64_t j0 = (uint64_t)blockIdx.x * blockDim.x, j = j0 + threadIdx.x;
   // contig of the block's first column from the table; each thread then walks forward the few contigs
   // a 256-column block can span
@@ -532,14 +534,14 @@ __global__ void k_align_singletons(AlignArgs a) {
       const uint64_t x0 = rev ? j + (uint64_t)(L - len) : j;
       int h = (int)a.pool_ncount[rid];
       const int nw = (len + 31) >> 5;
-      if (a.stitch && (rid >> 1) == lo) continue;
-      for (int i = 0; i < nw && h <= a.thresh; i++) {
+      if (STITCH && (rid >> 1) == lo) continue;
+      for (int i = 0; i < nw && h <= kThresh; i++) {
         const uint64_t o = oriented_word(r, W, len, rev != 0, i);
         const int rem = len - 32 * i;
         const uint64_t lm = rem >= 32 ? ~0ull : (1ull << (2 * rem)) - 1ull;
         h += __popcll((o ^ cons_bits(a.cons2, x0 + 32ull * i)) & lm);
       }
-      if (h <= a.thresh) atomicMin(a.best + rid, prio);
+      if (h <= kThresh) atomicMin(a.best + rid, prio);
     }
   }
 }
@@ -848,8 +850,8 @@ void run_encode(Ctx &c, const uint64_t *reads, const uint16_t *lens, uint32_t n,
     sa.cons2 = cons2; sa.seq_len = seq_len; sa.cstart = cstart; sa.num_contigs = NC;
     sa.dict[0] = sd[0].view; sa.dict[1] = sd[1].view;
     sa.pool_codes = end_codes; sa.pool_len = end_len; sa.pool_ncount = end_ncount; sa.W = W; sa.L = Ls; sa.best = sbest;
-    sa.tile_contig = tile_contig; sa.thresh = kThreshStitch; sa.stitch = 1;
-    k_align_singletons<<<grid_for(seq_len, 256), 256, 0, st>>>(sa);
+    sa.tile_contig = tile_contig;
+    k_align_singletons<true><<<grid_for(seq_len, 256), 256, 0, st>>>(sa);
     uint32_t *par_a = c.pool.dev<uint32_t>("st.par_a", NC), *par_b = c.pool.dev<uint32_t>("st.par_b", NC);
     long long *ta_a = c.pool.dev<long long>("st.ta_a", NC), *ta_b = c.pool.dev<long long>("st.ta_b", NC);
     int8_t *ts_a = c.pool.dev<int8_t>("st.ts_a", NC), *ts_b = c.pool.dev<int8_t>("st.ts_b", NC);
@@ -901,8 +903,8 @@ void run_encode(Ctx &c, const uint64_t *reads, const uint16_t *lens, uint32_t n,
       aa.cons2 = cons2; aa.seq_len = seq_len; aa.cstart = cstart; aa.num_contigs = NC;
       aa.dict[0] = ed[0].view; aa.dict[1] = ed[1].view;
       aa.pool_codes = pool_codes; aa.pool_len = pool_len; aa.pool_ncount = pool_ncount; aa.W = W; aa.L = L; aa.best = best;
-      aa.tile_contig = tile_contig; aa.thresh = kThreshEncoder; aa.stitch = 0;
-      k_align_singletons<<<grid_for(seq_len, 256), 256, 0, st>>>(aa);
+      aa.tile_contig = tile_contig;
+      k_align_singletons<false><<<grid_for(seq_len, 256), 256, 0, st>>>(aa);
       c.launches++;
     }
     uint8_t *fl_a = c.pool.dev<uint8_t>("en.fl_a", Pn), *fl_u = c.pool.dev<uint8_t>("en.fl_u", Pn);

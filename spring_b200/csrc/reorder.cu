@@ -27,9 +27,16 @@
 //     result is a pure function of (input, num_chains) and is restated exactly by oracle/spring_oracle.c,
 //     which for one chain is the reference's single-thread execution.
 //
-// Memory traffic per claimed read (L = 150): ~39 filter words (L2), ~7.5 slot sectors, one or two 40-byte
-// candidate rows + their claim words, 17 B of records; all other state stays in shared memory / registers
-// for the life of the kernel (DESIGN.md sections 5, 6).
+// Two instantiations of the free-running kernel: the production one has the lookup / compare counters and the tuning
+// knobs compiled out (no spills at 64 registers); the counting one (spring_b200_set_chain_stats, and always the
+// deterministic schedule) counts what the oracle counts.  What the kernel is sensitive to, in this order (measured,
+// profiles/r02_chains2_experiment.txt): registers and code size, serialised dependent loads, instruction count --
+// not DRAM traffic.  Hence: once-per-contig state in shared memory, the probe loop not unrolled, filter words of
+// multi-probe batches requested four at a time, the count pass as straight-line code.
+//
+// Memory traffic per claimed read (L = 150): ~39 filter words (L2 while the filters fit it), ~3 slot sectors, one or
+// two 40-byte candidate rows + their claim words, one 16-byte record; all other state stays in shared memory /
+// registers for the life of the kernel (DESIGN.md sections 5, 6).
 #include <algorithm>
 #include <cub/cub.cuh>
 #include "chain_common.cuh"

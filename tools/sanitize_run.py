@@ -15,6 +15,9 @@ for name in (sys.argv[1:] or ("se100_n", "var64_noisy", "long511", "heavy_bins",
         for chains in (1, 16):
             s = ctx.reorder_encode(hp.packed, hp.lengths, hp.max_readlen, hp.n_records, hp.order_n, hp.num_reads, chains)
     ctx.set_schedule(False)
+    for mode in (1, 0):  # contig stitching on (the stitch kernels and the second layout pass), then off for the re-blocking checks below
+        ctx.set_stitch(mode)
+        s = ctx.reorder_encode(hp.packed, hp.lengths, hp.max_readlen, hp.n_records, hp.order_n, hp.num_reads, 16)
     paired = hp.paired
     for preserve, block in ((False, 700), (True, 256000)):
         cp = capi.CP.from_buffer_copy(dnaio.CompressionParams(paired_end=paired, preserve_order=preserve, num_reads=hp.num_reads,
